@@ -1,0 +1,290 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into, imported by or called from the
+ * product path (livevisionkit_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may use it, and only as the checker / the CPU baseline.
+ *
+ * Scalar float32 CPU restatement of LiveVisionKit's FSR-EASU remap kernels
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:55-73   (APrxLo* bit-trick approximations)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:98-126  (easu_tap)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:131-176 (easu_accumulate)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:181-318 (easu)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:362-403 (easu_remap, per-pixel offset map)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:407-452 (easu_remap_homography)
+ * and of the host side that launches them
+ *   LiveVisionKit/Functions/Image.cpp:28-81, 85-151.
+ *
+ * Semantics chosen where OpenCL leaves latitude (the reference has no OpenCL-independent
+ * definition): IEEE float32, NO fused multiply-add (compile with -ffp-contract=off),
+ * native_recip(x) := 1.0f/x, convert_*_rtz/convert_uchar := C truncation.
+ * Parity status: UNPINNED by the reference (it ships no test vectors and no OpenCL device
+ * exists in the build container); pinned only against itself via tests/golden.
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -pthread -shared -fPIC).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <pthread.h>
+#include <unistd.h>
+
+/* Row-parallel driver (no OpenMP runtime in this image): splits [0, rows) over `threads` pthreads. */
+typedef void (*row_fn)(int y0, int y1, void* ctx);
+typedef struct { row_fn fn; void* ctx; int y0, y1; } row_job;
+static void* row_trampoline(void* p) { row_job* j = (row_job*)p; j->fn(j->y0, j->y1, j->ctx); return 0; }
+static void parallel_rows(row_fn fn, void* ctx, int rows, int threads)
+{
+    if (threads <= 0) threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (threads > 256) threads = 256;
+    if (threads > rows) threads = rows;
+    if (threads <= 1) { fn(0, rows, ctx); return; }
+    pthread_t tid[256];
+    row_job jobs[256];
+    for (int t = 0; t < threads; t++)
+    {
+        jobs[t].fn = fn; jobs[t].ctx = ctx;
+        jobs[t].y0 = (int)((long long)rows * t / threads);
+        jobs[t].y1 = (int)((long long)rows * (t + 1) / threads);
+        pthread_create(&tid[t], 0, row_trampoline, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(tid[t], 0);
+}
+
+static inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* FSR.cl:60,65 */
+static inline float aprx_lo_rsq(float a) { return as_float(0x5f347d74u - (as_uint(a) >> 1)); }
+static inline float aprx_lo_rcp(float a) { return as_float(0x7ef07ebbu - as_uint(a)); }
+
+static inline float fmax_cl(float a, float b) { return (a < b) ? b : a; } /* OpenCL max(): y if x<y */
+static inline float fmin_cl(float a, float b) { return (b < a) ? b : a; } /* OpenCL min(): y if y<x */
+static inline float saturate(float x) { return fmaxf(0.0f, fminf(1.0f, x)); } /* FSR.cl:79 */
+
+/* FSR.cl:98-126 */
+static inline void easu_tap(float aC[3], float* aW, float offx, float offy, float dirx, float diry,
+                            float lenx, float leny, float lob, float clp, const float c[3])
+{
+    float vx = (offx * dirx) + (offy * diry);
+    float vy = (offx * (-diry)) + (offy * dirx);
+    vx *= lenx;
+    vy *= leny;
+    float d2 = fmin_cl(vx * vx + vy * vy, clp);
+    float wA = lob * d2 - 1.0f;
+    float wB = (2.0f / 5.0f) * d2 - 1.0f;
+    wA *= wA;
+    wB = (25.0f / 16.0f) * (wB * wB) - (25.0f / 16.0f - 1.0f);
+    float w = wB * wA;
+    aC[0] += c[0] * w;
+    aC[1] += c[1] * w;
+    aC[2] += c[2] * w;
+    *aW += w;
+}
+
+/* FSR.cl:131-176. corner: 0=S 1=T 2=U 3=V */
+static inline void easu_accumulate(float dir[2], float* len, float ppx, float ppy, int corner,
+                                   float lA, float lB, float lC, float lD, float lE)
+{
+    float w = 0.0f;
+    if (corner == 3) w = ppx * ppy;
+    if (corner == 2) w = (1.0f - ppx) * ppy;
+    if (corner == 1) w = ppx * (1.0f - ppy);
+    if (corner == 0) w = (1.0f - ppx) * (1.0f - ppy);
+
+    float dc = lD - lC;
+    float cb = lC - lB;
+    float lenX = aprx_lo_rcp(fmax_cl(fabsf(dc), fabsf(cb)));
+    float dirX = lD - lB;
+    dir[0] += dirX * w;
+    lenX = saturate(fabsf(dirX) * lenX);
+    lenX *= lenX;
+    *len += lenX * w;
+
+    float ec = lE - lC;
+    float ca = lC - lA;
+    float lenY = aprx_lo_rcp(fmax_cl(fabsf(ec), fabsf(ca)));
+    float dirY = lE - lA;
+    dir[1] += dirY * w;
+    lenY = saturate(fabsf(dirY) * lenY);
+    lenY *= lenY;
+    *len += lenY * w;
+}
+
+/* FSR.cl:181-318.  src points at pixel (0,0); step in bytes; (sx,sy) = 'f'. yuv selects the
+ * YUV_INPUT build (Image.cpp:100-113 defines it iff src.format == YUV).  Note the #ifndef at
+ * FSR.cl:229 is inverted relative to its comments: WITHOUT YUV_INPUT luma = channel 0, WITH
+ * YUV_INPUT luma = 0.5*ch2 + (0.5*ch0 + ch1).  Reproduced as written. */
+static inline void easu(const uint8_t* src, int step, int sx, int sy, float ppx, float ppy, int yuv,
+                        uint8_t out[3])
+{
+    const float norm = 0.00392156862f;
+    const uint8_t* r0 = src + (size_t)(sy - 1) * step + 3 * sx;
+    const uint8_t* r1 = r0 + step - 3;
+    const uint8_t* r2 = r1 + step;
+    const uint8_t* r3 = r0 + 3 * (size_t)step;
+
+    float b[3], c[3], e[3], f[3], g[3], h[3], i[3], j[3], k[3], l[3], n[3], o[3];
+    for (int ch = 0; ch < 3; ch++)
+    {
+        b[ch] = (float)r0[ch] * norm;     c[ch] = (float)r0[3 + ch] * norm;
+        e[ch] = (float)r1[ch] * norm;     f[ch] = (float)r1[3 + ch] * norm;
+        g[ch] = (float)r1[6 + ch] * norm; h[ch] = (float)r1[9 + ch] * norm;
+        i[ch] = (float)r2[ch] * norm;     j[ch] = (float)r2[3 + ch] * norm;
+        k[ch] = (float)r2[6 + ch] * norm; l[ch] = (float)r2[9 + ch] * norm;
+        n[ch] = (float)r3[ch] * norm;     o[ch] = (float)r3[3 + ch] * norm;
+    }
+
+#define LUMA(p) (yuv ? ((p)[2] * 0.5f + ((p)[0] * 0.5f + (p)[1])) : (p)[0])
+    const float bL = LUMA(b), cL = LUMA(c), eL = LUMA(e), fL = LUMA(f), gL = LUMA(g), hL = LUMA(h);
+    const float iL = LUMA(i), jL = LUMA(j), kL = LUMA(k), lL = LUMA(l), nL = LUMA(n), oL = LUMA(o);
+#undef LUMA
+
+    float len = 0.0f, dir[2] = {0.0f, 0.0f};
+    easu_accumulate(dir, &len, ppx, ppy, 0, bL, eL, fL, gL, jL);
+    easu_accumulate(dir, &len, ppx, ppy, 1, cL, fL, gL, hL, kL);
+    easu_accumulate(dir, &len, ppx, ppy, 2, fL, iL, jL, kL, nL);
+    easu_accumulate(dir, &len, ppx, ppy, 3, gL, jL, kL, lL, oL);
+
+    float dir2x = dir[0] * dir[0], dir2y = dir[1] * dir[1];
+    float dirR = dir2x + dir2y;
+    int zro = dirR < (1.0f / 32768.0f);
+    dirR = aprx_lo_rsq(dirR);
+    dirR = zro ? 1.0f : dirR;
+    dir[0] = zro ? 1.0f : dir[0];
+    dir[0] *= dirR;
+    dir[1] *= dirR;
+
+    len = len * 0.5f;
+    len *= len;
+
+    float stretch = (dir[0] * dir[0] + dir[1] * dir[1]) * aprx_lo_rcp(fmax_cl(fabsf(dir[0]), fabsf(dir[1])));
+    float len2x = 1.0f + (stretch - 1.0f) * len;
+    float len2y = 1.0f + -0.5f * len;
+    float lob = 0.5f + ((1.0f / 4.0f - 0.04f) - 0.5f) * len;
+    float clp = aprx_lo_rcp(lob);
+
+    float mi4[3], ma4[3];
+    for (int ch = 0; ch < 3; ch++)
+    {
+        mi4[ch] = fmin_cl(f[ch], fmin_cl(g[ch], fmin_cl(j[ch], k[ch])));
+        ma4[ch] = fmax_cl(f[ch], fmax_cl(g[ch], fmax_cl(j[ch], k[ch])));
+    }
+
+    float aC[3] = {0.0f, 0.0f, 0.0f}, aW = 0.0f;
+    easu_tap(aC, &aW, 0.0f - ppx, -1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, b);
+    easu_tap(aC, &aW, 1.0f - ppx, -1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, c);
+    easu_tap(aC, &aW, -1.0f - ppx, 1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, i);
+    easu_tap(aC, &aW, 0.0f - ppx, 1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, j);
+    easu_tap(aC, &aW, 0.0f - ppx, 0.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, f);
+    easu_tap(aC, &aW, -1.0f - ppx, 0.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, e);
+    easu_tap(aC, &aW, 1.0f - ppx, 1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, k);
+    easu_tap(aC, &aW, 2.0f - ppx, 1.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, l);
+    easu_tap(aC, &aW, 2.0f - ppx, 0.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, h);
+    easu_tap(aC, &aW, 1.0f - ppx, 0.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, g);
+    easu_tap(aC, &aW, 0.0f - ppx, 2.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, n);
+    easu_tap(aC, &aW, 1.0f - ppx, 2.0f - ppy, dir[0], dir[1], len2x, len2y, lob, clp, o);
+
+    float rcpW = 1.0f / aW; /* native_recip */
+    for (int ch = 0; ch < 3; ch++)
+    {
+        float v = fmin_cl(ma4[ch], fmax_cl(mi4[ch], aC[ch] * rcpW));
+        out[ch] = (uint8_t)(int)(v * 255.0f); /* convert_uchar3: truncation */
+    }
+}
+
+/* Shared tail of both remap kernels, FSR.cl:383-402 / 432-451. */
+static inline void remap_pixel(const uint8_t* src, int src_step, int src_rows, int src_cols, uint8_t* dst_px,
+                               float subx, float suby, const uint8_t bg[3], int yuv)
+{
+    int sx = (int)subx; /* convert_int2_rtz */
+    int sy = (int)suby;
+    subx -= floorf(subx);
+    suby -= floorf(suby);
+
+    if (sx < 1 || sy < 1 || sx >= src_cols - 4 || sy >= src_rows - 4)
+    {
+        if (sx >= 0 && sx < src_cols && sy >= 0 && sy < src_rows)
+        {
+            const uint8_t* p = src + (size_t)sy * src_step + 3 * sx;
+            dst_px[0] = p[0]; dst_px[1] = p[1]; dst_px[2] = p[2];
+        }
+        else
+        {
+            dst_px[0] = bg[0]; dst_px[1] = bg[1]; dst_px[2] = bg[2];
+        }
+        return;
+    }
+    easu(src, src_step, sx, sy, subx, suby, yuv, dst_px);
+}
+
+/* FSR.cl:407-452 + Image.cpp:85-151.  t = already-inverted (dst->src) homography, row-major,
+ * given in double and narrowed to float exactly as cv::Vec4f(t.at<double>(..)) does. */
+typedef struct
+{
+    const uint8_t* src; int src_step, rows, cols; uint8_t* dst; int dst_step;
+    float r[9]; const uint8_t* bg; int yuv;
+} homog_ctx;
+
+static void homog_rows(int y0, int y1, void* p)
+{
+    const homog_ctx* c = (const homog_ctx*)p;
+    const float r1x = c->r[0], r1y = c->r[1], r1z = c->r[2];
+    const float r2x = c->r[3], r2y = c->r[4], r2z = c->r[5];
+    const float r3x = c->r[6], r3y = c->r[7], r3z = c->r[8];
+    for (int y = y0; y < y1; y++)
+    {
+        for (int x = 0; x < c->cols; x++)
+        {
+            float fx = (float)x, fy = (float)y;
+            float dz = 1.0f / (r3x * fx + r3y * fy + r3z);
+            float offx = (r1x * fx + r1y * fy + r1z) * dz - fx;
+            float offy = (r2x * fx + r2y * fy + r2z) * dz - fy;
+            float subx = (float)x + offx;
+            float suby = (float)y + offy;
+            remap_pixel(c->src, c->src_step, c->rows, c->cols, c->dst + (size_t)y * c->dst_step + 3 * x, subx, suby,
+                        c->bg, c->yuv);
+        }
+    }
+}
+
+void oracle_easu_remap_homography(const uint8_t* src, int src_step, int rows, int cols, uint8_t* dst, int dst_step,
+                                  const double t[9], const uint8_t bg[3], int yuv, int threads)
+{
+    homog_ctx c = {src, src_step, rows, cols, dst, dst_step, {0}, bg, yuv};
+    for (int k = 0; k < 9; k++) c.r[k] = (float)t[k];
+    parallel_rows(homog_rows, &c, rows, threads);
+}
+
+/* FSR.cl:362-403 + Image.cpp:28-81.  map = CV_32FC2 per-pixel offsets (pixels), map_step in bytes.
+ * dst has the size of the map (map_rows x map_cols). */
+typedef struct
+{
+    const uint8_t* src; int src_step, src_rows, src_cols; uint8_t* dst; int dst_step;
+    const float* map; int map_step, map_cols; const uint8_t* bg; int yuv;
+} map_ctx;
+
+static void map_rows_fn(int y0, int y1, void* p)
+{
+    const map_ctx* c = (const map_ctx*)p;
+    for (int y = y0; y < y1; y++)
+    {
+        const float* mrow = (const float*)((const uint8_t*)c->map + (size_t)y * c->map_step);
+        for (int x = 0; x < c->map_cols; x++)
+        {
+            float subx = (float)x + mrow[2 * x];
+            float suby = (float)y + mrow[2 * x + 1];
+            remap_pixel(c->src, c->src_step, c->src_rows, c->src_cols, c->dst + (size_t)y * c->dst_step + 3 * x,
+                        subx, suby, c->bg, c->yuv);
+        }
+    }
+}
+
+void oracle_easu_remap_map(const uint8_t* src, int src_step, int src_rows, int src_cols, uint8_t* dst, int dst_step,
+                           const float* map, int map_step, int map_rows, int map_cols, const uint8_t bg[3], int yuv,
+                           int threads)
+{
+    map_ctx c = {src, src_step, src_rows, src_cols, dst, dst_step, map, map_step, map_cols, bg, yuv};
+    parallel_rows(map_rows_fn, &c, map_rows, threads);
+}
+
+int oracle_max_threads(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
