@@ -1,0 +1,246 @@
+/*
+ * lvkb200 — C-ABI of the B200-native LiveVisionKit stabilization path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/OpenCV types.  Each entry
+ * point cites the reference interface it replaces (paths relative to /root/reference/LiveVisionKit).
+ * The C++ mirror of the reference API (lvk::VideoFilter / lvk::StabilizationFilter, same names and
+ * settings structs) that forwards to these calls lives in livevisionkit_b200/compat/ ;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - All functions return lvkb200_status; nothing throws across the boundary.  The compat layer
+ *     converts non-OK into lvk::context::assert_handler calls (Directives.hpp:37-44).
+ *   - A lvkb200_stream is one video stream == one lvk::StabilizationFilter instance: it owns one CUDA
+ *     stream, the device-resident frame ring, the tracker state and all scratch.  It is externally
+ *     synchronised (one caller thread at a time, like the reference, Filters/VideoFilter.cpp:108-152);
+ *     distinct handles are fully concurrent.
+ *   - Frames are packed 8-bit, 3 channels (the only layout that reaches lvk::remap, Functions/Image.cpp:32,96),
+ *     addressed by pointer + pitch (bytes) either in host memory (pinned recommended) or device memory.
+ *   - There is NO CPU fallback: every call needs a CUDA device and fails with LVKB200_ERR_NO_DEVICE /
+ *     LVKB200_ERR_CUDA otherwise.
+ */
+#ifndef LVKB200_H
+#define LVKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVKB200_ABI_VERSION 1
+
+typedef enum lvkb200_status
+{
+    LVKB200_OK = 0,
+    LVKB200_ERR_INVALID = 1,   /* bad argument / failed reference precondition (LVK_ASSERT equivalent) */
+    LVKB200_ERR_CUDA = 2,      /* a CUDA call failed; see lvkb200_last_error() */
+    LVKB200_ERR_NO_DEVICE = 3, /* no usable CUDA device */
+    LVKB200_ERR_NO_MODEL = 4,  /* motion estimator found no model (reference: empty cv::Mat -> LVK_ASSERT, Math/Homography.cpp:89-95) */
+    LVKB200_ERR_CAPACITY = 5   /* caller buffer too small */
+} lvkb200_status;
+
+/* lvk::VideoFrame::Format — Data/VideoFrame.hpp:27 (same numbering). */
+typedef enum lvkb200_format
+{
+    LVKB200_BGR = 0, LVKB200_BGRA = 1, LVKB200_RGB = 2, LVKB200_RGBA = 3, LVKB200_YUV = 4, LVKB200_GRAY = 5,
+    LVKB200_UNKNOWN = 6
+} lvkb200_format;
+
+typedef enum lvkb200_memspace { LVKB200_MEM_HOST = 0, LVKB200_MEM_DEVICE = 1 } lvkb200_memspace;
+
+/* Flat POD mirror of lvk::StabilizationFilterSettings and its bases:
+ *   FeatureDetectorSettings  Vision/FeatureDetector.hpp:28-37
+ *   FrameTrackerSettings     Vision/FrameTracker.hpp:31-44
+ *   PathSmootherSettings     Vision/PathSmoother.hpp:29-39
+ *   StabilizationFilterSettings  Filters/StabilizationFilter.hpp:28-39
+ * Field names and defaults are the reference's.  The three motion_resolution fields of the reference's
+ * multiple-inheritance struct are linked by configure() (StabilizationFilter.cpp:57-58) and are one field here. */
+typedef struct lvkb200_settings
+{
+    int32_t detection_resolution_width, detection_resolution_height; /* {256,256} */
+    int32_t detection_regions_width, detection_regions_height;       /* {2,2} */
+    int32_t force_detection;                                         /* false */
+    float max_feature_density;                                       /* 0.20 */
+    float min_feature_density;                                       /* 0.05 */
+    float accumulation_rate;                                         /* 2.0 */
+
+    int32_t motion_resolution_width, motion_resolution_height; /* {2,2} (StabilizationFilterSettings) */
+    int32_t track_local_motions;                               /* true */
+    float temporal_smoothing;                                  /* 1.0 */
+    float local_smoothing;                                     /* 20.0 */
+    uint64_t min_motion_samples;                               /* 75 */
+    float acceptance_threshold;                                /* 8.0 */
+    float uniformity_threshold;                                /* 0.20 */
+
+    uint64_t predictive_samples;                          /* 10 */
+    float corrective_limits_width, corrective_limits_height; /* {0.1,0.1} */
+    float smoothing_steps;                                /* 20.0 */
+    float response_rate;                                  /* 0.04 */
+
+    double background_colour[4]; /* cv::Scalar {255,0,255,0}, in frame channel order */
+    int32_t crop_to_stable_region; /* false */
+    int32_t stabilize_output;      /* true */
+    float min_scene_quality;       /* 0.8 */
+    float min_tracking_quality;    /* 0.3 */
+} lvkb200_settings;
+
+/* Per-submit result (replaces the out-parameter VideoFrame's emptiness/timestamp/format plus
+ * FrameTracker::tracking_stability(), Vision/FrameTracker.hpp:56). */
+typedef struct lvkb200_result
+{
+    int32_t has_output;          /* 0 <=> the reference released `output` (StabilizationFilter.cpp:94,134) */
+    uint64_t out_timestamp;      /* timestamp of the (delayed) frame written to `out` (WarpMesh.cpp:221) */
+    int32_t out_format;          /* its lvkb200_format (WarpMesh.cpp:222) */
+    float tracking_stability;    /* inlier ratio of this frame's motion estimate */
+    float scene_quality;         /* m_SceneQuality */
+    float trust_factor;          /* m_TrustFactor */
+    int32_t feature_count;       /* features alive after propagate() */
+    int32_t has_motion;          /* 0 <=> FrameTracker::track returned nullopt */
+} lvkb200_result;
+
+typedef struct lvkb200_keypoint
+{
+    float x, y;        /* cv::KeyPoint::pt */
+    float response;    /* FAST corner score */
+    int32_t class_id;  /* LVK borrows it as the feature age (FrameTracker.cpp:188) */
+} lvkb200_keypoint;
+
+typedef struct lvkb200_stream lvkb200_stream;
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+
+int lvkb200_abi_version(void);
+int lvkb200_device_count(void);                 /* 0 when no CUDA device/driver is usable */
+const char* lvkb200_last_error(void);           /* thread-local description of the last non-OK status */
+const char* lvkb200_status_string(lvkb200_status s);
+
+/* lvk::context::assert_handler — Directives.hpp:37-44, Directives.cpp:27-42.  NULL restores the default
+ * (which only records the message; it never aborts inside the library). */
+typedef void (*lvkb200_assert_handler)(const char* file, const char* function, const char* assertion);
+void lvkb200_set_assert_handler(lvkb200_assert_handler handler);
+
+/* StabilizationFilterSettings{} defaults / the OBS "Homography" preset (Modules/OBS-Plugin/Sources/
+ * Stabilisation/VSFilter.cpp:269-280) that north_star names (FAST grid -> LK -> homography RANSAC). */
+void lvkb200_settings_default(lvkb200_settings* s);
+void lvkb200_settings_obs_homography(lvkb200_settings* s);
+
+/* ---- lvk::StabilizationFilter ------------------------------------------------------------------------------- */
+
+/* StabilizationFilter::StabilizationFilter(settings) — Filters/StabilizationFilter.cpp:34-38. */
+lvkb200_status lvkb200_stream_create(int device, const lvkb200_settings* settings, lvkb200_stream** out);
+void lvkb200_stream_destroy(lvkb200_stream* s);
+
+/* StabilizationFilter::configure — StabilizationFilter.cpp:42-65. */
+lvkb200_status lvkb200_stream_configure(lvkb200_stream* s, const lvkb200_settings* settings);
+lvkb200_status lvkb200_stream_get_settings(const lvkb200_stream* s, lvkb200_settings* out);
+/* restart() :139-144, reset_context() :155-159, ready() :148-151, frame_delay() :192-195, stable_region() :199-. */
+lvkb200_status lvkb200_stream_restart(lvkb200_stream* s);
+lvkb200_status lvkb200_stream_reset_context(lvkb200_stream* s);
+int lvkb200_stream_ready(const lvkb200_stream* s);
+uint64_t lvkb200_stream_frame_delay(const lvkb200_stream* s);
+lvkb200_status lvkb200_stream_stable_region(const lvkb200_stream* s, int frame_width, int frame_height,
+                                            int* x, int* y, int* width, int* height);
+
+/* VideoFilter::apply(VideoFrame&& input, VideoFrame& output, profile) -> StabilizationFilter::filter
+ * (Filters/VideoFilter.cpp:46-58, Filters/StabilizationFilter.cpp:69-135).
+ * The input frame is copied into the stream's device ring before the call returns (the caller keeps its
+ * buffer; the reference moves it into m_FrameQueue).  `out` may alias `frame` (OBS calls
+ * apply(std::move(frame), frame), VSFilter.cpp:358).  When res->has_output == 0 `out` is untouched.
+ * With out_space == HOST the call returns after the output has landed in `out`; with DEVICE it returns
+ * once all work is enqueued on the stream's CUDA stream (call lvkb200_stream_sync, the equivalent of
+ * Stopwatch::sync_gpu / cv::ocl::finish, Timing/Stopwatch.cpp:127-131, before reading it). */
+lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                     lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
+                                     void* out, size_t out_pitch, lvkb200_memspace out_space, lvkb200_result* res);
+lvkb200_status lvkb200_stream_sync(lvkb200_stream* s);
+
+/* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
+ * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for
+ * the later one.  The per-stage analogue of Stopwatch (Timing/Stopwatch.cpp:42-64) for the bench harness. */
+#define LVKB200_EVENT_SLOTS 16
+lvkb200_status lvkb200_stream_event_record(lvkb200_stream* s, int index);
+lvkb200_status lvkb200_stream_event_elapsed_ms(lvkb200_stream* s, int start_index, int stop_index, float* ms);
+
+/* Debug / parity taps on the last submitted frame (what OBS "test mode" draws, StabilizationFilter.cpp:163-188,
+ * and what the parity tests compare against the oracle).  `which`: */
+typedef enum lvkb200_debug_item
+{
+    LVKB200_DBG_DETECTION_IMAGE = 0, /* uint8 det_w*det_h: m_CurrentFrame after resize (FrameTracker.cpp:117) */
+    LVKB200_DBG_DETECTED = 1,        /* lvkb200_keypoint[]: FeatureDetector::detect output (FeatureDetector.cpp:170) */
+    LVKB200_DBG_LK_MATCHED = 2,      /* float2[]: m_MatchedPoints before filtering (FrameTracker.cpp:140-146) */
+    LVKB200_DBG_LK_STATUS = 3,       /* uint8[]: m_MatchStatus */
+    LVKB200_DBG_TRACKED = 4,         /* float2[]: m_TrackedPoints after fast_filter (:149) */
+    LVKB200_DBG_MATCHED = 5,         /* float2[]: m_MatchedPoints after fast_filter */
+    LVKB200_DBG_INLIERS = 6,         /* uint8[]: m_InlierStatus */
+    LVKB200_DBG_HOMOGRAPHY = 7,      /* double[9]: estimated frame-to-frame homography (global-motion path) */
+    LVKB200_DBG_MOTION = 8,          /* float[rows*cols*2]: motion mesh before the trust factor */
+    LVKB200_DBG_CORRECTION = 9,      /* float[rows*cols*2]: PathSmoother::next result (+ scene crop if enabled) */
+    LVKB200_DBG_WARP_TRANSFORM = 10, /* double[9]: dst->src transform handed to the remap (WarpMesh.cpp:214) */
+    LVKB200_DBG_PROPAGATED = 11,     /* lvkb200_keypoint[]: m_TrackedFeatures after propagate (:183-193) */
+    LVKB200_DBG_FAST_COUNTS = 12     /* int32[regions]: raw FAST keypoints per region this frame, -1 = region skipped */
+} lvkb200_debug_item;
+/* Copies up to `capacity` bytes; *size receives the full size in bytes (0 if the item was not produced). */
+lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item which, void* buffer,
+                                          size_t capacity, size_t* size);
+
+/* Per-stage device time of the last submit, in microseconds (CUDA events): the per-stage analogue of
+ * VideoFilter::timings() (Filters/VideoFilter.hpp:58).  Stage order: ingest, pyramid, fast, lk, estimate, remap. */
+#define LVKB200_STAGE_COUNT 6
+lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB200_STAGE_COUNT]);
+
+/* ---- stage-level entry points (used by the parity tests: oracle inputs -> one GPU stage) --------------------- */
+
+/* lvk::remap(src, dst, homography, background, inverted=true) + easu_remap_homography
+ * (Functions/Image.cpp:85-151, Functions/OpenCL/Sources/FSR.cl:407-452).  t_inv: row-major dst->src 3x3. */
+lvkb200_status lvkb200_remap_homography(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                        lvkb200_memspace src_space, void* dst, size_t dst_pitch,
+                                        lvkb200_memspace dst_space, const double t_inv[9],
+                                        const uint8_t background[3], int yuv_input);
+
+/* WarpMesh::apply for meshes larger than 2x2 + lvk::remap(src, dst, offset_map, bg) + easu_remap
+ * (Math/WarpMesh.cpp:187-192, Image.cpp:28-81, FSR.cl:362-403).  offsets: rows*cols float2, normalized. */
+lvkb200_status lvkb200_remap_mesh(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                  lvkb200_memspace src_space, void* dst, size_t dst_pitch, lvkb200_memspace dst_space,
+                                  const float* offsets, int mesh_cols, int mesh_rows, const uint8_t background[3],
+                                  int yuv_input);
+
+/* WarpMesh::apply (both branches) — Math/WarpMesh.cpp:183-223. */
+lvkb200_status lvkb200_warp_mesh_apply(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                       lvkb200_memspace src_space, void* dst, size_t dst_pitch,
+                                       lvkb200_memspace dst_space, const float* offsets, int mesh_cols, int mesh_rows,
+                                       const uint8_t background[3], int yuv_input, double t_inv_out[9]);
+
+/* VideoFrame::viewAsFormat(GRAY) + cv::resize(INTER_AREA) (Data/VideoFrame.cpp:187-317,
+ * Vision/FrameTracker.cpp:117), fused.  det_out: host buffer det_w*det_h bytes. */
+lvkb200_status lvkb200_detection_image(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                       lvkb200_format format, lvkb200_memspace space, uint8_t* det_out, int det_w,
+                                       int det_h);
+
+/* cv::FastFeatureDetector(threshold, nonmax=true, TYPE_9_16)::detect(image(roi)) as called at
+ * Vision/FeatureDetector.cpp:130-134.  image: host uint8 width*height; keypoints are ROI-relative, in OpenCV's
+ * (y,x) emission order. */
+lvkb200_status lvkb200_fast_detect(lvkb200_stream* s, const uint8_t* image, int width, int height, int roi_x,
+                                   int roi_y, int roi_w, int roi_h, int threshold, lvkb200_keypoint* keypoints,
+                                   int capacity, int* count);
+
+/* cv::SparsePyrLKOpticalFlow((11,11), 3, {COUNT+EPS,5,0.01})::calc as configured at
+ * Vision/FrameTracker.cpp:41-48 and called at :140-146.  Host buffers. */
+lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const uint8_t* next, int width, int height,
+                                const float* points, int count, float* matched, uint8_t* status);
+
+/* FrameTracker::estimate_global_motion's cv::findHomography(..., UsacParams) (Vision/FrameTracker.cpp:337-359).
+ * Host buffers; h_out row-major 3x3 (h33 == 1); mask[i] = 1 <=> reprojection error < threshold. */
+lvkb200_status lvkb200_find_homography(lvkb200_stream* s, const float* src_points, const float* dst_points,
+                                       int count, float threshold, double h_out[9], uint8_t* mask);
+
+/* FrameTracker::estimate_local_motions (Vision/FrameTracker.cpp:200-321): least-squares motion mesh.
+ * mesh_state: in/out m_OptimizedMesh (2*cols*rows floats); offsets_out rows*cols float2; mask per point. */
+lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream* s, const float* tracked, const float* matched,
+                                              int count, float* mesh_state, float* offsets_out, uint8_t* mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVKB200_H */

@@ -1,0 +1,351 @@
+"""
+livevisionkit_b200 — B200-native LiveVisionKit stabilization path.
+
+Python mirror of the reference's filter interface for this path (lvk::VideoFilter::apply /
+lvk::StabilizationFilter, LiveVisionKit/Filters/{VideoFilter,StabilizationFilter}.hpp) on top of the C-ABI
+in include/lvkb200.h.  All compute happens in liblvkb200.so (hand-written CUDA, sm_100a); this module only
+marshals pointers.  There is no CPU fallback: importing works without a GPU (so the ABI can be checked),
+but creating a filter requires a CUDA device and a built library.
+
+Frames are HxWx3 uint8, either numpy arrays (host memory) or torch CUDA tensors (device memory, used in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import (BGR, BGRA, GRAY, RGB, RGBA, UNKNOWN, YUV, LvkB200Error, STAGE_NAMES)  # noqa: F401
+
+__all__ = ["StabilizationFilterSettings", "StabilizationFilter", "VideoFrame", "Stream", "BGR", "RGB", "YUV",
+           "LvkB200Error", "device_count"]
+
+
+def device_count() -> int:
+    return _capi.load().lvkb200_device_count()
+
+
+@dataclass
+class StabilizationFilterSettings:
+    """lvk::StabilizationFilterSettings (+ bases); field names and defaults are the reference's
+    (Filters/StabilizationFilter.hpp:28-39, Vision/FrameTracker.hpp:31-44, Vision/FeatureDetector.hpp:28-37,
+    Vision/PathSmoother.hpp:29-39).  Sizes are (width, height)."""
+    detection_resolution: tuple = (256, 256)
+    detection_regions: tuple = (2, 2)
+    force_detection: bool = False
+    max_feature_density: float = 0.20
+    min_feature_density: float = 0.05
+    accumulation_rate: float = 2.0
+    motion_resolution: tuple = (2, 2)
+    track_local_motions: bool = True
+    temporal_smoothing: float = 1.0
+    local_smoothing: float = 20.0
+    min_motion_samples: int = 75
+    acceptance_threshold: float = 8.0
+    uniformity_threshold: float = 0.20
+    predictive_samples: int = 10
+    corrective_limits: tuple = (0.1, 0.1)
+    smoothing_steps: float = 20.0
+    response_rate: float = 0.04
+    background_colour: tuple = (255, 0, 255)
+    crop_to_stable_region: bool = False
+    stabilize_output: bool = True
+    min_scene_quality: float = 0.8
+    min_tracking_quality: float = 0.3
+
+    @staticmethod
+    def obs_homography_preset() -> "StabilizationFilterSettings":
+        """OBS 'Homography' preset — Modules/OBS-Plugin/Sources/Stabilisation/VSFilter.cpp:269-280."""
+        return StabilizationFilterSettings(detection_resolution=(480, 270), detection_regions=(2, 1),
+                                           max_feature_density=0.12, min_feature_density=0.04, accumulation_rate=3.0,
+                                           track_local_motions=False, acceptance_threshold=3.0)
+
+    def to_c(self) -> _capi.Settings:
+        s = _capi.Settings()
+        s.detection_resolution_width, s.detection_resolution_height = self.detection_resolution
+        s.detection_regions_width, s.detection_regions_height = self.detection_regions
+        s.force_detection = int(self.force_detection)
+        s.max_feature_density = self.max_feature_density
+        s.min_feature_density = self.min_feature_density
+        s.accumulation_rate = self.accumulation_rate
+        s.motion_resolution_width, s.motion_resolution_height = self.motion_resolution
+        s.track_local_motions = int(self.track_local_motions)
+        s.temporal_smoothing = self.temporal_smoothing
+        s.local_smoothing = self.local_smoothing
+        s.min_motion_samples = self.min_motion_samples
+        s.acceptance_threshold = self.acceptance_threshold
+        s.uniformity_threshold = self.uniformity_threshold
+        s.predictive_samples = self.predictive_samples
+        s.corrective_limits_width, s.corrective_limits_height = self.corrective_limits
+        s.smoothing_steps = self.smoothing_steps
+        s.response_rate = self.response_rate
+        bg = list(self.background_colour) + [0.0] * (4 - len(self.background_colour))
+        for i in range(4):
+            s.background_colour[i] = float(bg[i])
+        s.crop_to_stable_region = int(self.crop_to_stable_region)
+        s.stabilize_output = int(self.stabilize_output)
+        s.min_scene_quality = self.min_scene_quality
+        s.min_tracking_quality = self.min_tracking_quality
+        return s
+
+
+@dataclass
+class VideoFrame:
+    """lvk::VideoFrame (Data/VideoFrame.hpp:25-31): pixel buffer + timestamp + format."""
+    data: object = None
+    timestamp: int = 0
+    format: int = BGR
+
+    def empty(self) -> bool:
+        return self.data is None
+
+
+def _buffer_info(buf):
+    """-> (pointer, pitch_bytes, height, width, channels, memspace)."""
+    if isinstance(buf, np.ndarray):
+        if buf.dtype != np.uint8 or buf.ndim not in (2, 3) or not buf.flags["C_CONTIGUOUS"] and buf.strides[-1] != 1:
+            raise ValueError("frames must be uint8 HxW[xC] arrays with contiguous rows")
+        ch = 1 if buf.ndim == 2 else buf.shape[2]
+        if buf.ndim == 3 and buf.strides[1] != ch:
+            raise ValueError("pixels must be packed")
+        return buf.ctypes.data, buf.strides[0], buf.shape[0], buf.shape[1], ch, _capi.MEM_HOST
+    if hasattr(buf, "data_ptr") and hasattr(buf, "is_cuda"):  # torch tensor (plumbing only)
+        if str(buf.dtype) != "torch.uint8" or buf.dim() not in (2, 3):
+            raise ValueError("frames must be uint8 HxW[xC] tensors")
+        ch = 1 if buf.dim() == 2 else buf.shape[2]
+        if buf.stride(-1) != 1 or (buf.dim() == 3 and buf.stride(1) != ch):
+            raise ValueError("pixels must be packed")
+        space = _capi.MEM_DEVICE if buf.is_cuda else _capi.MEM_HOST
+        return buf.data_ptr(), buf.stride(0), buf.shape[0], buf.shape[1], ch, space
+    raise TypeError(f"unsupported frame buffer type {type(buf)}")
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Stream:
+    """Thin object wrapper over a lvkb200_stream handle (one video stream / one CUDA stream)."""
+
+    def __init__(self, settings: StabilizationFilterSettings | None = None, device: int = 0):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        cs = (settings or StabilizationFilterSettings()).to_c()
+        _capi.check(self._lib.lvkb200_stream_create(device, C.byref(cs), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.lvkb200_stream_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- filter-level
+    def configure(self, settings: StabilizationFilterSettings):
+        cs = settings.to_c()
+        _capi.check(self._lib.lvkb200_stream_configure(self._h, C.byref(cs)))
+
+    def restart(self):
+        _capi.check(self._lib.lvkb200_stream_restart(self._h))
+
+    def reset_context(self):
+        _capi.check(self._lib.lvkb200_stream_reset_context(self._h))
+
+    def ready(self) -> bool:
+        return bool(self._lib.lvkb200_stream_ready(self._h))
+
+    def frame_delay(self) -> int:
+        return int(self._lib.lvkb200_stream_frame_delay(self._h))
+
+    def stable_region(self, width: int, height: int):
+        x, y, w, h = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _capi.check(self._lib.lvkb200_stream_stable_region(self._h, width, height, C.byref(x), C.byref(y), C.byref(w),
+                                                           C.byref(h)))
+        return x.value, y.value, w.value, h.value
+
+    def sync(self):
+        _capi.check(self._lib.lvkb200_stream_sync(self._h))
+
+    def submit(self, frame, out, fmt: int = BGR, timestamp: int = 0) -> _capi.Result:
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        optr, opitch, oh, ow, och, ospace = _buffer_info(out)
+        if (oh, ow, och) != (h, w, ch):
+            raise ValueError("output buffer must match the input frame")
+        res = _capi.Result()
+        _capi.check(self._lib.lvkb200_stream_submit(self._h, ptr, pitch, w, h, fmt, timestamp, space, optr, opitch,
+                                                    ospace, C.byref(res)))
+        return res
+
+    def event_record(self, index: int):
+        _capi.check(self._lib.lvkb200_stream_event_record(self._h, index))
+
+    def event_elapsed_ms(self, start: int, stop: int) -> float:
+        ms = C.c_float(0)
+        _capi.check(self._lib.lvkb200_stream_event_elapsed_ms(self._h, start, stop, C.byref(ms)))
+        return float(ms.value)
+
+    def stage_times_us(self) -> dict:
+        t = (C.c_float * _capi.STAGE_COUNT)()
+        _capi.check(self._lib.lvkb200_stream_stage_times_us(self._h, t))
+        return dict(zip(STAGE_NAMES, [float(v) for v in t]))
+
+    def debug_fetch(self, which: int, dtype, shape_tail=()):
+        size = C.c_size_t(0)
+        _capi.check(self._lib.lvkb200_stream_debug_fetch(self._h, which, None, 0, C.byref(size)))
+        if size.value == 0:
+            return None
+        raw = np.empty(size.value, dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_stream_debug_fetch(self._h, which, raw.ctypes.data, raw.nbytes, C.byref(size)))
+        arr = raw.view(dtype)
+        return arr.reshape((-1,) + tuple(shape_tail)) if shape_tail else arr
+
+    # ---- stage-level (parity tests: oracle inputs -> one GPU stage)
+    def remap_homography(self, src, t_inv, background=(255, 0, 255), yuv: bool = False, out=None):
+        ptr, pitch, h, w, ch, space = _buffer_info(src)
+        if ch != 3:
+            raise ValueError("remap needs 8UC3 frames")  # Image.cpp:96
+        if out is None:
+            out = np.empty((h, w, 3), dtype=np.uint8)
+        optr, opitch, _, _, _, ospace = _buffer_info(out)
+        t = np.ascontiguousarray(t_inv, dtype=np.float64).reshape(9)
+        bg = (C.c_uint8 * 3)(*[int(v) & 255 for v in background[:3]])
+        _capi.check(self._lib.lvkb200_remap_homography(self._h, ptr, pitch, w, h, space, optr, opitch, ospace,
+                                                       t.ctypes.data_as(C.POINTER(C.c_double)), bg, int(yuv)))
+        return out
+
+    def remap_mesh(self, src, offsets, background=(255, 0, 255), yuv: bool = False, out=None):
+        ptr, pitch, h, w, ch, space = _buffer_info(src)
+        if out is None:
+            out = np.empty((h, w, 3), dtype=np.uint8)
+        optr, opitch, _, _, _, ospace = _buffer_info(out)
+        m = _f32(offsets)
+        rows, cols = m.shape[:2]
+        bg = (C.c_uint8 * 3)(*[int(v) & 255 for v in background[:3]])
+        _capi.check(self._lib.lvkb200_remap_mesh(self._h, ptr, pitch, w, h, space, optr, opitch, ospace,
+                                                 m.ctypes.data_as(C.POINTER(C.c_float)), cols, rows, bg, int(yuv)))
+        return out
+
+    def warp_mesh_apply(self, src, offsets, background=(255, 0, 255), yuv: bool = False, out=None):
+        """WarpMesh::apply.  Returns (out, t_inv) — t_inv is the dst->src transform of the 2x2 branch."""
+        ptr, pitch, h, w, ch, space = _buffer_info(src)
+        if out is None:
+            out = np.empty((h, w, 3), dtype=np.uint8)
+        optr, opitch, _, _, _, ospace = _buffer_info(out)
+        m = _f32(offsets)
+        rows, cols = m.shape[:2]
+        t = np.zeros(9, dtype=np.float64)
+        bg = (C.c_uint8 * 3)(*[int(v) & 255 for v in background[:3]])
+        _capi.check(self._lib.lvkb200_warp_mesh_apply(self._h, ptr, pitch, w, h, space, optr, opitch, ospace,
+                                                      m.ctypes.data_as(C.POINTER(C.c_float)), cols, rows, bg,
+                                                      int(yuv), t.ctypes.data_as(C.POINTER(C.c_double))))
+        return out, t.reshape(3, 3)
+
+    def detection_image(self, frame, fmt: int, det_res):
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        det = np.empty((det_res[1], det_res[0]), dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_detection_image(self._h, ptr, pitch, w, h, fmt, space,
+                                                      det.ctypes.data_as(C.POINTER(C.c_uint8)), det_res[0],
+                                                      det_res[1]))
+        return det
+
+    def fast_detect(self, image: np.ndarray, roi, threshold: int, capacity: int = 1 << 16):
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        kps = (_capi.KeyPoint * capacity)()
+        n = C.c_int(0)
+        _capi.check(self._lib.lvkb200_fast_detect(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[1],
+                                                  img.shape[0], roi[0], roi[1], roi[2], roi[3], int(threshold), kps,
+                                                  capacity, C.byref(n)))
+        arr = np.frombuffer(kps, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("response", "f4"), ("class_id", "i4")]),
+                            count=n.value)
+        return arr.copy()
+
+    def lk_track(self, prev: np.ndarray, nxt: np.ndarray, points):
+        p = np.ascontiguousarray(prev, dtype=np.uint8)
+        q = np.ascontiguousarray(nxt, dtype=np.uint8)
+        pts = _f32(points, (-1, 2))
+        n = pts.shape[0]
+        matched = np.empty((n, 2), dtype=np.float32)
+        status = np.empty(n, dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_lk_track(self._h, p.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                               q.ctypes.data_as(C.POINTER(C.c_uint8)), p.shape[1], p.shape[0],
+                                               pts.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                               matched.ctypes.data_as(C.POINTER(C.c_float)),
+                                               status.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return matched, status
+
+    def find_homography(self, src_points, dst_points, threshold: float):
+        a, b = _f32(src_points, (-1, 2)), _f32(dst_points, (-1, 2))
+        n = a.shape[0]
+        H = np.zeros(9, dtype=np.float64)
+        mask = np.zeros(n, dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_find_homography(self._h, a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      b.ctypes.data_as(C.POINTER(C.c_float)), n, float(threshold),
+                                                      H.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      mask.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return H.reshape(3, 3), mask
+
+    def estimate_local_motions(self, tracked, matched, mesh_state):
+        a, b = _f32(tracked, (-1, 2)), _f32(matched, (-1, 2))
+        n = a.shape[0]
+        state = _f32(mesh_state).copy()
+        offsets = np.zeros_like(state)
+        mask = np.zeros(n, dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_estimate_local_motions(self._h, a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                             b.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                                             state.ctypes.data_as(C.POINTER(C.c_float)),
+                                                             offsets.ctypes.data_as(C.POINTER(C.c_float)),
+                                                             mask.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return state, offsets, mask
+
+
+class StabilizationFilter:
+    """lvk::StabilizationFilter behind lvk::VideoFilter::apply (Filters/StabilizationFilter.hpp:42-63,
+    Filters/VideoFilter.hpp:32-61).  apply() returns a VideoFrame whose .data is None while the look-ahead
+    queue fills (the reference releases `output`), otherwise the stabilized, delayed frame."""
+
+    def __init__(self, settings: StabilizationFilterSettings | None = None, device: int = 0):
+        self._settings = settings or StabilizationFilterSettings()
+        self.stream = Stream(self._settings, device)
+        self.alias = "Stabilization Filter"
+        self.last_result = None
+
+    def settings(self) -> StabilizationFilterSettings:
+        return self._settings
+
+    def configure(self, settings: StabilizationFilterSettings):
+        self.stream.configure(settings)
+        self._settings = settings
+
+    def restart(self):
+        self.stream.restart()
+
+    def reset_context(self):
+        self.stream.reset_context()
+
+    def ready(self) -> bool:
+        return self.stream.ready()
+
+    def frame_delay(self) -> int:
+        return self.stream.frame_delay()
+
+    def stable_region(self, width: int, height: int):
+        return self.stream.stable_region(width, height)
+
+    def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
+        """`output`: optional preallocated buffer (numpy or CUDA tensor) receiving the result."""
+        data = frame.data
+        if output is None:
+            output = np.empty_like(data) if isinstance(data, np.ndarray) else data.new_empty(data.shape)
+        res = self.stream.submit(data, output, frame.format, frame.timestamp)
+        self.last_result = res
+        if not res.has_output:
+            return VideoFrame(None, 0, UNKNOWN)
+        return VideoFrame(output, int(res.out_timestamp), int(res.out_format))

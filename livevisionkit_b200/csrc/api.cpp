@@ -1,0 +1,320 @@
+// C-ABI implementation (include/lvkb200.h).  Host C++ only: orchestration + calls into the kernel launchers.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.hpp"
+#include "host_math.hpp"
+#include "stream_impl.hpp"
+
+namespace lvkb200
+{
+
+std::string& last_error()
+{
+    thread_local std::string err;
+    return err;
+}
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+}
+
+static lvkb200_assert_handler g_assert_handler = nullptr;
+
+void report_assert(const char* file, const char* function, const char* assertion)
+{
+    const char* base = std::strrchr(file, '/');
+    set_error("assertion failed: %s in %s (%s)", assertion, function, base ? base + 1 : file);
+    if (g_assert_handler) g_assert_handler(base ? base + 1 : file, function, assertion);
+}
+
+}  // namespace lvkb200
+
+using namespace lvkb200;
+
+extern "C" {
+
+int lvkb200_abi_version(void) { return LVKB200_ABI_VERSION; }
+
+int lvkb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* lvkb200_last_error(void) { return last_error().c_str(); }
+
+const char* lvkb200_status_string(lvkb200_status s)
+{
+    switch (s)
+    {
+        case LVKB200_OK: return "ok";
+        case LVKB200_ERR_INVALID: return "invalid argument / failed precondition";
+        case LVKB200_ERR_CUDA: return "CUDA error";
+        case LVKB200_ERR_NO_DEVICE: return "no CUDA device";
+        case LVKB200_ERR_NO_MODEL: return "no motion model";
+        case LVKB200_ERR_CAPACITY: return "buffer too small";
+    }
+    return "unknown";
+}
+
+void lvkb200_set_assert_handler(lvkb200_assert_handler handler) { g_assert_handler = handler; }
+
+void lvkb200_settings_default(lvkb200_settings* s)
+{
+    if (!s) return;
+    std::memset(s, 0, sizeof(*s));
+    // FeatureDetectorSettings — Vision/FeatureDetector.hpp:28-37
+    s->detection_resolution_width = 256; s->detection_resolution_height = 256;
+    s->detection_regions_width = 2; s->detection_regions_height = 2;
+    s->force_detection = 0;
+    s->max_feature_density = 0.20f;
+    s->min_feature_density = 0.05f;
+    s->accumulation_rate = 2.0f;
+    // FrameTrackerSettings — Vision/FrameTracker.hpp:31-44 (motion_resolution overridden by StabilizationFilterSettings)
+    s->motion_resolution_width = 2; s->motion_resolution_height = 2;
+    s->track_local_motions = 1;
+    s->temporal_smoothing = 1.0f;
+    s->local_smoothing = 20.0f;
+    s->min_motion_samples = 75;
+    s->acceptance_threshold = 8.0f;
+    s->uniformity_threshold = 0.20f;
+    // PathSmootherSettings — Vision/PathSmoother.hpp:29-39
+    s->predictive_samples = 10;
+    s->corrective_limits_width = 0.1f; s->corrective_limits_height = 0.1f;
+    s->smoothing_steps = 20.0f;
+    s->response_rate = 0.04f;
+    // StabilizationFilterSettings — Filters/StabilizationFilter.hpp:28-39
+    s->background_colour[0] = 255; s->background_colour[1] = 0; s->background_colour[2] = 255; s->background_colour[3] = 0;
+    s->crop_to_stable_region = 0;
+    s->stabilize_output = 1;
+    s->min_scene_quality = 0.8f;
+    s->min_tracking_quality = 0.3f;
+}
+
+void lvkb200_settings_obs_homography(lvkb200_settings* s)
+{
+    if (!s) return;
+    lvkb200_settings_default(s);
+    // Modules/OBS-Plugin/Sources/Stabilisation/VSFilter.cpp:269-280
+    s->detection_resolution_width = 480; s->detection_resolution_height = 270;
+    s->detection_regions_width = 2; s->detection_regions_height = 1;
+    s->max_feature_density = 0.12f;
+    s->min_feature_density = 0.04f;
+    s->accumulation_rate = 3.0f;
+    s->track_local_motions = 0;
+    s->acceptance_threshold = 3.0f;
+    s->motion_resolution_width = 2; s->motion_resolution_height = 2;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+
+lvkb200_status lvkb200_stream_create(int device, const lvkb200_settings* settings, lvkb200_stream** out)
+{
+    LVKB_REQUIRE(out != nullptr);
+    *out = nullptr;
+    int n = lvkb200_device_count();
+    if (n <= 0 || device < 0 || device >= n)
+    {
+        set_error("no usable CUDA device (requested %d, found %d) — there is no CPU fallback", device, n);
+        return LVKB200_ERR_NO_DEVICE;
+    }
+    LVKB_CUDA(cudaSetDevice(device));
+    std::unique_ptr<lvkb200_stream> s(new lvkb200_stream());
+    s->device = device;
+    LVKB_CUDA(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
+    lvkb200_settings def;
+    lvkb200_settings_default(&def);
+    LVKB_TRY(s->configure(settings ? *settings : def));
+    *out = s.release();
+    return LVKB200_OK;
+}
+
+void lvkb200_stream_destroy(lvkb200_stream* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->cs) cudaStreamSynchronize(s->cs);
+    s->release();
+    if (s->cs) cudaStreamDestroy(s->cs);
+    delete s;
+}
+
+lvkb200_status lvkb200_stream_configure(lvkb200_stream* s, const lvkb200_settings* settings)
+{
+    LVKB_REQUIRE(s != nullptr && settings != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->configure(*settings);
+}
+
+lvkb200_status lvkb200_stream_get_settings(const lvkb200_stream* s, lvkb200_settings* out)
+{
+    LVKB_REQUIRE(s != nullptr && out != nullptr);
+    *out = s->settings;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_restart(lvkb200_stream* s)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->restart();
+}
+
+lvkb200_status lvkb200_stream_reset_context(lvkb200_stream* s)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->reset_context();
+}
+
+int lvkb200_stream_ready(const lvkb200_stream* s) { return s ? (s->ready() ? 1 : 0) : 0; }
+
+uint64_t lvkb200_stream_frame_delay(const lvkb200_stream* s) { return s ? s->settings.predictive_samples : 0; }
+
+lvkb200_status lvkb200_stream_stable_region(const lvkb200_stream* s, int frame_width, int frame_height, int* x, int* y,
+                                            int* width, int* height)
+{
+    LVKB_REQUIRE(s != nullptr && x && y && width && height);
+    s->stable_region(frame_width, frame_height, x, y, width, height);
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_sync(lvkb200_stream* s)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    LVKB_CUDA(cudaStreamSynchronize(s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_event_record(lvkb200_stream* s, int index)
+{
+    LVKB_REQUIRE(s != nullptr && index >= 0 && index < LVKB200_EVENT_SLOTS);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    if (!s->user_events[index]) LVKB_CUDA(cudaEventCreate(&s->user_events[index]));
+    LVKB_CUDA(cudaEventRecord(s->user_events[index], s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_event_elapsed_ms(lvkb200_stream* s, int start_index, int stop_index, float* ms)
+{
+    LVKB_REQUIRE(s != nullptr && ms != nullptr);
+    LVKB_REQUIRE(start_index >= 0 && start_index < LVKB200_EVENT_SLOTS && stop_index >= 0 &&
+                 stop_index < LVKB200_EVENT_SLOTS);
+    LVKB_REQUIRE(s->user_events[start_index] != nullptr && s->user_events[stop_index] != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    LVKB_CUDA(cudaEventSynchronize(s->user_events[stop_index]));
+    LVKB_CUDA(cudaEventElapsedTime(ms, s->user_events[start_index], s->user_events[stop_index]));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                     lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
+                                     void* out, size_t out_pitch, lvkb200_memspace out_space, lvkb200_result* res)
+{
+    LVKB_REQUIRE(s != nullptr && frame != nullptr && res != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->submit(frame, pitch, width, height, format, timestamp, frame_space, out, out_pitch, out_space, res);
+}
+
+lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item which, void* buffer, size_t capacity,
+                                          size_t* size)
+{
+    LVKB_REQUIRE(s != nullptr && size != nullptr);
+    return s->debug_fetch(which, buffer, capacity, size);
+}
+
+lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB200_STAGE_COUNT])
+{
+    LVKB_REQUIRE(s != nullptr && times != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->stage_times(times);
+}
+
+// ---- stage-level entry points ---------------------------------------------------------------------------------------
+
+lvkb200_status lvkb200_remap_homography(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                        lvkb200_memspace src_space, void* dst, size_t dst_pitch,
+                                        lvkb200_memspace dst_space, const double t_inv[9],
+                                        const uint8_t background[3], int yuv_input)
+{
+    LVKB_REQUIRE(s != nullptr && src != nullptr && dst != nullptr && t_inv != nullptr && background != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0);  // Image.cpp:94
+    LVKB_CUDA(cudaSetDevice(s->device));
+    RemapParams p{};
+    LVKB_TRY(s->stage_frame_in(src, src_pitch, width, height, 3, src_space, &p.src, &p.src_pitch));
+    LVKB_TRY(s->stage_frame_out(dst, dst_pitch, width, height, 3, dst_space, &p.dst, &p.dst_pitch));
+    p.width = width; p.height = height; p.yuv = yuv_input != 0;
+    std::memcpy(p.bg, background, 3);
+    float t[9];
+    for (int k = 0; k < 9; k++) t[k] = static_cast<float>(t_inv[k]);  // cv::Vec4f(t.at<double>()) — Image.cpp:133-135
+    LVKB_CUDA(launch_remap_homography(s->cs, p, t));
+    return s->finish_frame_out(dst, dst_pitch, width, height, 3, dst_space);
+}
+
+lvkb200_status lvkb200_remap_mesh(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                  lvkb200_memspace src_space, void* dst, size_t dst_pitch, lvkb200_memspace dst_space,
+                                  const float* offsets, int mesh_cols, int mesh_rows, const uint8_t background[3],
+                                  int yuv_input)
+{
+    LVKB_REQUIRE(s != nullptr && src != nullptr && dst != nullptr && offsets != nullptr && background != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0 && mesh_cols >= 2 && mesh_rows >= 2);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    RemapParams p{};
+    LVKB_TRY(s->stage_frame_in(src, src_pitch, width, height, 3, src_space, &p.src, &p.src_pitch));
+    LVKB_TRY(s->stage_frame_out(dst, dst_pitch, width, height, 3, dst_space, &p.dst, &p.dst_pitch));
+    p.width = width; p.height = height; p.yuv = yuv_input != 0;
+    std::memcpy(p.bg, background, 3);
+    const float* dmesh = nullptr;
+    LVKB_TRY(s->upload_mesh(offsets, mesh_cols, mesh_rows, &dmesh));
+    LVKB_CUDA(launch_remap_mesh(s->cs, p, dmesh, mesh_cols, mesh_rows));
+    return s->finish_frame_out(dst, dst_pitch, width, height, 3, dst_space);
+}
+
+lvkb200_status lvkb200_warp_mesh_apply(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                       lvkb200_memspace src_space, void* dst, size_t dst_pitch,
+                                       lvkb200_memspace dst_space, const float* offsets, int mesh_cols, int mesh_rows,
+                                       const uint8_t background[3], int yuv_input, double t_inv_out[9])
+{
+    LVKB_REQUIRE(s != nullptr && offsets != nullptr);
+    if (mesh_cols == 2 && mesh_rows == 2)
+    {
+        double t[9];
+        LVKB_REQUIRE(mesh2x2_to_transform(offsets, width, height, t));
+        if (t_inv_out) std::memcpy(t_inv_out, t, sizeof(t));
+        return lvkb200_remap_homography(s, src, src_pitch, width, height, src_space, dst, dst_pitch, dst_space, t,
+                                        background, yuv_input);
+    }
+    if (t_inv_out) std::memset(t_inv_out, 0, 9 * sizeof(double));
+    return lvkb200_remap_mesh(s, src, src_pitch, width, height, src_space, dst, dst_pitch, dst_space, offsets,
+                              mesh_cols, mesh_rows, background, yuv_input);
+}
+
+// ---- stages still to come (declared in the header; return a clear error until implemented) ----------------------
+#define LVKB_NOT_YET(name) do { set_error(name ": not implemented yet"); return LVKB200_ERR_INVALID; } while (0)
+
+lvkb200_status lvkb200_detection_image(lvkb200_stream*, const void*, size_t, int, int, lvkb200_format, lvkb200_memspace,
+                                       uint8_t*, int, int) { LVKB_NOT_YET("lvkb200_detection_image"); }
+lvkb200_status lvkb200_fast_detect(lvkb200_stream*, const uint8_t*, int, int, int, int, int, int, int,
+                                   lvkb200_keypoint*, int, int*) { LVKB_NOT_YET("lvkb200_fast_detect"); }
+lvkb200_status lvkb200_lk_track(lvkb200_stream*, const uint8_t*, const uint8_t*, int, int, const float*, int, float*,
+                                uint8_t*) { LVKB_NOT_YET("lvkb200_lk_track"); }
+lvkb200_status lvkb200_find_homography(lvkb200_stream*, const float*, const float*, int, float, double*, uint8_t*)
+{ LVKB_NOT_YET("lvkb200_find_homography"); }
+lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream*, const float*, const float*, int, float*, float*, uint8_t*)
+{ LVKB_NOT_YET("lvkb200_estimate_local_motions"); }
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Internal helpers shared by the C-ABI implementation and the kernel launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/lvkb200.h"
+
+namespace lvkb200
+{
+
+// Thread-local last-error text behind lvkb200_last_error().
+std::string& last_error();
+void set_error(const char* fmt, ...);
+
+// Reports a failed reference precondition through the installed assert handler
+// (lvk::context::assert_handler equivalent, Directives.hpp:37-44) and records it.
+void report_assert(const char* file, const char* function, const char* assertion);
+
+#define LVKB_CUDA(call)                                                                                               \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t err__ = (call);                                                                                   \
+        if (err__ != cudaSuccess)                                                                                     \
+        {                                                                                                             \
+            ::lvkb200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__));            \
+            return LVKB200_ERR_CUDA;                                                                                  \
+        }                                                                                                             \
+    } while (0)
+
+#define LVKB_REQUIRE(cond)                                                                                            \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if (!(cond))                                                                                                  \
+        {                                                                                                             \
+            ::lvkb200::report_assert(__FILE__, __func__, #cond);                                                      \
+            return LVKB200_ERR_INVALID;                                                                               \
+        }                                                                                                             \
+    } while (0)
+
+#define LVKB_TRY(expr)                                                                                                \
+    do                                                                                                                \
+    {                                                                                                                 \
+        lvkb200_status st__ = (expr);                                                                                 \
+        if (st__ != LVKB200_OK) return st__;                                                                          \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- kernel launchers (one per reference stage) --------------------------------------------------------------------
+
+struct RemapParams
+{
+    const uint8_t* src;  // device, packed 8UC3
+    size_t src_pitch;
+    uint8_t* dst;  // device, packed 8UC3
+    size_t dst_pitch;
+    int width, height;
+    uint8_t bg[3];
+    bool yuv;
+};
+
+// easu_remap_homography (FSR.cl:407-452). t = dst->src transform narrowed to float (Image.cpp:133-135).
+cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9]);
+// easu_remap (FSR.cl:362-403) with the WarpMesh::apply upsample (WarpMesh.cpp:190-191) fused in:
+// mesh = device pointer to rows*cols float2 normalized offsets.
+cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows);
+
+}  // namespace lvkb200
