@@ -181,6 +181,9 @@ typedef enum lvkb200_debug_item
     LVKB200_DBG_PROPAGATED = 11,     /* lvkb200_keypoint[]: m_TrackedFeatures after propagate (:183-193) */
     LVKB200_DBG_FAST_COUNTS = 12     /* int32[regions]: raw FAST keypoints per region this frame, -1 = region skipped */
 } lvkb200_debug_item;
+/* Taps are only recorded while capture is enabled (it adds a device->host copy of the detection image and a
+ * synchronisation per frame, so it is off by default — the equivalent of OBS "test mode", VSFilter.cpp:356-383). */
+lvkb200_status lvkb200_stream_set_debug_capture(lvkb200_stream* s, int enable);
 /* Copies up to `capacity` bytes; *size receives the full size in bytes (0 if the item was not produced). */
 lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item which, void* buffer,
                                           size_t capacity, size_t* size);

@@ -197,6 +197,9 @@ class Stream:
         _capi.check(self._lib.lvkb200_stream_stage_times_us(self._h, t))
         return dict(zip(STAGE_NAMES, [float(v) for v in t]))
 
+    def set_debug_capture(self, enable: bool = True):
+        _capi.check(self._lib.lvkb200_stream_set_debug_capture(self._h, int(enable)))
+
     def debug_fetch(self, which: int, dtype, shape_tail=()):
         size = C.c_size_t(0)
         _capi.check(self._lib.lvkb200_stream_debug_fetch(self._h, which, None, 0, C.byref(size)))

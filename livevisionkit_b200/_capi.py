@@ -73,6 +73,7 @@ SYMBOLS = {
     "lvkb200_stream_sync": (C.c_int, [_vp]),
     "lvkb200_stream_event_record": (C.c_int, [_vp, _i]),
     "lvkb200_stream_event_elapsed_ms": (C.c_int, [_vp, _i, _i, _fp]),
+    "lvkb200_stream_set_debug_capture": (C.c_int, [_vp, _i]),
     "lvkb200_stream_debug_fetch": (C.c_int, [_vp, _i, _vp, _sz, C.POINTER(_sz)]),
     "lvkb200_stream_stage_times_us": (C.c_int, [_vp, _fp]),
     "lvkb200_remap_homography": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _dp, _u8p, _i]),

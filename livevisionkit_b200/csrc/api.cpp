@@ -303,18 +303,155 @@ lvkb200_status lvkb200_warp_mesh_apply(lvkb200_stream* s, const void* src, size_
                               mesh_cols, mesh_rows, background, yuv_input);
 }
 
-// ---- stages still to come (declared in the header; return a clear error until implemented) ----------------------
-#define LVKB_NOT_YET(name) do { set_error(name ": not implemented yet"); return LVKB200_ERR_INVALID; } while (0)
+// ---- remaining stage-level entry points ------------------------------------------------------------------------------
 
-lvkb200_status lvkb200_detection_image(lvkb200_stream*, const void*, size_t, int, int, lvkb200_format, lvkb200_memspace,
-                                       uint8_t*, int, int) { LVKB_NOT_YET("lvkb200_detection_image"); }
-lvkb200_status lvkb200_fast_detect(lvkb200_stream*, const uint8_t*, int, int, int, int, int, int, int,
-                                   lvkb200_keypoint*, int, int*) { LVKB_NOT_YET("lvkb200_fast_detect"); }
-lvkb200_status lvkb200_lk_track(lvkb200_stream*, const uint8_t*, const uint8_t*, int, int, const float*, int, float*,
-                                uint8_t*) { LVKB_NOT_YET("lvkb200_lk_track"); }
-lvkb200_status lvkb200_find_homography(lvkb200_stream*, const float*, const float*, int, float, double*, uint8_t*)
-{ LVKB_NOT_YET("lvkb200_find_homography"); }
-lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream*, const float*, const float*, int, float*, float*, uint8_t*)
-{ LVKB_NOT_YET("lvkb200_estimate_local_motions"); }
+lvkb200_status lvkb200_stream_set_debug_capture(lvkb200_stream* s, int enable)
+{
+    LVKB_REQUIRE(s != nullptr);
+    s->debug_capture = enable != 0;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_detection_image(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                       lvkb200_format format, lvkb200_memspace space, uint8_t* det_out, int det_w,
+                                       int det_h)
+{
+    LVKB_REQUIRE(s != nullptr && frame != nullptr && det_out != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0 && det_w > 0 && det_h > 0);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const int ch = (format == LVKB200_GRAY) ? 1 : ((format == LVKB200_BGRA || format == LVKB200_RGBA) ? 4 : 3);
+    const uint8_t* dsrc = nullptr;
+    size_t dpitch = 0;
+    LVKB_TRY(s->stage_frame_in(frame, pitch, width, height, ch, space, &dsrc, &dpitch));
+    IngestPlan plan;  // stage-level calls use a private plan so the stream's own geometry cache is untouched
+    lvkb200_status st = plan.prepare(width, height, det_w, det_h, s->cs);
+    DeviceBuffer ddet;
+    PinnedBuffer hdet;
+    const size_t det_pitch = (static_cast<size_t>(det_w) + 15) / 16 * 16;
+    if (st == LVKB200_OK && ddet.ensure(det_pitch * det_h) != cudaSuccess) st = LVKB200_ERR_CUDA;
+    if (st == LVKB200_OK && hdet.ensure(static_cast<size_t>(det_w) * det_h) != cudaSuccess) st = LVKB200_ERR_CUDA;
+    if (st == LVKB200_OK) st = plan.launch(s->cs, dsrc, dpitch, format, ddet.as<uint8_t>(), det_pitch);
+    if (st == LVKB200_OK)
+    {
+        cudaError_t e = cudaMemcpy2DAsync(hdet.ptr, det_w, ddet.ptr, det_pitch, det_w, det_h, cudaMemcpyDeviceToHost, s->cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->cs);
+        if (e != cudaSuccess) { set_error("detection_image: %s", cudaGetErrorString(e)); st = LVKB200_ERR_CUDA; }
+        else std::memcpy(det_out, hdet.ptr, static_cast<size_t>(det_w) * det_h);
+    }
+    cudaStreamSynchronize(s->cs);
+    plan.release(); ddet.release(); hdet.release();
+    return st;
+}
+
+// Uploads a host gray image into a temporary device buffer (pitch aligned to 16).
+static lvkb200_status upload_gray(lvkb200_stream* s, const uint8_t* img, int w, int h, DeviceBuffer& buf, size_t* pitch)
+{
+    *pitch = (static_cast<size_t>(w) + 15) / 16 * 16;
+    LVKB_CUDA(buf.ensure(*pitch * h));
+    LVKB_CUDA(cudaMemcpy2DAsync(buf.ptr, *pitch, img, w, w, h, cudaMemcpyHostToDevice, s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_fast_detect(lvkb200_stream* s, const uint8_t* image, int width, int height, int roi_x,
+                                   int roi_y, int roi_w, int roi_h, int threshold, lvkb200_keypoint* keypoints,
+                                   int capacity, int* count)
+{
+    LVKB_REQUIRE(s != nullptr && image != nullptr && count != nullptr);
+    LVKB_REQUIRE(capacity == 0 || keypoints != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    DeviceBuffer dimg;
+    size_t pitch = 0;
+    FastDetector det;
+    std::vector<std::vector<FastPoint>> pts;
+    lvkb200_status st = upload_gray(s, image, width, height, dimg, &pitch);
+    if (st == LVKB200_OK) st = det.prepare(width, height);
+    const FastRegion rg{roi_x, roi_y, roi_w, roi_h, threshold};
+    if (st == LVKB200_OK) st = det.launch(s->cs, dimg.as<uint8_t>(), pitch, &rg, 1);
+    if (st == LVKB200_OK) st = det.fetch(s->cs, pts);
+    cudaStreamSynchronize(s->cs);
+    if (st == LVKB200_OK)
+    {
+        *count = static_cast<int>(pts[0].size());
+        const int n = std::min(*count, capacity);
+        for (int i = 0; i < n; i++)
+            keypoints[i] = {static_cast<float>(pts[0][i].x), static_cast<float>(pts[0][i].y),
+                            static_cast<float>(pts[0][i].score), -1};
+        if (*count > capacity) st = LVKB200_ERR_CAPACITY;
+    }
+    det.release(); dimg.release();
+    return st;
+}
+
+lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const uint8_t* next, int width, int height,
+                                const float* points, int count, float* matched, uint8_t* status)
+{
+    LVKB_REQUIRE(s != nullptr && prev != nullptr && next != nullptr);
+    LVKB_REQUIRE(count == 0 || (points != nullptr && matched != nullptr && status != nullptr));
+    LVKB_CUDA(cudaSetDevice(s->device));
+    if (count == 0) return LVKB200_OK;
+    DeviceBuffer dprev, dnext, dp, dq, dst;
+    LkPyramid pp, pn;
+    size_t pitch = 0;
+    lvkb200_status st = upload_gray(s, prev, width, height, dprev, &pitch);
+    if (st == LVKB200_OK) st = upload_gray(s, next, width, height, dnext, &pitch);
+    if (st == LVKB200_OK) st = pp.prepare(width, height);
+    if (st == LVKB200_OK) st = pn.prepare(width, height);
+    if (st == LVKB200_OK) st = pp.build(s->cs, dprev.as<uint8_t>(), pitch);
+    if (st == LVKB200_OK) st = pn.build(s->cs, dnext.as<uint8_t>(), pitch);
+    auto cuda_ok = [&](cudaError_t e) { if (e != cudaSuccess && st == LVKB200_OK) { set_error("lk_track: %s", cudaGetErrorString(e)); st = LVKB200_ERR_CUDA; } };
+    if (st == LVKB200_OK)
+    {
+        cuda_ok(dp.ensure(sizeof(float2) * count));
+        cuda_ok(dq.ensure(sizeof(float2) * count));
+        cuda_ok(dst.ensure(count));
+    }
+    if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dp.ptr, points, sizeof(float2) * count, cudaMemcpyHostToDevice, s->cs));
+    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dq.as<float2>(), dst.as<uint8_t>());
+    if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(matched, dq.ptr, sizeof(float2) * count, cudaMemcpyDeviceToHost, s->cs));
+    if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(status, dst.ptr, count, cudaMemcpyDeviceToHost, s->cs));
+    cuda_ok(cudaStreamSynchronize(s->cs));
+    pp.release(); pn.release(); dprev.release(); dnext.release(); dp.release(); dq.release(); dst.release();
+    return st;
+}
+
+lvkb200_status lvkb200_find_homography(lvkb200_stream* s, const float* src_points, const float* dst_points, int count,
+                                       float threshold, double h_out[9], uint8_t* mask)
+{
+    LVKB_REQUIRE(s != nullptr && src_points != nullptr && dst_points != nullptr && h_out != nullptr && mask != nullptr);
+    LVKB_REQUIRE(count >= 4);  // FrameTracker.cpp:335
+    LVKB_CUDA(cudaSetDevice(s->device));
+    std::vector<float> a(src_points, src_points + 2 * static_cast<size_t>(count));
+    std::vector<float> b(dst_points, dst_points + 2 * static_cast<size_t>(count));
+    std::vector<uint8_t> m;
+    bool found = false;
+    LVKB_TRY(s->run_homography(a, b, threshold, h_out, m, &found));
+    std::memcpy(mask, m.data(), count);
+    if (!found)
+    {
+        set_error("find_homography: no model (degenerate correspondences)");
+        return LVKB200_ERR_NO_MODEL;
+    }
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream* s, const float* tracked, const float* matched, int count,
+                                              float* mesh_state, float* offsets_out, uint8_t* mask)
+{
+    LVKB_REQUIRE(s != nullptr && tracked != nullptr && matched != nullptr && mesh_state != nullptr &&
+                 offsets_out != nullptr && mask != nullptr);
+    MeshSolver solver;
+    solver.configure(s->settings);
+    const size_t elems = static_cast<size_t>(2) * s->settings.motion_resolution_width * s->settings.motion_resolution_height;
+    std::memcpy(solver.state().data(), mesh_state, sizeof(float) * elems);
+    std::vector<float> a(tracked, tracked + 2 * static_cast<size_t>(count));
+    std::vector<float> b(matched, matched + 2 * static_cast<size_t>(count));
+    Mesh offsets;
+    std::vector<uint8_t> m;
+    solver.estimate(a, b, offsets, m);
+    std::memcpy(mesh_state, solver.state().data(), sizeof(float) * elems);
+    std::memcpy(offsets_out, offsets.data(), sizeof(float) * elems);
+    std::memcpy(mask, m.data(), count);
+    return LVKB200_OK;
+}
 
 }  // extern "C"

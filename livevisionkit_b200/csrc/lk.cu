@@ -1,0 +1,354 @@
+// K1 + K4 — image pyramid, Scharr derivatives and sparse pyramidal Lucas-Kanade for sm_100a.
+//
+// Replaces cv::SparsePyrLKOpticalFlow::calc as configured and called by FrameTracker
+// (LiveVisionKit/Vision/FrameTracker.cpp:33-35,41-48,140-146): window 11x11, 3 pyramid levels above the base,
+// TermCriteria(COUNT+EPS, 5, 0.01), flags 0, minEigThreshold 1e-4, no error output.
+// OpenCV's CPU algorithm (upstream video/lkpyramid.cpp, imgproc pyrDown — not under /root/reference) restated:
+//   * pyramid: pyrDown = separable [1 4 6 4 1], (sum+128)>>8, BORDER_REFLECT_101, size (n+1)/2; every level is
+//     stored with an 11-px REFLECT_101 border so window reads never need clamping;
+//   * Scharr derivatives of every level as int16 (dx, dy) pairs, zero border;
+//   * per point, coarse to fine: 14-bit fixed-point bilinear patch of the previous image (5 fractional bits) and of
+//     its derivatives, 2x2 gradient matrix, min-eigenvalue test, <= 5 Newton iterations with the same stopping rules.
+// Window sums are accumulated EXACTLY in integers (OpenCV accumulates the same integer products in float32 SIMD
+// lanes), converted to float once: positions agree to ~1e-4 px, status identically (tests/test_lk_gpu.py).
+// One warp tracks one feature through all levels in a single launch: 121 window pixels = 4 per lane, patch kept in
+// registers, warp-shuffle reductions for A11/A12/A22/b1/b2.  Compiled with --fmad=false (the CPU path has no FMA).
+
+#include "common.hpp"
+#include "lk.hpp"
+
+namespace lvkb200
+{
+namespace
+{
+
+constexpr int P = LK_PAD;  // 11
+constexpr int WIN = 11;
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    // cv::borderInterpolate(BORDER_REFLECT_101) for |overshoot| < n
+    if (n == 1) return 0;
+    while (p < 0 || p >= n)
+    {
+        if (p < 0) p = -p;
+        else p = 2 * (n - 1) - p;
+    }
+    return p;
+}
+
+// Level 0: copy the detection image into the padded layout.
+__global__ void k_pyr_pad0(const uint8_t* __restrict__ src, size_t src_pitch, int w, int h, uint8_t* __restrict__ dst,
+                           size_t dst_pitch)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= w + 2 * P || py >= h + 2 * P) return;
+    const int x = reflect101(px - P, w), y = reflect101(py - P, h);
+    dst[(size_t)py * dst_pitch + px] = __ldg(src + (size_t)y * src_pitch + x);
+}
+
+// Level l (padded) from level l-1 (padded): pyrDown evaluated at every padded pixel's reflected coordinate.
+__global__ void k_pyr_down(const uint8_t* __restrict__ prev, size_t prev_pitch, uint8_t* __restrict__ dst,
+                           size_t dst_pitch, int w, int h)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= w + 2 * P || py >= h + 2 * P) return;
+    const int x = reflect101(px - P, w), y = reflect101(py - P, h);
+    const uint8_t* base = prev + (size_t)(2 * y - 2 + P) * prev_pitch + (2 * x - 2 + P);
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+    {
+        const uint8_t* r = base + (size_t)j * prev_pitch;
+        const int row = (int)r[0] + 4 * (int)r[1] + 6 * (int)r[2] + 4 * (int)r[3] + (int)r[4];
+        const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+        sum += kj * row;
+    }
+    dst[(size_t)py * dst_pitch + px] = (uint8_t)((sum + 128) >> 8);
+}
+
+struct ScharrArg
+{
+    const uint8_t* img[LK_MAX_LEVELS];
+    short2* deriv[LK_MAX_LEVELS];
+    size_t img_pitch[LK_MAX_LEVELS];
+    size_t deriv_pitch[LK_MAX_LEVELS];  // in short2 elements
+    int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
+};
+
+// calcScharrDeriv for every level in one launch (blockIdx.z = level); zero border.
+__global__ void k_scharr(ScharrArg a)
+{
+    const int l = blockIdx.z;
+    const int w = a.w[l], h = a.h[l];
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= w + 2 * P || py >= h + 2 * P) return;
+    short2 out = make_short2(0, 0);
+    const int x = px - P, y = py - P;
+    if (x >= 0 && x < w && y >= 0 && y < h)
+    {
+        const uint8_t* c = a.img[l] + (size_t)py * a.img_pitch[l] + px;
+        const size_t s = a.img_pitch[l];
+        const int u0 = c[-(ptrdiff_t)s - 1], u1 = c[-(ptrdiff_t)s], u2 = c[-(ptrdiff_t)s + 1];
+        const int m0 = c[-1], m2 = c[1];
+        const int d0 = c[s - 1], d1 = c[s], d2 = c[s + 1];
+        const int t0l = (u0 + d0) * 3 + m0 * 10, t0r = (u2 + d2) * 3 + m2 * 10;
+        const int t1l = d0 - u0, t1c = d1 - u1, t1r = d2 - u2;
+        out.x = (short)(t0r - t0l);
+        out.y = (short)((t1r + t1l) * 3 + t1c * 10);
+    }
+    a.deriv[l][(size_t)py * a.deriv_pitch[l] + px] = out;
+}
+
+struct LkArg
+{
+    const uint8_t* prev[LK_MAX_LEVELS];
+    const uint8_t* next[LK_MAX_LEVELS];
+    const short2* deriv[LK_MAX_LEVELS];
+    size_t img_pitch[LK_MAX_LEVELS];
+    size_t deriv_pitch[LK_MAX_LEVELS];
+    int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
+    int max_level;
+};
+
+__device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+
+__global__ void __launch_bounds__(128)
+    k_lk_track(LkArg a, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
+               uint8_t* __restrict__ status)
+{
+    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float2 p0 = prev_pts[pt];
+    const float half = 5.0f;       // (winSize - 1) * 0.5
+    const float FLT_SCALE = 1.0f / (float)(1 << 20);
+    float2 out = make_float2(0.f, 0.f);
+    bool ok = true;
+
+    // window pixel assignment: idx = lane + 32*q, q < 4, idx < 121
+    int wx[4], wy[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+        const int idx = lane + 32 * q;
+        wy[q] = idx / WIN;
+        wx[q] = idx - wy[q] * WIN;
+    }
+
+    for (int level = a.max_level; level >= 0; level--)
+    {
+        const int cols = a.w[level], rows = a.h[level];
+        const float inv = (float)(1.0 / (double)(1 << level));
+        float2 prevPt = make_float2(p0.x * inv, p0.y * inv);
+        float2 nextPt = (level == a.max_level) ? prevPt : make_float2(out.x * 2.0f, out.y * 2.0f);
+        out = nextPt;
+
+        prevPt.x -= half;
+        prevPt.y -= half;
+        const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+        if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows)
+        {
+            if (level == 0) ok = false;
+            continue;
+        }
+        float fa = prevPt.x - (float)ipx, fb = prevPt.y - (float)ipy;
+        int iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+        int iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+        int iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+
+        const size_t ipitch = a.img_pitch[level], dpitch = a.deriv_pitch[level];
+        const uint8_t* I = a.prev[level] + (size_t)(ipy + P) * ipitch + (ipx + P);
+        const short2* D = a.deriv[level] + (size_t)(ipy + P) * dpitch + (ipx + P);
+
+        int Ival[4], Ix[4], Iy[4];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            Ival[q] = 0; Ix[q] = 0; Iy[q] = 0;
+            if (lane + 32 * q < WIN * WIN)
+            {
+                const uint8_t* s = I + (size_t)wy[q] * ipitch + wx[q];
+                const short2* d = D + (size_t)wy[q] * dpitch + wx[q];
+                Ival[q] = descale((int)s[0] * iw00 + (int)s[1] * iw01 + (int)s[ipitch] * iw10 + (int)s[ipitch + 1] * iw11, 9);
+                const short2 d00 = d[0], d01 = d[1], d10 = d[dpitch], d11 = d[dpitch + 1];
+                Ix[q] = descale((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11, 14);
+                Iy[q] = descale((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11, 14);
+                sA11 += Ix[q] * Ix[q];
+                sA12 += Ix[q] * Iy[q];
+                sA22 += Iy[q] * Iy[q];
+            }
+        }
+        sA11 = __reduce_add_sync(0xffffffffu, sA11);
+        sA12 = __reduce_add_sync(0xffffffffu, sA12);
+        sA22 = __reduce_add_sync(0xffffffffu, sA22);
+
+        const float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+        float Dt = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+        if ((double)minEig < 1e-4 || Dt < 1.1920928955078125e-07f)
+        {
+            if (level == 0) ok = false;
+            continue;
+        }
+        Dt = 1.f / Dt;
+
+        nextPt.x -= half;
+        nextPt.y -= half;
+        float2 prevDelta = make_float2(0.f, 0.f);
+        const uint8_t* Jbase = a.next[level];
+
+        for (int j = 0; j < 5; j++)
+        {
+            const int inx = (int)floorf(nextPt.x), iny = (int)floorf(nextPt.y);
+            if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows)
+            {
+                if (level == 0) ok = false;
+                break;
+            }
+            fa = nextPt.x - (float)inx;
+            fb = nextPt.y - (float)iny;
+            iw00 = __float2int_rn((1.f - fa) * (1.f - fb) * 16384.f);
+            iw01 = __float2int_rn(fa * (1.f - fb) * 16384.f);
+            iw10 = __float2int_rn((1.f - fa) * fb * 16384.f);
+            iw11 = 16384 - iw00 - iw01 - iw10;
+
+            const uint8_t* J = Jbase + (size_t)(iny + P) * ipitch + (inx + P);
+            long long sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                if (lane + 32 * q < WIN * WIN)
+                {
+                    const uint8_t* s = J + (size_t)wy[q] * ipitch + wx[q];
+                    const int diff = descale((int)s[0] * iw00 + (int)s[1] * iw01 + (int)s[ipitch] * iw10 +
+                                                 (int)s[ipitch + 1] * iw11, 9) - Ival[q];
+                    sb1 += (long long)(diff * Ix[q]);
+                    sb2 += (long long)(diff * Iy[q]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                sb1 += __shfl_xor_sync(0xffffffffu, sb1, o);
+                sb2 += __shfl_xor_sync(0xffffffffu, sb2, o);
+            }
+            const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+            const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
+            nextPt.x += delta.x;
+            nextPt.y += delta.y;
+            out = make_float2(nextPt.x + half, nextPt.y + half);
+
+            if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= 0.01 * 0.01) break;
+            if (j > 0 && fabs((double)(delta.x + prevDelta.x)) < 0.01 && fabs((double)(delta.y + prevDelta.y)) < 0.01)
+            {
+                out.x -= delta.x * 0.5f;
+                out.y -= delta.y * 0.5f;
+                break;
+            }
+            prevDelta = delta;
+        }
+    }
+    if (lane == 0)
+    {
+        next_pts[pt] = out;
+        status[pt] = ok ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+lvkb200_status LkPyramid::prepare(int width, int height)
+{
+    if (width == w[0] && height == h[0] && levels > 0) return LVKB200_OK;
+    // buildOpticalFlowPyramid stops when a level is not larger than the window
+    LVKB_REQUIRE(width > WIN && height > WIN);
+    int lw = width, lh = height;
+    levels = 0;
+    for (int l = 0; l <= LK_REF_MAX_LEVEL; l++)
+    {
+        if (l > 0)
+        {
+            lw = (lw + 1) / 2;
+            lh = (lh + 1) / 2;
+            if (lw <= WIN || lh <= WIN) break;
+        }
+        w[l] = lw;
+        h[l] = lh;
+        img_pitch[l] = (size_t)((lw + 2 * P + 15) / 16 * 16);
+        deriv_pitch[l] = (size_t)((lw + 2 * P + 3) / 4 * 4);
+        LVKB_CUDA(img[l].ensure(img_pitch[l] * (lh + 2 * P + 1) + 16));
+        LVKB_CUDA(deriv[l].ensure(sizeof(short2) * (deriv_pitch[l] * (lh + 2 * P + 1) + 16)));
+        levels++;
+    }
+    valid = false;
+    return LVKB200_OK;
+}
+
+void LkPyramid::release()
+{
+    for (int l = 0; l < LK_MAX_LEVELS; l++)
+    {
+        img[l].release();
+        deriv[l].release();
+    }
+    levels = 0;
+    valid = false;
+    w[0] = h[0] = 0;
+}
+
+lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_pitch)
+{
+    const dim3 blk(32, 8);
+    {
+        const dim3 grid(div_up(w[0] + 2 * P, 32), div_up(h[0] + 2 * P, 8));
+        k_pyr_pad0<<<grid, blk, 0, cs>>>(det, det_pitch, w[0], h[0], img[0].as<uint8_t>(), img_pitch[0]);
+    }
+    for (int l = 1; l < levels; l++)
+    {
+        const dim3 grid(div_up(w[l] + 2 * P, 32), div_up(h[l] + 2 * P, 8));
+        k_pyr_down<<<grid, blk, 0, cs>>>(img[l - 1].as<uint8_t>(), img_pitch[l - 1], img[l].as<uint8_t>(),
+                                         img_pitch[l], w[l], h[l]);
+    }
+    ScharrArg sa{};
+    for (int l = 0; l < levels; l++)
+    {
+        sa.img[l] = img[l].as<uint8_t>();
+        sa.deriv[l] = deriv[l].as<short2>();
+        sa.img_pitch[l] = img_pitch[l];
+        sa.deriv_pitch[l] = deriv_pitch[l];
+        sa.w[l] = w[l];
+        sa.h[l] = h[l];
+    }
+    const dim3 grid(div_up(w[0] + 2 * P, 32), div_up(h[0] + 2 * P, 8), levels);
+    k_scharr<<<grid, blk, 0, cs>>>(sa);
+    LVKB_CUDA(cudaGetLastError());
+    valid = true;
+    return LVKB200_OK;
+}
+
+lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts, int n,
+                        float2* d_next_pts, uint8_t* d_status)
+{
+    if (n <= 0) return LVKB200_OK;
+    LVKB_REQUIRE(prev.levels == next.levels && prev.levels > 0 && prev.w[0] == next.w[0] && prev.h[0] == next.h[0]);
+    LkArg a{};
+    for (int l = 0; l < prev.levels; l++)
+    {
+        a.prev[l] = prev.img[l].as<uint8_t>();
+        a.next[l] = next.img[l].as<uint8_t>();
+        a.deriv[l] = prev.deriv[l].as<short2>();
+        a.img_pitch[l] = prev.img_pitch[l];
+        a.deriv_pitch[l] = prev.deriv_pitch[l];
+        a.w[l] = prev.w[l];
+        a.h[l] = prev.h[l];
+    }
+    a.max_level = prev.levels - 1;
+    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, n, d_next_pts, d_status);
+    LVKB_CUDA(cudaGetLastError());
+    return LVKB200_OK;
+}
+
+}  // namespace lvkb200

@@ -1,4 +1,7 @@
 // lvkb200_stream: per-frame orchestration of the stabilization path (host C++), state and scratch.
+// Mirrors StabilizationFilter::filter (LiveVisionKit/Filters/StabilizationFilter.cpp:69-135) and
+// FrameTracker::track (LiveVisionKit/Vision/FrameTracker.cpp:108-196); every pixel- or point-parallel step is a
+// CUDA kernel (ingest.cu, lk.cu, fast.cu, ransac.cu, remap.cu), the order-dependent bookkeeping is host_logic.hpp.
 #include "stream_impl.hpp"
 
 #include <algorithm>
@@ -9,6 +12,12 @@
 using namespace lvkb200;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr float QA_UPDATE_RATE = 0.1f;  // StabilizationFilter.cpp:29
+constexpr float QA_BLEND_STEP = 0.05f;  // StabilizationFilter.cpp:30
+constexpr float HOMOGRAPHY_DISTRIBUTION_THRESHOLD = 0.6f;  // FrameTracker.cpp:37
+
+enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_FAST, ST_LK, ST_ESTIMATE, ST_REMAP };
 
 lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
 {
@@ -26,6 +35,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     LVKB_REQUIRE(s.detection_regions_width > 0 && s.detection_regions_height > 0);
     LVKB_REQUIRE(s.detection_regions_height <= s.detection_resolution_height);
     LVKB_REQUIRE(s.detection_regions_width <= s.detection_resolution_width);
+    LVKB_REQUIRE(s.detection_regions_width * s.detection_regions_height <= FAST_MAX_REGIONS);
     LVKB_REQUIRE(s.min_feature_density <= s.max_feature_density);
     LVKB_REQUIRE(s.min_feature_density > 0.0f);
     LVKB_REQUIRE(s.accumulation_rate > 0.0f);
@@ -36,56 +46,570 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     LVKB_REQUIRE(s.predictive_samples > 0);
     LVKB_REQUIRE(s.smoothing_steps > 0.0f);
     LVKB_REQUIRE(s.response_rate >= 0.0f && s.response_rate <= 1.0f);
+
+    // StabilizationFilter.cpp:51-52: disabling the stabilization resets the context
+    if (configured && settings.stabilize_output && !s.stabilize_output) LVKB_TRY(reset_context());
+
+    const bool det_changed = !configured || s.detection_resolution_width != settings.detection_resolution_width ||
+                             s.detection_resolution_height != settings.detection_resolution_height;
     settings = s;
+
+    smoother.configure(s);
+
+    // m_FrameQueue.resize(time_delay + 1): StreamBuffer::resize keeps the newest frames (Data/StreamBuffer.tpp:206-221)
+    const size_t capacity = static_cast<size_t>(s.predictive_samples) + 1;
+    if (ring.size() != capacity)
+    {
+        if (cs) LVKB_CUDA(cudaStreamSynchronize(cs));
+        std::vector<QueuedFrame> fresh(capacity);
+        const size_t keep = std::min(ring_size, capacity);
+        for (size_t i = 0; i < keep; i++)
+            std::swap(fresh[i], ring[(ring_start + (ring_size - keep) + i) % ring.size()]);
+        for (auto& f : ring) f.buf.release();
+        ring.swap(fresh);
+        ring_start = 0;
+        ring_size = keep;
+    }
+
+    grid.configure(s);
+    mesh_solver.configure(s);
+    det_w = s.detection_resolution_width;
+    det_h = s.detection_resolution_height;
+    if (det_changed)
+    {
+        // FrameTracker.cpp:84-90 rescales the previous detection frame; we restart tracking instead (one motion
+        // sample is skipped after a detection-resolution change; documented in DESIGN.md).
+        features.clear();
+        grid.reset();
+        frame_initialized = false;
+        pyr[0].valid = pyr[1].valid = false;
+    }
     configured = true;
     return LVKB200_OK;
 }
 
-lvkb200_status lvkb200_stream::restart() { return LVKB200_OK; }
-lvkb200_status lvkb200_stream::reset_context() { return LVKB200_OK; }
-bool lvkb200_stream::ready() const { return false; }
+lvkb200_status lvkb200_stream::restart()
+{
+    // StabilizationFilter::restart — StabilizationFilter.cpp:139-144
+    scene_quality = 1.0f;
+    ring_start = 0;
+    ring_size = 0;
+    return reset_context();
+}
+
+lvkb200_status lvkb200_stream::reset_context()
+{
+    // FrameTracker::restart (FrameTracker.cpp:97-104) + PathSmoother::restart (PathSmoother.cpp:139-145)
+    tracking_stability = 0.0f;
+    features.clear();
+    grid.reset();
+    frame_initialized = false;
+    mesh_solver.restart();
+    smoother.restart();
+    return LVKB200_OK;
+}
 
 void lvkb200_stream::stable_region(int fw, int fh, int* x, int* y, int* w, int* h) const
 {
     // StabilizationFilter::stable_region (StabilizationFilter.cpp:199-): scene margins scaled to the frame.
-    const float thc = 1.0f * settings.corrective_limits_width, tvc = 1.0f * settings.corrective_limits_height;
-    const float mx = thc / 2, my = tvc / 2, mw = 1.0f - thc, mh = 1.0f - tvc;
-    *x = static_cast<int>(std::lrintf(mx * static_cast<float>(fw)));
-    *y = static_cast<int>(std::lrintf(my * static_cast<float>(fh)));
-    *w = static_cast<int>(std::lrintf(mw * static_cast<float>(fw)));
-    *h = static_cast<int>(std::lrintf(mh * static_cast<float>(fh)));
+    *x = static_cast<int>(std::lrintf(smoother.margin_x * static_cast<float>(fw)));
+    *y = static_cast<int>(std::lrintf(smoother.margin_y * static_cast<float>(fh)));
+    *w = static_cast<int>(std::lrintf(smoother.margin_w * static_cast<float>(fw)));
+    *h = static_cast<int>(std::lrintf(smoother.margin_h * static_cast<float>(fh)));
 }
 
-lvkb200_status lvkb200_stream::submit(const void*, size_t, int, int, lvkb200_format, uint64_t, lvkb200_memspace, void*,
-                                      size_t, lvkb200_memspace, lvkb200_result*)
+void lvkb200_stream::stage_begin(int stage)
 {
-    set_error("submit: not implemented yet");
-    return LVKB200_ERR_INVALID;
+    if (!stage_ev[stage][0])
+    {
+        cudaEventCreate(&stage_ev[stage][0]);
+        cudaEventCreate(&stage_ev[stage][1]);
+    }
+    cudaEventRecord(stage_ev[stage][0], cs);
+    stage_used[stage] = true;
 }
 
-lvkb200_status lvkb200_stream::debug_fetch(lvkb200_debug_item, void*, size_t, size_t* size)
-{
-    *size = 0;
-    return LVKB200_OK;
-}
+void lvkb200_stream::stage_end(int stage) { cudaEventRecord(stage_ev[stage][1], cs); }
 
 lvkb200_status lvkb200_stream::stage_times(float* times)
 {
-    for (int i = 0; i < LVKB200_STAGE_COUNT; i++) times[i] = 0.0f;
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
+    {
+        times[i] = 0.0f;
+        if (stage_used[i] && stage_ev[i][0])
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, stage_ev[i][0], stage_ev[i][1]) == cudaSuccess) times[i] = ms * 1000.0f;
+            else cudaGetLastError();
+        }
+    }
     return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::ensure_points(int n)
+{
+    if (n <= point_capacity) return LVKB200_OK;
+    const int cap = std::max(n, 4096);
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    LVKB_CUDA(d_pts_prev.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(d_pts_next.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(d_status.ensure(cap));
+    LVKB_CUDA(d_src.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(d_dst.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(d_mask.ensure(cap));
+    LVKB_CUDA(d_models.ensure(sizeof(float) * 9 * RANSAC_HYPOTHESES));
+    LVKB_CUDA(d_scores.ensure(sizeof(float) * RANSAC_HYPOTHESES));
+    LVKB_CUDA(d_result.ensure(sizeof(RansacResult)));
+    LVKB_CUDA(h_pts_prev.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(h_pts_next.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(h_status.ensure(cap));
+    LVKB_CUDA(h_src.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(h_dst.ensure(sizeof(float2) * cap));
+    LVKB_CUDA(h_mask.ensure(cap));
+    LVKB_CUDA(h_result.ensure(sizeof(RansacResult)));
+    point_capacity = cap;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::run_lk(const std::vector<float>& pts, std::vector<float>& matched,
+                                      std::vector<uint8_t>& status)
+{
+    const int n = static_cast<int>(pts.size() / 2);
+    matched.resize(pts.size());
+    status.resize(n);
+    if (n == 0) return LVKB200_OK;
+    LVKB_TRY(ensure_points(n));
+    std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
+    LVKB_CUDA(cudaMemcpyAsync(d_pts_prev.ptr, h_pts_prev.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
+    LVKB_TRY(lk_track(cs, pyr[cur ^ 1], pyr[cur], d_pts_prev.as<float2>(), n, d_pts_next.as<float2>(),
+                      d_status.as<uint8_t>()));
+    LVKB_CUDA(cudaMemcpyAsync(h_pts_next.ptr, d_pts_next.ptr, sizeof(float2) * n, cudaMemcpyDeviceToHost, cs));
+    LVKB_CUDA(cudaMemcpyAsync(h_status.ptr, d_status.ptr, n, cudaMemcpyDeviceToHost, cs));
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    std::memcpy(matched.data(), h_pts_next.ptr, sizeof(float) * pts.size());
+    std::memcpy(status.data(), h_status.ptr, n);
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked, const std::vector<float>& matched,
+                                              float threshold, double h[9], std::vector<uint8_t>& mask, bool* found)
+{
+    const int n = static_cast<int>(tracked.size() / 2);
+    LVKB_REQUIRE(n >= 4);  // FrameTracker.cpp:335
+    LVKB_TRY(ensure_points(n));
+    std::memcpy(h_src.ptr, tracked.data(), sizeof(float) * tracked.size());
+    std::memcpy(h_dst.ptr, matched.data(), sizeof(float) * matched.size());
+    LVKB_CUDA(cudaMemcpyAsync(d_src.ptr, h_src.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_dst.ptr, h_dst.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
+    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), n, threshold, d_models.as<float>(),
+                               d_scores.as<float>(), d_result.as<RansacResult>(), d_mask.as<uint8_t>()));
+    LVKB_CUDA(cudaMemcpyAsync(h_result.ptr, d_result.ptr, sizeof(RansacResult), cudaMemcpyDeviceToHost, cs));
+    LVKB_CUDA(cudaMemcpyAsync(h_mask.ptr, d_mask.ptr, n, cudaMemcpyDeviceToHost, cs));
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    const RansacResult* r = h_result.as<RansacResult>();
+    *found = r->found != 0;
+    mask.assign(h_mask.as<uint8_t>(), h_mask.as<uint8_t>() + n);
+    std::memcpy(h, r->h, sizeof(double) * 9);
+    return LVKB200_OK;
+}
+
+// lvk::fast_erase on parallel arrays (Functions/Container.tpp:31-39)
+template <typename T>
+static inline void fast_erase_n(std::vector<T>& v, size_t index, size_t width)
+{
+    const size_t last = v.size() / width - 1;
+    for (size_t k = 0; k < width; k++) std::swap(v[index * width + k], v[last * width + k]);
+    v.resize(last * width);
+}
+
+lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, bool* has_motion)
+{
+    *has_motion = false;
+    tracking_stability = 0.0f;  // FrameTracker.cpp:113
+
+    // ---- advance time and import the next frame (FrameTracker.cpp:116-117; gray view StabilizationFilter.cpp:98)
+    cur ^= 1;
+    det_pitch = align_up(static_cast<size_t>(det_w), 16);
+    LVKB_CUDA(d_det.ensure(det_pitch * det_h));
+    LVKB_TRY(ingest.prepare(frame.w, frame.h, det_w, det_h, cs));
+    LVKB_TRY(fast.prepare(det_w, det_h));
+    LVKB_TRY(pyr[0].prepare(det_w, det_h));
+    LVKB_TRY(pyr[1].prepare(det_w, det_h));
+
+    stage_begin(ST_INGEST);
+    LVKB_TRY(ingest.launch(cs, frame.buf.as<uint8_t>(), frame.pitch, frame.format, d_det.as<uint8_t>(), det_pitch));
+    stage_end(ST_INGEST);
+    stage_begin(ST_PYRAMID);
+    LVKB_TRY(pyr[cur].build(cs, d_det.as<uint8_t>(), det_pitch));
+    stage_end(ST_PYRAMID);
+
+    if (debug_capture)
+    {
+        LVKB_CUDA(h_det.ensure(static_cast<size_t>(det_w) * det_h));
+        LVKB_CUDA(cudaMemcpy2DAsync(h_det.ptr, det_w, d_det.ptr, det_pitch, det_w, det_h, cudaMemcpyDeviceToHost, cs));
+        LVKB_CUDA(cudaStreamSynchronize(cs));
+        dbg_det.assign(h_det.as<uint8_t>(), h_det.as<uint8_t>() + static_cast<size_t>(det_w) * det_h);
+    }
+
+    // ---- we need at least two frames (FrameTracker.cpp:120-124)
+    if (!frame_initialized || !pyr[cur ^ 1].valid)
+    {
+        frame_initialized = true;
+        return LVKB200_OK;
+    }
+
+    // ---- FeatureDetector::detect (FrameTracker.cpp:127)
+    std::vector<FastRegion> regions;
+    std::vector<int> region_index;
+    std::vector<std::vector<FastPoint>> fast_points;
+    grid.plan_detection(regions, region_index);
+    stage_begin(ST_FAST);
+    if (!regions.empty())
+    {
+        LVKB_TRY(fast.launch(cs, d_det.as<uint8_t>(), det_pitch, regions.data(), static_cast<int>(regions.size())));
+        stage_end(ST_FAST);
+        LVKB_TRY(fast.fetch(cs, fast_points));
+    }
+    else
+        stage_end(ST_FAST);
+    const float distribution = grid.finish_detection(region_index, fast_points, features, dbg_fast_counts);
+    if (debug_capture)
+    {
+        dbg_detected.resize(features.size());
+        for (size_t i = 0; i < features.size(); i++)
+            dbg_detected[i] = {features[i].x, features[i].y, features[i].response, features[i].class_id};
+    }
+    if (features.size() < settings.min_motion_samples || distribution < settings.uniformity_threshold)
+    {
+        features.clear();
+        return LVKB200_OK;
+    }
+
+    // ---- sparse optical flow (FrameTracker.cpp:135-146)
+    std::vector<float> tracked(features.size() * 2), matched;
+    std::vector<uint8_t> status;
+    for (size_t i = 0; i < features.size(); i++)
+    {
+        tracked[2 * i] = features[i].x;
+        tracked[2 * i + 1] = features[i].y;
+    }
+    stage_begin(ST_LK);
+    LVKB_TRY(run_lk(tracked, matched, status));
+    stage_end(ST_LK);
+    if (debug_capture)
+    {
+        dbg_lk_matched = matched;
+        dbg_lk_status = status;
+    }
+
+    // ---- fast_filter(features, tracked, matched, status) (FrameTracker.cpp:149, Container.tpp:97-121)
+    for (int k = static_cast<int>(status.size()) - 1; k >= 0; k--)
+    {
+        if (!status[k])
+        {
+            std::swap(features[k], features.back());
+            features.pop_back();
+            fast_erase_n(tracked, k, 2);
+            fast_erase_n(matched, k, 2);
+        }
+    }
+    if (matched.size() / 2 < settings.min_motion_samples)
+    {
+        features.clear();
+        return LVKB200_OK;
+    }
+    if (debug_capture)
+    {
+        dbg_tracked = tracked;
+        dbg_matched = matched;
+    }
+
+    // ---- motion estimation (FrameTracker.cpp:157-176)
+    std::vector<uint8_t> inliers;
+    stage_begin(ST_ESTIMATE);
+    if (settings.track_local_motions)
+    {
+        mesh_solver.estimate(tracked, matched, motion, inliers);
+    }
+    else
+    {
+        double h[9];
+        bool found = false;
+        if (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD)
+        {
+            LVKB_TRY(run_homography(tracked, matched, settings.acceptance_threshold, h, inliers, &found));
+        }
+        else
+        {
+            // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) branch (FrameTracker.cpp:362-373); until the similarity
+            // estimator lands the homography estimator is used for badly distributed features as well.
+            LVKB_TRY(run_homography(tracked, matched, settings.acceptance_threshold, h, inliers, &found));
+        }
+        if (!found)
+        {
+            // cv::findHomography returned an empty matrix: the reference asserts (Math/Homography.cpp:89-95).
+            // Reported through the assert handler; the frame is then treated as "no motion".
+            stage_end(ST_ESTIMATE);
+            report_assert(__FILE__, "estimate_global_motion", "homography estimation found no model");
+            features.clear();
+            return LVKB200_OK;
+        }
+        std::memcpy(dbg_h, h, sizeof(h));
+        dbg_has_h = true;
+        mesh_set_to_homography(h, static_cast<float>(det_w), static_cast<float>(det_h), settings.motion_resolution_width,
+                               settings.motion_resolution_height, motion);
+    }
+    stage_end(ST_ESTIMATE);
+    if (debug_capture) dbg_inliers = inliers;
+
+    // ---- tracking stability = inlier ratio (FrameTracker.cpp:179, Container.tpp:125-129)
+    size_t inl = 0;
+    for (uint8_t v : inliers) inl += (v == 1);
+    tracking_stability = static_cast<float>(inl) / static_cast<float>(inliers.size());
+
+    // ---- drop outliers, age inliers, propagate (FrameTracker.cpp:183-193)
+    for (int i = static_cast<int>(inliers.size()) - 1; i >= 0; i--)
+    {
+        if (inliers[i])
+        {
+            features[i].class_id++;
+            features[i].x = matched[2 * i];
+            features[i].y = matched[2 * i + 1];
+        }
+        else
+        {
+            std::swap(features[i], features.back());
+            features.pop_back();
+        }
+    }
+    grid.propagate(features);
+    if (debug_capture)
+    {
+        dbg_propagated.resize(features.size());
+        for (size_t i = 0; i < features.size(); i++)
+            dbg_propagated[i] = {features[i].x, features[i].y, features[i].response, features[i].class_id};
+    }
+    *has_motion = true;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& offsets, void* out, size_t out_pitch,
+                                          lvkb200_memspace out_space)
+{
+    // WarpMesh::apply — Math/WarpMesh.cpp:183-223
+    RemapParams p{};
+    p.src = src.buf.as<uint8_t>();
+    p.src_pitch = src.pitch;
+    p.width = src.w;
+    p.height = src.h;
+    p.yuv = src.format == LVKB200_YUV;  // Image.cpp:100
+    for (int k = 0; k < 3; k++) p.bg[k] = static_cast<uint8_t>(settings.background_colour[k]);  // Image.cpp:136-141
+    LVKB_TRY(stage_frame_out(out, out_pitch, src.w, src.h, 3, out_space, &p.dst, &p.dst_pitch));
+    stage_begin(ST_REMAP);
+    if (settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2)
+    {
+        double t[9];
+        LVKB_REQUIRE(mesh2x2_to_transform(offsets.data(), src.w, src.h, t));
+        std::memcpy(dbg_t, t, sizeof(t));
+        dbg_has_t = true;
+        float tf[9];
+        for (int k = 0; k < 9; k++) tf[k] = static_cast<float>(t[k]);
+        LVKB_CUDA(launch_remap_homography(cs, p, tf));
+    }
+    else
+    {
+        const float* dmesh = nullptr;
+        LVKB_TRY(upload_mesh(offsets.data(), settings.motion_resolution_width, settings.motion_resolution_height, &dmesh));
+        LVKB_CUDA(launch_remap_mesh(cs, p, dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
+    }
+    stage_end(ST_REMAP);
+    return finish_frame_out(out, out_pitch, src.w, src.h, 3, out_space);
+}
+
+lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width, int height, lvkb200_format format,
+                                      uint64_t timestamp, lvkb200_memspace frame_space, void* out, size_t out_pitch,
+                                      lvkb200_memspace out_space, lvkb200_result* res)
+{
+    std::memset(res, 0, sizeof(*res));
+    res->out_format = LVKB200_UNKNOWN;
+    LVKB_REQUIRE(format != LVKB200_UNKNOWN);  // StabilizationFilter.cpp:71
+    LVKB_REQUIRE(width > 0 && height > 0);    // :72
+    // Only packed 3-channel frames reach lvk::remap (Image.cpp:32,96).
+    LVKB_REQUIRE(format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV);
+    const size_t row = static_cast<size_t>(width) * 3;
+    LVKB_REQUIRE(pitch >= row);
+    for (auto& u : stage_used) u = false;
+    dbg_has_h = dbg_has_t = false;
+    dbg_detected.clear(); dbg_propagated.clear(); dbg_lk_matched.clear(); dbg_lk_status.clear(); dbg_tracked.clear();
+    dbg_matched.clear(); dbg_inliers.clear(); dbg_motion.clear(); dbg_correction.clear(); dbg_fast_counts.clear();
+
+    // ---- m_FrameQueue.push(std::move(input)): the frame becomes resident in the device ring
+    const size_t cap = ring.size();
+    size_t slot;
+    if (ring_size == cap)
+    {
+        slot = ring_start;  // StreamBuffer::push on a full ring overwrites the oldest (StreamBuffer.tpp:37-84)
+        ring_start = (ring_start + 1) % cap;
+    }
+    else
+    {
+        slot = (ring_start + ring_size) % cap;
+        ring_size++;
+    }
+    QueuedFrame& q = ring[slot];
+    q.pitch = align_up(row, 16);
+    LVKB_CUDA(q.buf.ensure(q.pitch * height));
+    q.w = width; q.h = height; q.format = format; q.timestamp = timestamp;
+    LVKB_CUDA(cudaMemcpy2DAsync(q.buf.ptr, q.pitch, frame, pitch, row, height,
+                                frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+    // The caller keeps ownership of its buffer: host memory must have been consumed before we return.
+    struct InputGuard
+    {
+        lvkb200_stream* s;
+        bool host;
+        ~InputGuard() { if (host && s->input_copied) cudaEventSynchronize(s->input_copied); }
+    } input_guard{this, frame_space == LVKB200_MEM_HOST};
+    if (frame_space == LVKB200_MEM_HOST)
+    {
+        if (!input_copied) LVKB_CUDA(cudaEventCreateWithFlags(&input_copied, cudaEventDisableTiming));
+        LVKB_CUDA(cudaEventRecord(input_copied, cs));
+    }
+
+    if (!settings.stabilize_output)
+    {
+        // StabilizationFilter.cpp:77-95: only up-keep the delay
+        if (ready())
+        {
+            QueuedFrame& oldest = ring[ring_start];
+            ring_start = (ring_start + 1) % cap;
+            ring_size--;
+            LVKB_REQUIRE(out != nullptr);
+            if (settings.crop_to_stable_region)
+            {
+                const uint8_t black[3] = {0, 0, 0};  // WarpMesh::apply default background
+                lvkb200_settings saved = settings;
+                for (int k = 0; k < 3; k++) settings.background_colour[k] = black[k];
+                const lvkb200_status st = apply_mesh(oldest, smoother.scene_crop, out, out_pitch, out_space);
+                settings = saved;
+                LVKB_TRY(st);
+            }
+            else
+            {
+                LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, oldest.buf.ptr, oldest.pitch, static_cast<size_t>(oldest.w) * 3,
+                                            oldest.h,
+                                            out_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
+                if (out_space == LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(cs));
+            }
+            res->has_output = 1;
+            res->out_timestamp = oldest.timestamp;
+            res->out_format = oldest.format;
+        }
+        res->scene_quality = scene_quality;
+        res->trust_factor = trust_factor;
+        return LVKB200_OK;
+    }
+
+    // ---- track the motion of the incoming frame (StabilizationFilter.cpp:98-99)
+    Mesh motion;
+    bool has_motion = false;
+    LVKB_TRY(track(q, motion, &has_motion));
+    const size_t elems = static_cast<size_t>(settings.motion_resolution_width) * settings.motion_resolution_height * 2;
+    if (!has_motion) motion.assign(elems, 0.0f);  // m_NullMotion
+    if (debug_capture) dbg_motion = motion;
+
+    // ---- quality assurance (StabilizationFilter.cpp:101-115)
+    const float tracking_quality = tracking_stability;
+    scene_quality = scene_quality + QA_UPDATE_RATE * (tracking_quality - scene_quality);
+    if (tracking_quality < settings.min_tracking_quality)
+        trust_factor = 0.0f;
+    else if (scene_quality < settings.min_scene_quality)
+        trust_factor = step_to<float>(trust_factor, 0.0f, QA_BLEND_STEP);
+    else
+        trust_factor = step_to<float>(trust_factor, 1.0f, QA_BLEND_STEP);
+    for (float& v : motion) v *= trust_factor;
+
+    // ---- path smoothing (StabilizationFilter.cpp:121)
+    Mesh correction;
+    smoother.next(motion, correction);
+
+    if (ready())
+    {
+        QueuedFrame& next_frame = ring[ring_start];
+        ring_start = (ring_start + 1) % cap;
+        ring_size--;
+        if (settings.crop_to_stable_region)
+            for (size_t k = 0; k < elems; k++) correction[k] += smoother.scene_crop[k];
+        if (debug_capture) dbg_correction = correction;
+        LVKB_REQUIRE(out != nullptr);
+        LVKB_TRY(apply_mesh(next_frame, correction, out, out_pitch, out_space));
+        res->has_output = 1;
+        res->out_timestamp = next_frame.timestamp;
+        res->out_format = next_frame.format;
+    }
+    else if (debug_capture)
+        dbg_correction = correction;
+
+    res->tracking_stability = tracking_stability;
+    res->scene_quality = scene_quality;
+    res->trust_factor = trust_factor;
+    res->feature_count = static_cast<int32_t>(features.size());
+    res->has_motion = has_motion ? 1 : 0;
+    return LVKB200_OK;
+}
+
+template <typename T>
+static lvkb200_status copy_out(const T* data, size_t count, void* buffer, size_t capacity, size_t* size)
+{
+    *size = count * sizeof(T);
+    if (buffer && capacity > 0) std::memcpy(buffer, data, std::min(capacity, *size));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::debug_fetch(lvkb200_debug_item which, void* buffer, size_t capacity, size_t* size)
+{
+    *size = 0;
+    switch (which)
+    {
+        case LVKB200_DBG_DETECTION_IMAGE: return copy_out(dbg_det.data(), dbg_det.size(), buffer, capacity, size);
+        case LVKB200_DBG_DETECTED: return copy_out(dbg_detected.data(), dbg_detected.size(), buffer, capacity, size);
+        case LVKB200_DBG_LK_MATCHED: return copy_out(dbg_lk_matched.data(), dbg_lk_matched.size(), buffer, capacity, size);
+        case LVKB200_DBG_LK_STATUS: return copy_out(dbg_lk_status.data(), dbg_lk_status.size(), buffer, capacity, size);
+        case LVKB200_DBG_TRACKED: return copy_out(dbg_tracked.data(), dbg_tracked.size(), buffer, capacity, size);
+        case LVKB200_DBG_MATCHED: return copy_out(dbg_matched.data(), dbg_matched.size(), buffer, capacity, size);
+        case LVKB200_DBG_INLIERS: return copy_out(dbg_inliers.data(), dbg_inliers.size(), buffer, capacity, size);
+        case LVKB200_DBG_HOMOGRAPHY: return dbg_has_h ? copy_out(dbg_h, 9, buffer, capacity, size) : LVKB200_OK;
+        case LVKB200_DBG_MOTION: return copy_out(dbg_motion.data(), dbg_motion.size(), buffer, capacity, size);
+        case LVKB200_DBG_CORRECTION: return copy_out(dbg_correction.data(), dbg_correction.size(), buffer, capacity, size);
+        case LVKB200_DBG_WARP_TRANSFORM: return dbg_has_t ? copy_out(dbg_t, 9, buffer, capacity, size) : LVKB200_OK;
+        case LVKB200_DBG_PROPAGATED: return copy_out(dbg_propagated.data(), dbg_propagated.size(), buffer, capacity, size);
+        case LVKB200_DBG_FAST_COUNTS: return copy_out(dbg_fast_counts.data(), dbg_fast_counts.size(), buffer, capacity, size);
+    }
+    return LVKB200_ERR_INVALID;
 }
 
 void lvkb200_stream::release()
 {
-    stage_in.release();
-    stage_out.release();
-    mesh_dev.release();
-    mesh_pinned.release();
+    stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
+    ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
+    d_pts_prev.release(); d_pts_next.release(); d_status.release(); d_src.release(); d_dst.release(); d_mask.release();
+    d_models.release(); d_scores.release(); d_result.release();
+    h_pts_prev.release(); h_pts_next.release(); h_status.release(); h_src.release(); h_dst.release(); h_mask.release();
+    h_result.release(); h_det.release();
+    for (auto& f : ring) f.buf.release();
+    if (input_copied) cudaEventDestroy(input_copied);
+    input_copied = nullptr;
     for (auto& e : user_events)
     {
         if (e) cudaEventDestroy(e);
         e = nullptr;
     }
+    for (auto& pair : stage_ev)
+        for (auto& e : pair)
+        {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
 }
 
 lvkb200_status lvkb200_stream::stage_frame_in(const void* p, size_t pitch, int w, int h, int ch, lvkb200_memspace space,

@@ -1,10 +1,16 @@
-// lvkb200_stream definition (opaque to C callers).
+// lvkb200_stream definition (opaque to C callers): one video stream == one lvk::StabilizationFilter instance.
 #pragma once
 
 #include <cstring>
 #include <vector>
 
 #include "common.hpp"
+#include "fast.hpp"
+#include "host_logic.hpp"
+#include "host_mesh.hpp"
+#include "ingest.hpp"
+#include "lk.hpp"
+#include "ransac.hpp"
 #include "stream.hpp"
 
 struct lvkb200_stream
@@ -13,16 +19,62 @@ struct lvkb200_stream
     cudaStream_t cs = nullptr;
     lvkb200_settings settings{};
     bool configured = false;
+    bool debug_capture = false;
 
-    // scratch used by the stage-level entry points when the caller hands host memory
+    // ---- scratch used by the stage-level entry points when the caller hands host memory
     lvkb200::DeviceBuffer stage_in, stage_out, mesh_dev;
     lvkb200::PinnedBuffer mesh_pinned;
     cudaEvent_t user_events[LVKB200_EVENT_SLOTS] = {};
 
+    // ---- device-side stages
+    lvkb200::IngestPlan ingest;
+    lvkb200::FastDetector fast;
+    lvkb200::LkPyramid pyr[2];
+    int cur = 0;  // pyr[cur] = current frame, pyr[cur ^ 1] = previous frame
+    lvkb200::DeviceBuffer d_det;
+    size_t det_pitch = 0;
+    lvkb200::DeviceBuffer d_pts_prev, d_pts_next, d_status, d_src, d_dst, d_mask, d_models, d_scores, d_result;
+    lvkb200::PinnedBuffer h_pts_prev, h_pts_next, h_status, h_src, h_dst, h_mask, h_result, h_det;
+    int point_capacity = 0;
+
+    // ---- StabilizationFilter / FrameTracker / FeatureDetector / PathSmoother host state
+    lvkb200::FeatureGrid grid;
+    lvkb200::PathSmoother smoother;
+    lvkb200::MeshSolver mesh_solver;
+    std::vector<lvkb200::Feature> features;  // m_TrackedFeatures
+    bool frame_initialized = false;
+    int det_w = 0, det_h = 0;
+    float tracking_stability = 0.f, scene_quality = 0.f, trust_factor = 0.f;
+
+    // ---- m_FrameQueue: device-resident ring of full-resolution frames
+    struct QueuedFrame
+    {
+        lvkb200::DeviceBuffer buf;
+        size_t pitch = 0;
+        int w = 0, h = 0;
+        lvkb200_format format = LVKB200_UNKNOWN;
+        uint64_t timestamp = 0;
+    };
+    std::vector<QueuedFrame> ring;
+    size_t ring_start = 0, ring_size = 0;
+    cudaEvent_t input_copied = nullptr;  // the caller's (host) frame has been consumed
+
+    // ---- per-stage CUDA events of the last submit (ingest, pyramid, fast, lk, estimate, remap)
+    cudaEvent_t stage_ev[LVKB200_STAGE_COUNT + 1][2] = {};
+    bool stage_used[LVKB200_STAGE_COUNT] = {};
+
+    // ---- debug taps of the last submit
+    std::vector<uint8_t> dbg_det, dbg_lk_status, dbg_inliers;
+    std::vector<lvkb200_keypoint> dbg_detected, dbg_propagated;
+    std::vector<float> dbg_lk_matched, dbg_tracked, dbg_matched, dbg_motion, dbg_correction;
+    std::vector<int32_t> dbg_fast_counts;
+    double dbg_h[9] = {}, dbg_t[9] = {};
+    bool dbg_has_h = false, dbg_has_t = false;
+
     lvkb200_status configure(const lvkb200_settings& s);
     lvkb200_status restart();
     lvkb200_status reset_context();
-    bool ready() const;
+    bool ready() const { return ring_size == ring.size() && !ring.empty(); }
     void stable_region(int fw, int fh, int* x, int* y, int* w, int* h) const;
     lvkb200_status submit(const void* frame, size_t pitch, int width, int height, lvkb200_format format,
                           uint64_t timestamp, lvkb200_memspace frame_space, void* out, size_t out_pitch,
@@ -30,6 +82,17 @@ struct lvkb200_stream
     lvkb200_status debug_fetch(lvkb200_debug_item which, void* buffer, size_t capacity, size_t* size);
     lvkb200_status stage_times(float* times);
     void release();
+
+    // FrameTracker::track on the frame in `slot`; fills motion (empty == nullopt).
+    lvkb200_status track(const QueuedFrame& frame, lvkb200::Mesh& motion, bool* has_motion);
+    lvkb200_status ensure_points(int n);
+    lvkb200_status run_lk(const std::vector<float>& pts, std::vector<float>& matched, std::vector<uint8_t>& status);
+    lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold,
+                                  double h[9], std::vector<uint8_t>& mask, bool* found);
+    lvkb200_status apply_mesh(const QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,
+                              lvkb200_memspace out_space);
+    void stage_begin(int stage);
+    void stage_end(int stage);
 
     // Makes a device view of a caller frame: device memory is used in place, host memory is copied
     // (async, on this stream) into stage_in with a 16-byte aligned pitch.

@@ -1,0 +1,155 @@
+"""Free-running parity: lvkb200 StabilizationFilter (C-ABI, CUDA) vs the oracle on the same synthetic clip.
+
+What is asserted, per frame:
+  * output cadence (empty frames while the look-ahead queue fills), timestamps, QA state;
+  * detection image bit-exact; FAST/grid feature list bit-exact while the two states are identical;
+  * LK status identical, matched points <= 0.01 px; inlier masks identical (clean clip);
+  * estimated homography within the stated corner-displacement bound of cv2's USAC model;
+  * the remap inside the pipeline is bit-exact GIVEN the pipeline's own transform (oracle remap of the queued frame
+    with the GPU's dst->src transform), and the final pixels are compared to the oracle's final pixels as a report.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _corner_disp(A, B, w, h):
+    c = np.array([[0, 0, 1], [w, 0, 1], [0, h, 1], [w, h, 1]], dtype=np.float64).T
+    a, b = A @ c, B @ c
+    return float(np.abs(a[:2] / a[2] - b[:2] / b[2]).max())
+
+
+def _kp_array(tr):
+    return np.array(tr, dtype=np.float64).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("preset,res,frames", [("H", "1080p", 36), ("D", "720p", 30)])
+def test_free_running_vs_oracle(oracle, preset, res, frames):
+    import livevisionkit_b200 as L
+    from livevisionkit_b200 import _capi as K
+    from tools.synth import Clip
+
+    clip = Clip(res, "shake" if preset == "H" else "pan", frames=frames, fps=60 if preset == "H" else 30)
+    so = oracle.StabilizationSettings.obs_homography_preset() if preset == "H" else oracle.StabilizationSettings()
+    sg = L.StabilizationFilterSettings.obs_homography_preset() if preset == "H" else L.StabilizationFilterSettings()
+    ref = oracle.StabilizationFilter(so)
+    flt = L.StabilizationFilter(sg, device=0)
+    ref.restart()  # scene quality 1.0 -> the trust factor ramps up immediately, corrections become non-trivial
+    flt.restart()
+    flt.stream.set_debug_capture(True)
+    w, h = clip.width, clip.height
+    det_w, det_h = so.detection_resolution
+    queue = []
+    stats = {"max_H_disp": 0.0, "max_lk": 0.0, "max_T_disp": 0.0, "pix_exact_given_T": [], "pix_vs_oracle": []}
+    in_sync = True
+    for i in range(frames):
+        frame = clip[i]
+        queue.append(frame)
+        out_ref, ts_ref = ref.apply(frame, oracle.BGR, 1000 + i)
+        tr = ref.trace
+        vf = flt.apply(L.VideoFrame(frame, 1000 + i, L.BGR))
+        res_g = flt.last_result
+        s = flt.stream
+
+        # cadence / metadata
+        assert (out_ref is None) == vf.empty(), f"frame {i}: output cadence differs"
+        assert bool(res_g.has_motion) == bool(tr["has_motion"]), f"frame {i}: has_motion differs"
+        assert abs(res_g.trust_factor - float(tr["trust"])) < 1e-6
+        assert abs(res_g.scene_quality - float(tr["scene_quality"])) < 1e-5
+
+        # K0
+        det = s.debug_fetch(K.DBG_DETECTION_IMAGE, np.uint8).reshape(det_h, det_w)
+        assert (det == tr["det"]).all(), f"frame {i}: detection image differs"
+
+        if "detected" in tr:
+            kd = s.debug_fetch(K.DBG_DETECTED, np.dtype([("x", "f4"), ("y", "f4"), ("r", "f4"), ("c", "i4")]))
+            a = _kp_array(tr["detected"])
+            assert len(kd) == len(a), f"frame {i}: feature count {len(kd)} vs {len(a)}"
+            g = np.stack([kd["x"], kd["y"], kd["r"], kd["c"]], axis=1).astype(np.float64)
+            same = bool((g == a).all())
+            if in_sync and not same:
+                # float LK differences (<= 1e-4 px) in propagated positions are the only legitimate source
+                assert np.abs(g[:, :2] - a[:, :2]).max() <= 0.01 and (g[:, 2:] == a[:, 2:]).all(), \
+                    f"frame {i}: feature lists diverged"
+            fc = s.debug_fetch(K.DBG_FAST_COUNTS, np.int32)
+            assert list(fc) == list(tr["fast_counts"]), f"frame {i}: FAST counts {list(fc)} vs {tr['fast_counts']}"
+        if "lk_status" in tr:
+            st = s.debug_fetch(K.DBG_LK_STATUS, np.uint8)
+            mt = s.debug_fetch(K.DBG_LK_MATCHED, np.float32).reshape(-1, 2)
+            assert (st == tr["lk_status"]).all(), f"frame {i}: LK status differs"
+            ok = st == 1
+            stats["max_lk"] = max(stats["max_lk"], float(np.abs(mt[ok] - tr["lk_out"][ok]).max()))
+        if "inliers" in tr:
+            inl = s.debug_fetch(K.DBG_INLIERS, np.uint8)
+            assert (inl == tr["inliers"]).all(), f"frame {i}: inlier mask differs"
+            assert abs(res_g.tracking_stability - float(tr["stability"])) < 1e-6
+        if "H" in tr:
+            Hg = s.debug_fetch(K.DBG_HOMOGRAPHY, np.float64).reshape(3, 3)
+            stats["max_H_disp"] = max(stats["max_H_disp"], _corner_disp(Hg, tr["H"], det_w, det_h))
+
+        if not vf.empty():
+            src = queue[i - ref.frame_delay()]
+            assert vf.timestamp == ts_ref == 1000 + i - ref.frame_delay()
+            if sg.motion_resolution == (2, 2):
+                T = s.debug_fetch(K.DBG_WARP_TRANSFORM, np.float64).reshape(3, 3)
+                stats["max_T_disp"] = max(stats["max_T_disp"], _corner_disp(T, tr["warp_T"], w, h))
+                given = oracle.remap_homography(src, T, so.background_colour, False)
+                stats["pix_exact_given_T"].append(float((given == vf.data).mean()))
+                assert np.abs(given.astype(np.int16) - vf.data.astype(np.int16)).max() <= 1
+            d = np.abs(out_ref.astype(np.int16) - vf.data.astype(np.int16))
+            stats["pix_vs_oracle"].append((int(d.max()), float((d <= 1).mean())))
+    print(f"[{preset} {res}] max LK |dpos| {stats['max_lk']:.2e} px; max H corner disp vs cv2 {stats['max_H_disp']:.4f} px "
+          f"(detection res); max warp-transform corner disp {stats['max_T_disp']:.4f} px (frame res); "
+          f"pixels bit-exact given own transform: min {min(stats['pix_exact_given_T'] or [1.0]):.6f}; "
+          f"final pixels vs oracle (max |d|, frac<=1LSB): {stats['pix_vs_oracle'][-3:]}")
+    assert stats["max_lk"] <= 0.01
+    assert stats["max_H_disp"] <= 0.25
+    assert min(stats["pix_exact_given_T"] or [1.0]) == 1.0
+    assert flt.frame_delay() == ref.frame_delay() == 10
+
+
+def test_host_and_device_frames_agree(oracle):
+    torch = pytest.importorskip("torch")
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    clip = Clip("720p", "shake", frames=14)
+    s = L.StabilizationFilterSettings.obs_homography_preset()
+    a, b = L.StabilizationFilter(s, 0), L.StabilizationFilter(s, 0)
+    for i in range(14):
+        f = clip[i]
+        va = a.apply(L.VideoFrame(f, i, L.BGR))
+        d = torch.from_numpy(f).cuda()
+        out = torch.empty_like(d)
+        torch.cuda.synchronize()
+        vb = b.apply(L.VideoFrame(d, i, L.BGR), output=out)
+        b.stream.sync()
+        assert va.empty() == vb.empty()
+        if not va.empty():
+            assert (va.data == vb.data.cpu().numpy()).all() and va.timestamp == vb.timestamp == i - 10
+
+
+def test_stabilize_output_off_is_a_pure_delay(oracle):
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    clip = Clip((640, 360), "shake", frames=13)
+    s = L.StabilizationFilterSettings.obs_homography_preset()
+    s.stabilize_output = False
+    f = L.StabilizationFilter(s, 0)
+    for i in range(13):
+        v = f.apply(L.VideoFrame(clip[i], i, L.BGR))
+        if i < 10:
+            assert v.empty()
+        else:
+            assert (v.data == clip[i - 10]).all() and v.timestamp == i - 10
+
+
+def test_configure_preconditions(oracle):
+    import livevisionkit_b200 as L
+    s = L.StabilizationFilterSettings()
+    s.min_tracking_quality = 1.5  # LVK_ASSERT_01 (StabilizationFilter.cpp:44)
+    with pytest.raises(L.LvkB200Error) as e:
+        L.StabilizationFilter(s, 0)
+    assert e.value.status == 1

@@ -1,0 +1,235 @@
+"""Stage-isolated parity of the tracking kernels (through the C-ABI) against the cv2-based oracle:
+K0 detection image (bit-exact), K2 FAST keypoints (coordinates, order, response: bit-exact),
+K1+K4 pyramidal LK (status bit-exact, positions <= 0.01 px), K6a homography RANSAC (mask + H contract)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _clip(res, n=3, kind="shake"):
+    from tools.synth import Clip
+    return Clip(res, kind, frames=n)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K0
+
+
+@pytest.mark.parametrize("res,det", [("1080p", (480, 270)), ("4k", (480, 270)), ("720p", (480, 270)),
+                                     ("1080p", (256, 256)), ("720p", (256, 256)), ("4k", (256, 256)),
+                                     ((960, 540), (480, 270)), ((1440, 810), (480, 270)), ((480, 270), (480, 270))])
+def test_detection_image_bit_exact(gpu_stream, oracle, res, det):
+    frame = _clip(res, 1)[0]
+    for fmt in (oracle.BGR, oracle.RGB, oracle.YUV):
+        ref = oracle.detection_image(frame, fmt, det)
+        got = gpu_stream.detection_image(frame, fmt, det)
+        bad = int((ref != got).sum())
+        print(f"{res}->{det} fmt={fmt}: mismatching pixels {bad}")
+        assert bad == 0
+
+
+def test_detection_image_odd_sizes(gpu_stream, oracle):
+    rng = np.random.default_rng(3)
+    for (w, h, dw, dh) in [(963, 541, 480, 270), (1366, 768, 256, 256), (1000, 600, 333, 200)]:
+        frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = oracle.detection_image(frame, oracle.BGR, (dw, dh))
+        got = gpu_stream.detection_image(frame, oracle.BGR, (dw, dh))
+        assert (ref == got).all(), f"{w}x{h}->{dw}x{dh}: {(ref != got).sum()} mismatches"
+
+
+def test_detection_image_device_memory(gpu_stream, oracle):
+    torch = pytest.importorskip("torch")
+    frame = _clip("1080p", 1)[0]
+    d = torch.from_numpy(frame).cuda()
+    torch.cuda.synchronize()
+    got = gpu_stream.detection_image(d, oracle.BGR, (480, 270))
+    assert (got == oracle.detection_image(frame, oracle.BGR, (480, 270))).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2
+
+
+def _fast_ref(img, roi, thr):
+    x, y, w, h = roi
+    det = cv2.FastFeatureDetector_create(int(thr), True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    kps = det.detect(img[y:y + h, x:x + w], None)
+    return np.array([(k.pt[0], k.pt[1], k.response) for k in kps], dtype=np.float32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("thr", [10, 25, 60])
+def test_fast_bit_exact(gpu_stream, oracle, thr):
+    frame = _clip("1080p", 1)[0]
+    det = oracle.detection_image(frame, oracle.BGR, (480, 270))
+    for roi in [(0, 0, 240, 270), (240, 0, 240, 270), (0, 0, 480, 270), (17, 9, 101, 77)]:
+        ref = _fast_ref(det, roi, thr)
+        got = gpu_stream.fast_detect(det, roi, thr)
+        g = np.stack([got["x"], got["y"], got["response"]], axis=1) if len(got) else np.zeros((0, 3), np.float32)
+        print(f"thr={thr} roi={roi}: cv2 {len(ref)} gpu {len(g)}")
+        assert len(ref) == len(g)
+        assert (ref == g).all()  # coordinates, emission order and response
+
+
+def test_fast_random_noise(gpu_stream):
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (131, 203), dtype=np.uint8)
+    ref = _fast_ref(img, (0, 0, 203, 131), 20)
+    got = gpu_stream.fast_detect(img, (0, 0, 203, 131), 20)
+    g = np.stack([got["x"], got["y"], got["response"]], axis=1)
+    assert len(ref) == len(g) and (ref == g).all()
+
+
+def test_fast_flat_image_is_empty(gpu_stream):
+    img = np.full((64, 64), 128, dtype=np.uint8)
+    assert len(gpu_stream.fast_detect(img, (0, 0, 64, 64), 10)) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K1 + K4
+
+
+def _lk_ref(prev, nxt, pts):
+    lk = cv2.SparsePyrLKOpticalFlow_create(winSize=(11, 11), maxLevel=3,
+                                           crit=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 5, 0.01))
+    out, status, _ = lk.calc(prev, nxt, pts.reshape(-1, 1, 2).astype(np.float32), None)
+    return out.reshape(-1, 2), status.reshape(-1)
+
+
+def _final_oob(points, w, h):
+    """cv2-python always requests the error output, which adds one bounds test on the FINAL position
+    (lkpyramid.cpp, err branch); the reference's C++ call passes no err (FrameTracker.cpp:140-146), and so do we."""
+    p = points - 5.0
+    ix, iy = np.floor(p[:, 0]), np.floor(p[:, 1])
+    return (ix < -11) | (ix >= w) | (iy < -11) | (iy >= h)
+
+
+@pytest.mark.parametrize("det", [(480, 270), (256, 256)])
+def test_lk_parity(gpu_stream, oracle, det):
+    clip = _clip("1080p", 4)
+    a = oracle.detection_image(clip[0], oracle.BGR, det)
+    b = oracle.detection_image(clip[2], oracle.BGR, det)
+    kps = cv2.FastFeatureDetector_create(15, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16).detect(a, None)
+    pts = np.array([k.pt for k in kps], dtype=np.float32)
+    rng = np.random.default_rng(1)
+    # add border / flat-area probes and sub-pixel positions
+    extra = np.array([[0.0, 0.0], [det[0] - 1.0, det[1] - 1.0], [2.5, 100.25], [det[0] - 2.0, 3.0], [-3.0, 5.0]],
+                     dtype=np.float32)
+    pts = np.concatenate([pts + rng.uniform(-0.5, 0.5, pts.shape).astype(np.float32), extra])
+    ref, rstat = _lk_ref(a, b, pts)
+    got, gstat = gpu_stream.lk_track(a, b, pts)
+    explained = (rstat == 0) & (gstat == 1) & _final_oob(got, det[0], det[1])
+    mism = (rstat != gstat) & ~explained
+    both = (rstat == 1) & (gstat == 1)
+    err = np.abs(ref[both] - got[both]).max() if both.any() else 0.0
+    print(f"det={det}: {len(pts)} pts, status mismatches {int(mism.sum())} (+{int(explained.sum())} explained by the "
+          f"python-only err check), tracked {int(both.sum())}, max |dpos| = {err:.2e} px, "
+          f"bit-identical positions {float((ref[both] == got[both]).all(axis=1).mean()):.4f}")
+    assert mism.sum() == 0
+    assert err <= 0.01
+
+
+def test_lk_large_motion_and_flat(gpu_stream):
+    rng = np.random.default_rng(5)
+    a = cv2.GaussianBlur(rng.integers(0, 256, (270, 480)).astype(np.uint8), (0, 0), 2.0)
+    M = np.float32([[1, 0, 6.3], [0, 1, -4.1]])
+    b = cv2.warpAffine(a, M, (480, 270), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+    a[100:160, 200:300] = 77  # flat patch -> minEig rejection
+    b[100:160, 200:300] = 77
+    ys, xs = np.mgrid[8:262:12, 8:472:12]
+    pts = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32)
+    ref, rstat = _lk_ref(a, b, pts)
+    got, gstat = gpu_stream.lk_track(a, b, pts)
+    explained = (rstat == 0) & (gstat == 1) & _final_oob(got, 480, 270)
+    assert ((rstat != gstat) & ~explained).sum() == 0
+    both = (rstat == 1) & (gstat == 1)
+    assert both.sum() > 100 and (gstat == 0).sum() > 5
+    assert np.abs(ref[both] - got[both]).max() <= 0.01
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K6a
+
+
+def _corner_disp(H1, H2, w, h):
+    c = np.array([[0, 0, 1], [w, 0, 1], [0, h, 1], [w, h, 1]], dtype=np.float64).T
+    a = H1 @ c
+    b = H2 @ c
+    return float(np.abs(a[:2] / a[2] - b[:2] / b[2]).max())
+
+
+def _err2_f32(H, p, q):
+    m = H.astype(np.float32).reshape(9)
+    x, y = p[:, 0], p[:, 1]
+    z = np.float32(1.0) / (m[6] * x + m[7] * y + m[8])
+    dx = q[:, 0] - (m[0] * x + m[1] * y + m[2]) * z
+    dy = q[:, 1] - (m[3] * x + m[4] * y + m[5]) * z
+    return dx * dx + dy * dy
+
+
+@pytest.mark.parametrize("noise,outliers", [(0.0, 0.0), (0.05, 0.0), (0.1, 0.15), (0.3, 0.3)])
+def test_homography_contract(gpu_stream, oracle, noise, outliers):
+    rng = np.random.default_rng(int(noise * 100) + int(outliers * 1000))
+    n, w, h, thr = 1200, 480, 270, 3.0
+    p = np.stack([rng.uniform(5, w - 5, n), rng.uniform(5, h - 5, n)], axis=1).astype(np.float32)
+    Ht = np.array([[1.002, -0.006, 2.4], [0.0055, 0.999, -1.7], [2e-6, -1e-6, 1.0]])
+    ph = np.concatenate([p, np.ones((n, 1), np.float32)], axis=1).astype(np.float64) @ Ht.T
+    q = (ph[:, :2] / ph[:, 2:]).astype(np.float32) + rng.normal(0, noise, (n, 2)).astype(np.float32)
+    n_out = int(outliers * n)
+    q[:n_out] += rng.uniform(-40, 40, (n_out, 2)).astype(np.float32)
+    Hc, mc = cv2.findHomography(p.reshape(-1, 1, 2), q.reshape(-1, 1, 2), oracle.usac_params(thr))
+    Hg, mg = gpu_stream.find_homography(p, q, thr)
+    mc = mc.reshape(-1).astype(np.uint8)
+    # (1) our mask is exactly the thresholded float32 forward error of OUR returned H
+    assert ((_err2_f32(Hg, p, q) < np.float32(thr * thr)).astype(np.uint8) == mg).all()
+    # (2) masks agree with cv2 except points within epsilon of the threshold under either model
+    e_c, e_g = np.sqrt(_err2_f32(Hc, p, q)), np.sqrt(_err2_f32(Hg, p, q))
+    borderline = (np.abs(e_c - thr) < 0.25) | (np.abs(e_g - thr) < 0.25)
+    hard = (mc != mg) & ~borderline
+    disp = _corner_disp(Hc, Hg, w, h)
+    print(f"noise={noise} outliers={outliers}: inliers cv2 {int(mc.sum())} gpu {int(mg.sum())}, mask mismatches "
+          f"{int((mc != mg).sum())} ({int(hard.sum())} not borderline), corner displacement vs cv2 {disp:.4f} px, "
+          f"vs truth: cv2 {_corner_disp(Hc, Ht, w, h):.4f} gpu {_corner_disp(Hg, Ht, w, h):.4f}")
+    assert hard.sum() == 0
+    # (3) H within the estimator's own input-order variance (<= ~0.2 px on noisy data)
+    assert disp <= (1e-3 if noise == 0.0 else 0.25)
+    assert abs(Hg[2, 2] - 1.0) < 1e-12
+
+
+def test_homography_degenerate_is_no_model(gpu_stream):
+    import livevisionkit_b200 as L
+    t = np.linspace(0, 400, 100, dtype=np.float32)
+    p = np.stack([t, 0.5 * t + 3], axis=1).astype(np.float32)  # collinear (cv2 returns None: SURVEY App. B12)
+    with pytest.raises(L.LvkB200Error) as e:
+        gpu_stream.find_homography(p, p + 1.0, 3.0)
+    assert e.value.status == 4  # LVKB200_ERR_NO_MODEL
+
+
+def test_homography_pure_translation(gpu_stream):
+    rng = np.random.default_rng(9)
+    p = np.stack([rng.uniform(0, 480, 75), rng.uniform(0, 270, 75)], axis=1).astype(np.float32)
+    q = p + np.float32([3.0, -2.0])
+    H, m = gpu_stream.find_homography(p, q, 3.0)
+    assert m.all()
+    assert np.allclose(H, [[1, 0, 3], [0, 1, -2], [0, 0, 1]], atol=1e-4)
+
+
+def test_local_motions_vs_oracle(gpu_stream, oracle):
+    import livevisionkit_b200 as L
+    s = L.Stream(L.StabilizationFilterSettings(), 0)  # defaults: 256x256, 2x2 mesh, local motions
+    rng = np.random.default_rng(4)
+    n = 900
+    p = np.stack([rng.uniform(0, 256, n), rng.uniform(0, 256, n)], axis=1).astype(np.float32)
+    q = (p * np.float32(1.003) + np.float32([1.2, -0.8]) + rng.normal(0, 0.05, (n, 2))).astype(np.float32)
+    q[:40] += 25.0
+    trk = oracle.FrameTracker(oracle.StabilizationSettings())
+    state = np.zeros(8, dtype=np.float32)
+    for it in range(3):  # warm-started over consecutive "frames"
+        motion_ref, inl_ref = trk.estimate_local_motions(p.tolist(), q.tolist())
+        state, offsets, mask = s.estimate_local_motions(p, q, state)
+        assert (mask == inl_ref).all()
+        assert np.abs(offsets.reshape(2, 2, 2) - motion_ref).max() * 256 <= 1e-3  # corner displacement in px
+        assert np.abs(state - trk.optimized_mesh).max() <= 1e-3
+    s.close()
