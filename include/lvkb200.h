@@ -192,6 +192,13 @@ lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item 
  * VideoFilter::timings() (Filters/VideoFilter.hpp:58).  Stage order: ingest, pyramid, fast, lk, estimate, remap. */
 #define LVKB200_STAGE_COUNT 6
 lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB200_STAGE_COUNT]);
+/* Running per-stage totals (microseconds of device time, CUDA events on the stream's own CUDA stream) and sample
+ * counts since the last reset — the Stopwatch history (Timing/Stopwatch.cpp:142-166) per stage.  Harvested lazily,
+ * so keeping them costs no synchronisation inside submit. */
+lvkb200_status lvkb200_stream_stage_totals_us(lvkb200_stream* s, double totals[LVKB200_STAGE_COUNT],
+                                              uint64_t counts[LVKB200_STAGE_COUNT], int reset);
+/* Number of CUDA kernels this library has launched in this process (all streams). */
+uint64_t lvkb200_kernel_launch_count(void);
 
 /* ---- stage-level entry points (used by the parity tests: oracle inputs -> one GPU stage) --------------------- */
 

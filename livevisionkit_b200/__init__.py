@@ -197,6 +197,13 @@ class Stream:
         _capi.check(self._lib.lvkb200_stream_stage_times_us(self._h, t))
         return dict(zip(STAGE_NAMES, [float(v) for v in t]))
 
+    def stage_totals_us(self, reset: bool = False):
+        """-> ({stage: total_us}, {stage: samples}) accumulated since the last reset (CUDA events, own stream)."""
+        t = (C.c_double * _capi.STAGE_COUNT)()
+        n = (C.c_uint64 * _capi.STAGE_COUNT)()
+        _capi.check(self._lib.lvkb200_stream_stage_totals_us(self._h, t, n, int(reset)))
+        return dict(zip(STAGE_NAMES, [float(v) for v in t])), dict(zip(STAGE_NAMES, [int(v) for v in n]))
+
     def set_debug_capture(self, enable: bool = True):
         _capi.check(self._lib.lvkb200_stream_set_debug_capture(self._h, int(enable)))
 

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/lvkb200.h).  Host C++ only: orchestration + calls into the kernel launchers.
 #include <algorithm>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "common.hpp"
@@ -27,6 +28,9 @@ void set_error(const char* fmt, ...)
 }
 
 static lvkb200_assert_handler g_assert_handler = nullptr;
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 void report_assert(const char* file, const char* function, const char* assertion)
 {
@@ -55,6 +59,8 @@ int lvkb200_device_count(void)
 }
 
 const char* lvkb200_last_error(void) { return last_error().c_str(); }
+
+uint64_t lvkb200_kernel_launch_count(void) { return launch_count(); }
 
 const char* lvkb200_status_string(lvkb200_status s)
 {
@@ -235,6 +241,14 @@ lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item 
 {
     LVKB_REQUIRE(s != nullptr && size != nullptr);
     return s->debug_fetch(which, buffer, capacity, size);
+}
+
+lvkb200_status lvkb200_stream_stage_totals_us(lvkb200_stream* s, double totals[LVKB200_STAGE_COUNT],
+                                              uint64_t counts[LVKB200_STAGE_COUNT], int reset)
+{
+    LVKB_REQUIRE(s != nullptr && totals != nullptr && counts != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->stage_totals(totals, counts, reset != 0);
 }
 
 lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB200_STAGE_COUNT])

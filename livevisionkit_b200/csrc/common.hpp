@@ -51,6 +51,10 @@ void report_assert(const char* file, const char* function, const char* assertion
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Process-wide count of kernels launched by this library (bench.py reports it as gpu_launches).
+void count_launches(int n);
+uint64_t launch_count();
+
 // ---- kernel launchers (one per reference stage) --------------------------------------------------------------------
 
 struct RemapParams

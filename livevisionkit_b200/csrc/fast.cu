@@ -213,8 +213,9 @@ lvkb200_status FastDetector::prepare(int width, int height)
     row_cap = width / 2 + 2;  // strict 8-neighbour NMS: no two adjacent pixels survive
     max_rows = height;
     out_cap = ((width + 1) / 2) * ((height + 1) / 2) + 1;
+    // No clearing needed (and none on the legacy stream, which would race with this stream's kernels):
+    // k_fast_score writes every pixel of a region before k_fast_nms_row reads it, and nothing else is read.
     LVKB_CUDA(d_score.ensure(score_pitch * height));
-    LVKB_CUDA(cudaMemset(d_score.ptr, 0, score_pitch * height));
     LVKB_CUDA(d_row_x.ensure(sizeof(uint16_t) * FAST_MAX_REGIONS * (size_t)max_rows * row_cap));
     LVKB_CUDA(d_row_s.ensure(sizeof(uint8_t) * FAST_MAX_REGIONS * (size_t)max_rows * row_cap));
     LVKB_CUDA(d_row_count.ensure(sizeof(int) * FAST_MAX_REGIONS * (size_t)max_rows));
@@ -256,6 +257,7 @@ lvkb200_status FastDetector::launch(cudaStream_t cs, const uint8_t* img, size_t 
     k_fast_gather<<<n, 256, sizeof(int) * (max_rows + 1), cs>>>(arg, max_rows, row_cap, d_row_x.as<uint16_t>(),
                                                                 d_row_s.as<uint8_t>(), d_row_count.as<int>(), out_cap,
                                                                 d_out.as<FastPoint>(), d_out_count.as<int>());
+    count_launches(3);
     LVKB_CUDA(cudaGetLastError());
     launched = n;
     return LVKB200_OK;

@@ -180,10 +180,12 @@ lvkb200_status IngestPlan::prepare(int src_w, int src_h, int dst_w, int dst_h, c
     LVKB_CUDA(d_xw.ensure(xwv.size() * sizeof(float)));
     LVKB_CUDA(d_yw.ensure(ywv.size() * sizeof(float)));
     LVKB_CUDA(cudaStreamSynchronize(cs));  // tables of a previous geometry may still be in use
-    LVKB_CUDA(cudaMemcpy(d_xtab.ptr, xt.data(), xt.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    LVKB_CUDA(cudaMemcpy(d_ytab.ptr, yt.data(), yt.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    LVKB_CUDA(cudaMemcpy(d_xw.ptr, xwv.data(), xwv.size() * sizeof(float), cudaMemcpyHostToDevice));
-    LVKB_CUDA(cudaMemcpy(d_yw.ptr, ywv.data(), ywv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // stream-ordered uploads (the stream is non-blocking: the legacy stream would not be ordered with its kernels)
+    LVKB_CUDA(cudaMemcpyAsync(d_xtab.ptr, xt.data(), xt.size() * sizeof(int2), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_ytab.ptr, yt.data(), yt.size() * sizeof(int2), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_xw.ptr, xwv.data(), xwv.size() * sizeof(float), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_yw.ptr, ywv.data(), ywv.size() * sizeof(float), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaStreamSynchronize(cs));  // the host vectors die at scope exit
     sw = src_w; sh = src_h; dw = dst_w; dh = dst_h;
     return LVKB200_OK;
 }
@@ -212,6 +214,7 @@ lvkb200_status IngestPlan::launch(cudaStream_t cs, const uint8_t* src, size_t pi
     k_ingest_gray_area<<<grid, THREADS, 0, cs>>>(src, pitch, stride, c0, c1, c2, dw, dh, d_xtab.as<int2>(),
                                                  d_xw.as<float>(), xcount, d_ytab.as<int2>(), d_yw.as<float>(), ycount,
                                                  fast, fast_scale, dst, dst_pitch);
+    count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;
 }

@@ -324,6 +324,7 @@ lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_
     }
     const dim3 grid(div_up(w[0] + 2 * P, 32), div_up(h[0] + 2 * P, 8), levels);
     k_scharr<<<grid, blk, 0, cs>>>(sa);
+    count_launches(levels + 1);
     LVKB_CUDA(cudaGetLastError());
     valid = true;
     return LVKB200_OK;
@@ -347,6 +348,7 @@ lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid&
     }
     a.max_level = prev.levels - 1;
     k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, n, d_next_pts, d_status);
+    count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;
 }

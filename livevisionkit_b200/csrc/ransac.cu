@@ -390,6 +390,7 @@ lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const flo
     k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, n, 0x9E3779B9u, d_models);
     k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, n, d_models, thr2, d_scores);
     k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, n, d_models, d_scores, thr2, RANSAC_REFINE_ITERS, d_result, d_mask);
+    count_launches(3);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;
 }

@@ -317,6 +317,7 @@ cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const
     else
         k_easu_remap<0, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
                                                                 p.height, T, nullptr, 0, 0, 0.0, 0.0, bg);
+    count_launches(1);
     return cudaGetLastError();
 }
 
@@ -334,6 +335,7 @@ cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float
     else
         k_easu_remap<1, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
                                                                 p.height, T, m, mesh_cols, mesh_rows, sx, sy, bg);
+    count_launches(1);
     return cudaGetLastError();
 }
 

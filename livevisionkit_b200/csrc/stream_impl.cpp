@@ -120,27 +120,66 @@ void lvkb200_stream::stable_region(int fw, int fh, int* x, int* y, int* w, int* 
 
 void lvkb200_stream::stage_begin(int stage)
 {
-    if (!stage_ev[stage][0])
+    cudaEvent_t* ev = stage_ev[stage_parity][stage];
+    if (!ev[0])
     {
-        cudaEventCreate(&stage_ev[stage][0]);
-        cudaEventCreate(&stage_ev[stage][1]);
+        cudaEventCreate(&ev[0]);
+        cudaEventCreate(&ev[1]);
     }
-    cudaEventRecord(stage_ev[stage][0], cs);
-    stage_used[stage] = true;
+    cudaEventRecord(ev[0], cs);
+    stage_used[stage_parity][stage] = true;
 }
 
-void lvkb200_stream::stage_end(int stage) { cudaEventRecord(stage_ev[stage][1], cs); }
+void lvkb200_stream::stage_end(int stage) { cudaEventRecord(stage_ev[stage_parity][stage][1], cs); }
+
+// Adds the (completed) stage durations recorded in slot `parity` to the running totals and frees the slot.
+void lvkb200_stream::harvest_stage_times(int parity)
+{
+    for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
+    {
+        if (!stage_used[parity][i]) continue;
+        stage_used[parity][i] = false;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, stage_ev[parity][i][0], stage_ev[parity][i][1]) == cudaSuccess)
+        {
+            stage_total_us[i] += static_cast<double>(ms) * 1000.0;
+            stage_count[i]++;
+        }
+        else
+            cudaGetLastError();
+    }
+}
+
+lvkb200_status lvkb200_stream::stage_totals(double* totals, uint64_t* counts, bool reset)
+{
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    harvest_stage_times(0);
+    harvest_stage_times(1);
+    for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
+    {
+        totals[i] = stage_total_us[i];
+        counts[i] = stage_count[i];
+        if (reset)
+        {
+            stage_total_us[i] = 0.0;
+            stage_count[i] = 0;
+        }
+    }
+    return LVKB200_OK;
+}
 
 lvkb200_status lvkb200_stream::stage_times(float* times)
 {
+    // durations of the LAST submit (slot of the previous parity), read without consuming them
     LVKB_CUDA(cudaStreamSynchronize(cs));
+    const int p = stage_parity;
     for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
     {
         times[i] = 0.0f;
-        if (stage_used[i] && stage_ev[i][0])
+        if (stage_used[p][i] && stage_ev[p][i][0])
         {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, stage_ev[i][0], stage_ev[i][1]) == cudaSuccess) times[i] = ms * 1000.0f;
+            if (cudaEventElapsedTime(&ms, stage_ev[p][i][0], stage_ev[p][i][1]) == cudaSuccess) times[i] = ms * 1000.0f;
             else cudaGetLastError();
         }
     }
@@ -439,7 +478,8 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     LVKB_REQUIRE(format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV);
     const size_t row = static_cast<size_t>(width) * 3;
     LVKB_REQUIRE(pitch >= row);
-    for (auto& u : stage_used) u = false;
+    stage_parity ^= 1;
+    harvest_stage_times(stage_parity);  // this slot holds the events of two submits ago: long complete
     dbg_has_h = dbg_has_t = false;
     dbg_detected.clear(); dbg_propagated.clear(); dbg_lk_matched.clear(); dbg_lk_status.clear(); dbg_tracked.clear();
     dbg_matched.clear(); dbg_inliers.clear(); dbg_motion.clear(); dbg_correction.clear(); dbg_fast_counts.clear();
@@ -604,12 +644,13 @@ void lvkb200_stream::release()
         if (e) cudaEventDestroy(e);
         e = nullptr;
     }
-    for (auto& pair : stage_ev)
-        for (auto& e : pair)
-        {
-            if (e) cudaEventDestroy(e);
-            e = nullptr;
-        }
+    for (auto& slot : stage_ev)
+        for (auto& pair : slot)
+            for (auto& e : pair)
+            {
+                if (e) cudaEventDestroy(e);
+                e = nullptr;
+            }
 }
 
 lvkb200_status lvkb200_stream::stage_frame_in(const void* p, size_t pitch, int w, int h, int ch, lvkb200_memspace space,

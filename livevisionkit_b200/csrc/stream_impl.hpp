@@ -60,8 +60,14 @@ struct lvkb200_stream
     cudaEvent_t input_copied = nullptr;  // the caller's (host) frame has been consumed
 
     // ---- per-stage CUDA events of the last submit (ingest, pyramid, fast, lk, estimate, remap)
-    cudaEvent_t stage_ev[LVKB200_STAGE_COUNT + 1][2] = {};
-    bool stage_used[LVKB200_STAGE_COUNT] = {};
+    // Double-buffered by frame parity so that totals can be harvested two frames late without any extra sync.
+    cudaEvent_t stage_ev[2][LVKB200_STAGE_COUNT][2] = {};
+    bool stage_used[2][LVKB200_STAGE_COUNT] = {};
+    int stage_parity = 0;
+    double stage_total_us[LVKB200_STAGE_COUNT] = {};
+    uint64_t stage_count[LVKB200_STAGE_COUNT] = {};
+    void harvest_stage_times(int parity);
+    lvkb200_status stage_totals(double* totals, uint64_t* counts, bool reset);
 
     // ---- debug taps of the last submit
     std::vector<uint8_t> dbg_det, dbg_lk_status, dbg_inliers;

@@ -1,0 +1,76 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/lvkb200.h declares (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "lvkb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lvkb200_[a-z0-9_]+)\s*\(", text)) - {"lvkb200_assert_handler"})
+
+
+def test_library_exports_every_declared_symbol():
+    from livevisionkit_b200 import _capi
+    lib = _capi.load()
+    declared = _declared_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/lvkb200.h but not exported by liblvkb200.so"
+    assert sorted(_capi.SYMBOLS) == declared, "ctypes table and header disagree"
+
+
+def test_abi_version_and_strings():
+    from livevisionkit_b200 import _capi
+    lib = _capi.load()
+    assert lib.lvkb200_abi_version() == 1
+    assert lib.lvkb200_status_string(0) == b"ok"
+    assert b"device" in lib.lvkb200_status_string(3)
+
+
+def test_settings_defaults_match_reference_values():
+    """StabilizationFilterSettings{} (Filters/StabilizationFilter.hpp:28-39 + bases) and the OBS Homography preset
+    (VSFilter.cpp:269-280), as returned by the library and as mirrored in Python."""
+    import livevisionkit_b200 as L
+    from livevisionkit_b200 import _capi
+    lib = _capi.load()
+    s = _capi.Settings()
+    lib.lvkb200_settings_default(C.byref(s))
+    py = L.StabilizationFilterSettings().to_c()
+    for name, _ in _capi.Settings._fields_:
+        a, b = getattr(s, name), getattr(py, name)
+        if name == "background_colour":
+            assert list(a) == list(b) == [255.0, 0.0, 255.0, 0.0]
+        else:
+            assert a == b, name
+    assert (s.detection_resolution_width, s.detection_resolution_height) == (256, 256)
+    assert s.track_local_motions == 1 and s.min_motion_samples == 75 and s.predictive_samples == 10
+    assert abs(s.acceptance_threshold - 8.0) < 1e-6 and abs(s.min_scene_quality - 0.8) < 1e-6
+    lib.lvkb200_settings_obs_homography(C.byref(s))
+    ph = L.StabilizationFilterSettings.obs_homography_preset().to_c()
+    for name, _ in _capi.Settings._fields_:
+        if name != "background_colour":
+            assert getattr(s, name) == getattr(ph, name), name
+    assert (s.detection_resolution_width, s.detection_resolution_height) == (480, 270)
+    assert s.track_local_motions == 0 and abs(s.acceptance_threshold - 3.0) < 1e-6
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to create a stream (LVKB200_ERR_NO_DEVICE); it never computes on
+    the CPU and never imports the oracle."""
+    import livevisionkit_b200 as L
+    if L.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(L.LvkB200Error) as e:
+        L.StabilizationFilter()
+    assert e.value.status == 3
+    for f in ("__init__.py", "_capi.py"):
+        src = open(os.path.join(ROOT, "livevisionkit_b200", f)).read()
+        assert not re.search(r"^\s*(from|import)\s+(oracle|cv2)\b", src, flags=re.M), f"{f} imports the checker"
+    for f in os.listdir(os.path.join(ROOT, "livevisionkit_b200", "csrc")):
+        src = open(os.path.join(ROOT, "livevisionkit_b200", "csrc", f)).read()
+        assert "oracle/" not in src.replace("oracle/easu_ref.c", "").replace("tests/", ""), f"{f} references the oracle"
