@@ -86,22 +86,46 @@ __global__ void __launch_bounds__(TW* TH)
         }
         if (has_arc9(dark) || has_arc9(bright))
         {
-            int a0 = t, b0 = t;  // a0: max over arcs of min d;  b0: max over arcs of min (-d)
+            // cornerScore<16> in OpenCV's own two-pass form (arcs [k..k+8] and [k+1..k+9] for even k, with its
+            // early-outs).  NOTE: the shorter "max over 16 arcs of min/-max" formulation is miscompiled by
+            // nvcc 12.9 for sm_100a (integer negation folded into VIMNMX3: tools/dbg/score_variants.cu shows 55 % wrong
+            // results on a B200), so keep this form.
+            int e[25];
 #pragma unroll
-            for (int s = 0; s < 16; s++)
+            for (int k = 0; k < 25; k++) e[k] = d[k & 15];
+#define D(i) e[(i)]
+            int a0 = t;
+#pragma unroll
+            for (int k = 0; k < 16; k += 2)
             {
-                int mn = d[s], mx = d[s];
-#pragma unroll
-                for (int j = 1; j < 9; j++)
-                {
-                    const int e = d[(s + j) & 15];
-                    mn = min(mn, e);
-                    mx = max(mx, e);
-                }
-                a0 = max(a0, mn);
-                b0 = max(b0, -mx);
+                int a = min(D(k + 1), D(k + 2));
+                a = min(a, D(k + 3));
+                if (a <= a0) continue;
+                a = min(a, D(k + 4));
+                a = min(a, D(k + 5));
+                a = min(a, D(k + 6));
+                a = min(a, D(k + 7));
+                a = min(a, D(k + 8));
+                a0 = max(a0, min(a, D(k)));
+                a0 = max(a0, min(a, D(k + 9)));
             }
-            result = max(a0, b0) - 1;
+            int b0 = -a0;
+#pragma unroll
+            for (int k = 0; k < 16; k += 2)
+            {
+                int b = max(D(k + 1), D(k + 2));
+                b = max(b, D(k + 3));
+                b = max(b, D(k + 4));
+                b = max(b, D(k + 5));
+                if (b >= b0) continue;
+                b = max(b, D(k + 6));
+                b = max(b, D(k + 7));
+                b = max(b, D(k + 8));
+                b0 = min(b0, max(b, D(k)));
+                b0 = min(b0, max(b, D(k + 9)));
+            }
+#undef D
+            result = -b0 - 1;
         }
     }
     score[(size_t)(rg.y + ly) * score_pitch + rg.x + lx] = (uint8_t)result;
