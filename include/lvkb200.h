@@ -236,9 +236,12 @@ lvkb200_status lvkb200_fast_detect(lvkb200_stream* s, const uint8_t* image, int 
                                    int capacity, int* count);
 
 /* cv::SparsePyrLKOpticalFlow((11,11), 3, {COUNT+EPS,5,0.01})::calc as configured at
- * Vision/FrameTracker.cpp:41-48 and called at :140-146.  Host buffers. */
+ * Vision/FrameTracker.cpp:41-48 and called at :140-146.  Host buffers.
+ * call_index = number of calc() calls already made on the same tracker object: upstream OpenCV squares the object's
+ * TermCriteria::epsilon in place on every call, and the reference reuses one m_OpticalTracker for all frames, so the
+ * (n+1)-th call stops on |delta|^2 <= 0.01^(2^(n+1)).  lvkb200_stream_submit advances this per stream by itself. */
 lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const uint8_t* next, int width, int height,
-                                const float* points, int count, float* matched, uint8_t* status);
+                                const float* points, int count, int call_index, float* matched, uint8_t* status);
 
 /* FrameTracker::estimate_global_motion's cv::findHomography(..., UsacParams) (Vision/FrameTracker.cpp:337-359).
  * Host buffers; h_out row-major 3x3 (h33 == 1); mask[i] = 1 <=> reprojection error < threshold. */

@@ -277,7 +277,7 @@ class Stream:
                             count=n.value)
         return arr.copy()
 
-    def lk_track(self, prev: np.ndarray, nxt: np.ndarray, points):
+    def lk_track(self, prev: np.ndarray, nxt: np.ndarray, points, call_index: int = 0):
         p = np.ascontiguousarray(prev, dtype=np.uint8)
         q = np.ascontiguousarray(nxt, dtype=np.uint8)
         pts = _f32(points, (-1, 2))
@@ -286,7 +286,7 @@ class Stream:
         status = np.empty(n, dtype=np.uint8)
         _capi.check(self._lib.lvkb200_lk_track(self._h, p.ctypes.data_as(C.POINTER(C.c_uint8)),
                                                q.ctypes.data_as(C.POINTER(C.c_uint8)), p.shape[1], p.shape[0],
-                                               pts.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                               pts.ctypes.data_as(C.POINTER(C.c_float)), n, int(call_index),
                                                matched.ctypes.data_as(C.POINTER(C.c_float)),
                                                status.ctypes.data_as(C.POINTER(C.c_uint8))))
         return matched, status

@@ -83,7 +83,7 @@ SYMBOLS = {
     "lvkb200_warp_mesh_apply": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _fp, _i, _i, _u8p, _i, _dp]),
     "lvkb200_detection_image": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, _u8p, _i, _i]),
     "lvkb200_fast_detect": (C.c_int, [_vp, _u8p, _i, _i, _i, _i, _i, _i, _i, C.POINTER(KeyPoint), _i, C.POINTER(_i)]),
-    "lvkb200_lk_track": (C.c_int, [_vp, _u8p, _u8p, _i, _i, _fp, _i, _fp, _u8p]),
+    "lvkb200_lk_track": (C.c_int, [_vp, _u8p, _u8p, _i, _i, _fp, _i, _i, _fp, _u8p]),
     "lvkb200_find_homography": (C.c_int, [_vp, _fp, _fp, _i, C.c_float, _dp, _u8p]),
     "lvkb200_estimate_local_motions": (C.c_int, [_vp, _fp, _fp, _i, _fp, _fp, _u8p]),
 }

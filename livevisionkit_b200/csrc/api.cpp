@@ -397,7 +397,7 @@ lvkb200_status lvkb200_fast_detect(lvkb200_stream* s, const uint8_t* image, int 
 }
 
 lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const uint8_t* next, int width, int height,
-                                const float* points, int count, float* matched, uint8_t* status)
+                                const float* points, int count, int call_index, float* matched, uint8_t* status)
 {
     LVKB_REQUIRE(s != nullptr && prev != nullptr && next != nullptr);
     LVKB_REQUIRE(count == 0 || (points != nullptr && matched != nullptr && status != nullptr));
@@ -420,7 +420,8 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
         cuda_ok(dst.ensure(count));
     }
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dp.ptr, points, sizeof(float2) * count, cudaMemcpyHostToDevice, s->cs));
-    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dq.as<float2>(), dst.as<uint8_t>());
+    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dq.as<float2>(), dst.as<uint8_t>(),
+                                         lk_epsilon_for_call(std::max(call_index, 0)));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(matched, dq.ptr, sizeof(float2) * count, cudaMemcpyDeviceToHost, s->cs));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(status, dst.ptr, count, cudaMemcpyDeviceToHost, s->cs));
     cuda_ok(cudaStreamSynchronize(s->cs));

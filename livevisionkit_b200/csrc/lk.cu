@@ -115,7 +115,7 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 
 __global__ void __launch_bounds__(128)
     k_lk_track(LkArg a, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
-               uint8_t* __restrict__ status)
+               uint8_t* __restrict__ status, double epsilon_sq)
 {
     const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pt >= n) return;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128)
             nextPt.y += delta.y;
             out = make_float2(nextPt.x + half, nextPt.y + half);
 
-            if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= 0.01 * 0.01) break;
+            if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= epsilon_sq) break;
             if (j > 0 && fabs((double)(delta.x + prevDelta.x)) < 0.01 && fabs((double)(delta.y + prevDelta.y)) < 0.01)
             {
                 out.x -= delta.x * 0.5f;
@@ -330,8 +330,23 @@ lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_
     return LVKB200_OK;
 }
 
+double lk_epsilon_for_call(int call_index)
+{
+    // SparsePyrLKOpticalFlowImpl::calc clamps and SQUARES its member TermCriteria::epsilon in place on every call
+    // (upstream lkpyramid.cpp), and the reference keeps ONE tracker object for the life of the FrameTracker
+    // (m_OpticalTracker, FrameTracker.cpp:41-48), so call n stops on |delta|^2 <= 0.01^(2^(n+1)):
+    // 1e-4, 1e-8, 1e-16, ... and 0 from the 9th call on.  Reproduced, in double like the original.
+    double eps = 0.01;
+    for (int i = 0; i <= call_index && eps != 0.0; i++)
+    {
+        eps = std::min(std::max(eps, 0.0), 10.0);
+        eps *= eps;
+    }
+    return eps;
+}
+
 lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts, int n,
-                        float2* d_next_pts, uint8_t* d_status)
+                        float2* d_next_pts, uint8_t* d_status, double epsilon_sq)
 {
     if (n <= 0) return LVKB200_OK;
     LVKB_REQUIRE(prev.levels == next.levels && prev.levels > 0 && prev.w[0] == next.w[0] && prev.h[0] == next.h[0]);
@@ -347,7 +362,7 @@ lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid&
         a.h[l] = prev.h[l];
     }
     a.max_level = prev.levels - 1;
-    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, n, d_next_pts, d_status);
+    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, n, d_next_pts, d_status, epsilon_sq);
     count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;

@@ -25,8 +25,11 @@ struct LkPyramid
     void release();
 };
 
+// Squared stopping epsilon of the (call_index+1)-th calc() on one cv::SparsePyrLKOpticalFlow object (see lk.cu).
+double lk_epsilon_for_call(int call_index);
+
 // Tracks n points from `prev` to `next` (device arrays of float2 / uint8).
 lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts, int n,
-                        float2* d_next_pts, uint8_t* d_status);
+                        float2* d_next_pts, uint8_t* d_status, double epsilon_sq);
 
 }  // namespace lvkb200

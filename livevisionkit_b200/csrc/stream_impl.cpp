@@ -222,7 +222,8 @@ lvkb200_status lvkb200_stream::run_lk(const std::vector<float>& pts, std::vector
     std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
     LVKB_CUDA(cudaMemcpyAsync(d_pts_prev.ptr, h_pts_prev.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
     LVKB_TRY(lk_track(cs, pyr[cur ^ 1], pyr[cur], d_pts_prev.as<float2>(), n, d_pts_next.as<float2>(),
-                      d_status.as<uint8_t>()));
+                      d_status.as<uint8_t>(), lk_epsilon_for_call(lk_calls)));
+    lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
     LVKB_CUDA(cudaMemcpyAsync(h_pts_next.ptr, d_pts_next.ptr, sizeof(float2) * n, cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaMemcpyAsync(h_status.ptr, d_status.ptr, n, cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaStreamSynchronize(cs));

@@ -43,6 +43,7 @@ struct lvkb200_stream
     lvkb200::MeshSolver mesh_solver;
     std::vector<lvkb200::Feature> features;  // m_TrackedFeatures
     bool frame_initialized = false;
+    int lk_calls = 0;  // calc() calls made on this tracker's cv::SparsePyrLKOpticalFlow equivalent
     int det_w = 0, det_h = 0;
     float tracking_stability = 0.f, scene_quality = 0.f, trust_factor = 0.f;
 
