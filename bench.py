@@ -171,7 +171,8 @@ def main():
 
     # ---- synthetic clip (distinct frames: 330 x 6.2 MB = 2.05 GB > L2, so consecutive steps never re-hit lines)
     n_frames = args.warmup + args.steps
-    clip = Clip(RES, "shake", frames=n_frames, seed=42 + rank)
+    from tools.scaling import stream_seed
+    clip = Clip(RES, "shake", frames=n_frames, seed=stream_seed(rank))
     host_frames = [clip[i] for i in range(n_frames)]
     settings = L.StabilizationFilterSettings.obs_homography_preset()
 
@@ -231,20 +232,13 @@ def main():
     parity_fail = int(not np.array_equal(pinned_out[(n_frames - 1) % 4].numpy(), last_dev_out))
 
     # ======== reduce over ranks: max time, summed frames (one all_gather of the counter struct over NCCL) ========
+    from tools import scaling
     mine = torch.tensor([float(args.steps), dev_ms, e2e_ms, float(launches), float(parity_fail), wall * 1e3,
                          wall_e2e * 1e3, float(outputs)], dtype=torch.float64, device=dev)
-    if world > 1:
-        allc = torch.empty(world * mine.numel(), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allc, mine)
-        allc = allc.view(world, -1).cpu().numpy()
-    else:
-        allc = mine.view(1, -1).cpu().numpy()
+    agg = scaling.aggregate(scaling.gather_counters(mine))
     if rank == 0:
-        total_frames = float(allc[:, 0].sum())
-        t_dev = float(allc[:, 1].max())
-        t_e2e = float(allc[:, 2].max())
-        value = total_frames / (t_dev * 1e-3)
-        e2e = total_frames / (t_e2e * 1e-3)
+        t_dev, t_e2e = agg["dev_ms"], agg["e2e_ms"]
+        value, e2e = agg["value_fps"], agg["e2e_fps"]
         peaks, peak_kind = _peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         remap_us = totals["remap"] / max(counts["remap"], 1)
@@ -268,16 +262,16 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": WIDTH * HEIGHT * 3,
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 3, "ms_per_step": t_e2e / args.steps,
                     "note": "pinned host input -> lvk StabilizationFilter.apply -> pinned host output, every step"},
-            "gpu_launches": int(allc[:, 3].sum()),
+            "gpu_launches": agg["launches"],
             "roofline": {"bound": "hbm", "kernel": "k_easu_remap<homography>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "avg_kernel_us": remap_us, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "EASU is FP32-issue bound (~300 instr/px), not HBM bound; see DESIGN.md"},
             "stage_us": {k: (totals[k] / counts[k] if counts[k] else 0.0) for k in totals},
             "clocks": clocks,
-            "outputs": int(allc[:, 7].sum()),
-            "parity_failures": int(allc[:, 4].sum()),
-            "wall_ms_per_step": float(allc[:, 5].max()) / args.steps,
+            "outputs": agg["outputs"],
+            "parity_failures": agg["parity_failures"],
+            "wall_ms_per_step": agg["wall_ms"] / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
