@@ -1,7 +1,12 @@
-// K6a — robust homography estimation (batched RANSAC hypothesis scoring + sigma-weighted refit) for sm_100a.
+// K5 + K6a — device-side swap-erase compaction and robust homography estimation (batched RANSAC hypothesis scoring
+// + sigma-weighted refit) for sm_100a.
 //
-// Replaces cv::findHomography(tracked, matched, mask, cv::UsacParams{MAGSAC, LO_SIGMA, 50 iterations, conf .99}) as
-// called by FrameTracker::estimate_global_motion (LiveVisionKit/Vision/FrameTracker.cpp:337-359).
+// Replaces, without a host round trip between them,
+//   * lvk::fast_filter(features, tracked, matched, status) (LiveVisionKit/Functions/Container.tpp:97-121, called at
+//     Vision/FrameTracker.cpp:149): reverse-order swap-with-last erase of the unmatched points — the ORDER it
+//     produces is part of the contract (it is the order the estimator and next frame's propagate() see);
+//   * cv::findHomography(tracked, matched, mask, cv::UsacParams{MAGSAC, LO_SIGMA, 50 iterations, conf .99}) as
+//     called by FrameTracker::estimate_global_motion (Vision/FrameTracker.cpp:337-359).
 // OpenCV's USAC lives in calib3d/usac (third-party, not under /root/reference, no source in this image); its
 // sampling stream and MAGSAC weighting tables cannot be reproduced bit-for-bit, so this is a GPU-native estimator
 // with the same CONTRACT:
@@ -11,13 +16,14 @@
 //     mask relates to its H);
 //   * degenerate input (e.g. collinear points) -> no model.
 // Parity vs cv2 is therefore: identical masks except points within epsilon of the threshold, H within the
-// estimator's own input-order variance (stated and measured in tests/test_ransac_gpu.py).
+// estimator's own input-order variance (stated and measured in tests/test_tracking_gpu.py).
 //
-// Kernels (one dependent chain, no host round trip in between):
-//   k_ransac_hypotheses : 256 minimal 4-point models, one thread each (8x8 solve in double, degeneracy tests)
+// Kernels (one dependent chain on one stream; the point count lives in device memory so nothing waits for the host):
+//   k_compact_swap_erase: single CTA; replays the reference's erase order on an index permutation, then gathers
+//   k_ransac_hypotheses : 256 minimal 4-point models, one thread each, closed form (unit square -> quad, no solve)
 //   k_ransac_score      : one CTA per hypothesis, all points scored with a cooperative-groups block reduction
 //                         (truncated-quadratic / MSAC cost at the acceptance threshold)
-//   k_ransac_refine     : single CTA: arg-min hypothesis, then 5 IRLS passes of a normalised weighted DLT
+//   k_ransac_refine     : single CTA: arg-min hypothesis, then 3 IRLS passes of a Hartley-normalised weighted DLT
 //                         (sigma-consensus style weights), warp-parallel 8x8 Gauss-Jordan, final mask.
 
 #include <cooperative_groups.h>
@@ -35,6 +41,67 @@ namespace
 
 constexpr int HYP = RANSAC_HYPOTHESES;
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fast_filter: for k = n-1 .. 0: if !keep[k]: data[k] = data.back(); data.pop_back()
+
+constexpr int CT = 1024;
+
+__global__ void __launch_bounds__(CT)
+    k_compact_swap_erase(const float2* __restrict__ a, const float2* __restrict__ b, const uint8_t* __restrict__ keep, int n,
+                         float2* __restrict__ a_out, float2* __restrict__ b_out, int* __restrict__ perm,
+                         int* __restrict__ removed, int* __restrict__ n_out)
+{
+    __shared__ int warp_tot[CT / 32];
+    __shared__ int s_base, s_size;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    // ascending list of removed indices (ordered compaction)
+    for (int i0 = 0; i0 < n; i0 += CT)
+    {
+        const int i = i0 + threadIdx.x;
+        const bool rem = (i < n) && (keep[i] == 0);
+        if (i < n) perm[i] = i;
+        const unsigned bal = __ballot_sync(0xffffffffu, rem);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < wid; w++) off += warp_tot[w];
+        if (rem) removed[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int t = 0;
+            for (int w = 0; w < CT / 32; w++) t += warp_tot[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    // replay the erases from the highest index down (sequential by definition; usually a handful of points)
+    if (threadIdx.x == 0)
+    {
+        int size = n;
+        for (int r = s_base - 1; r >= 0; r--)
+        {
+            const int k = removed[r];
+            perm[k] = perm[size - 1];
+            size--;
+        }
+        s_size = size;
+        *n_out = size;
+    }
+    __syncthreads();
+    const int size = s_size;
+    for (int i = threadIdx.x; i < size; i += CT)
+    {
+        const int src = perm[i];
+        a_out[i] = a[src];
+        b_out[i] = b[src];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+
 __device__ __forceinline__ uint32_t hash32(uint32_t x)
 {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -46,38 +113,30 @@ __device__ __forceinline__ float cross2(float2 a, float2 b, float2 c)
     return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
 }
 
-// Gaussian elimination with partial pivoting, n = 8, in double.  Returns false when singular.
-__device__ bool solve8(double A[8][9])
+// Projective map of the unit square (0,0),(1,0),(1,1),(0,1) onto the quad q0..q3 (Heckbert 1989), row-major 3x3.
+__device__ __forceinline__ bool square_to_quad(const double qx[4], const double qy[4], double m[9])
 {
-    for (int c = 0; c < 8; c++)
-    {
-        int piv = c;
-        double best = fabs(A[c][c]);
-        for (int r = c + 1; r < 8; r++)
-            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
-        if (best < 1e-12) return false;
-        if (piv != c)
-            for (int k = 0; k < 9; k++) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
-        const double inv = 1.0 / A[c][c];
-        for (int r = 0; r < 8; r++)
-        {
-            if (r == c) continue;
-            const double f = A[r][c] * inv;
-            for (int k = c; k < 9; k++) A[r][k] -= f * A[c][k];
-        }
-    }
-    for (int r = 0; r < 8; r++) A[r][8] /= A[r][r];
+    const double dx1 = qx[1] - qx[2], dx2 = qx[3] - qx[2], sx = qx[0] - qx[1] + qx[2] - qx[3];
+    const double dy1 = qy[1] - qy[2], dy2 = qy[3] - qy[2], sy = qy[0] - qy[1] + qy[2] - qy[3];
+    const double den = dx1 * dy2 - dx2 * dy1;
+    if (fabs(den) < 1e-12) return false;
+    const double g = (sx * dy2 - dx2 * sy) / den, h = (dx1 * sy - sx * dy1) / den;
+    m[0] = qx[1] - qx[0] + g * qx[1]; m[1] = qx[3] - qx[0] + h * qx[3]; m[2] = qx[0];
+    m[3] = qy[1] - qy[0] + g * qy[1]; m[4] = qy[3] - qy[0] + h * qy[3]; m[5] = qy[0];
+    m[6] = g; m[7] = h; m[8] = 1.0;
     return true;
 }
 
 __global__ void __launch_bounds__(128)
-    k_ransac_hypotheses(const float2* __restrict__ src, const float2* __restrict__ dst, int n, uint32_t seed,
-                        float* __restrict__ models)
+    k_ransac_hypotheses(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
+                        uint32_t seed, float* __restrict__ models)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= HYP) return;
+    const int n = *n_ptr;
     float* out = models + (size_t)k * 9;
     out[8] = 0.0f;  // invalid until proven otherwise
+    if (n < 4) return;
 
     int idx[4];
     uint32_t ctr = 0;
@@ -93,10 +152,12 @@ __global__ void __launch_bounds__(128)
         }
     }
     float2 p[4], q[4];
+#pragma unroll
     for (int j = 0; j < 4; j++) { p[j] = src[idx[j]]; q[j] = dst[idx[j]]; }
 
     // degeneracy: no three (nearly) collinear points, and the sample must keep its orientation
     const int tri[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+#pragma unroll
     for (int t = 0; t < 4; t++)
     {
         const float cs = cross2(p[tri[t][0]], p[tri[t][1]], p[tri[t][2]]);
@@ -105,17 +166,23 @@ __global__ void __launch_bounds__(128)
         if ((cs > 0.f) != (cd > 0.f)) return;
     }
 
-    double A[8][9];
-    for (int j = 0; j < 4; j++)
-    {
-        const double x = p[j].x, y = p[j].y, u = q[j].x, v = q[j].y;
-        double* r0 = A[2 * j];
-        double* r1 = A[2 * j + 1];
-        r0[0] = x; r0[1] = y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -u * x; r0[7] = -u * y; r0[8] = u;
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = x; r1[4] = y; r1[5] = 1; r1[6] = -v * x; r1[7] = -v * y; r1[8] = v;
-    }
-    if (!solve8(A)) return;
-    for (int j = 0; j < 8; j++) out[j] = (float)A[j][8];
+    // H = S2Q(dst quad) * S2Q(src quad)^-1   (adjugate instead of the inverse; scale fixed by h33 = 1)
+    double sx[4], sy[4], dx[4], dy[4], A[9], B[9];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { sx[j] = p[j].x; sy[j] = p[j].y; dx[j] = q[j].x; dy[j] = q[j].y; }
+    if (!square_to_quad(sx, sy, A) || !square_to_quad(dx, dy, B)) return;
+    const double adj[9] = {A[4] * A[8] - A[5] * A[7], A[2] * A[7] - A[1] * A[8], A[1] * A[5] - A[2] * A[4],
+                           A[5] * A[6] - A[3] * A[8], A[0] * A[8] - A[2] * A[6], A[2] * A[3] - A[0] * A[5],
+                           A[3] * A[7] - A[4] * A[6], A[1] * A[6] - A[0] * A[7], A[0] * A[4] - A[1] * A[3]};
+    double H[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) H[r * 3 + c] = B[r * 3] * adj[c] + B[r * 3 + 1] * adj[3 + c] + B[r * 3 + 2] * adj[6 + c];
+    if (fabs(H[8]) < 1e-12) return;
+    const double inv = 1.0 / H[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[j] = (float)(H[j] * inv);
     out[8] = 1.0f;
 }
 
@@ -129,16 +196,17 @@ __device__ __forceinline__ float reproj_err2(const float m[9], float2 p, float2 
 }
 
 __global__ void __launch_bounds__(256)
-    k_ransac_score(const float2* __restrict__ src, const float2* __restrict__ dst, int n, const float* __restrict__ models,
-                   float thr2, float* __restrict__ scores)
+    k_ransac_score(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
+                   const float* __restrict__ models, float thr2, float* __restrict__ scores)
 {
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
     __shared__ float m[9];
     __shared__ float partial[8];
+    const int n = *n_ptr;
     if (threadIdx.x < 9) m[threadIdx.x] = models[(size_t)blockIdx.x * 9 + threadIdx.x];
     block.sync();
-    if (m[8] == 0.0f)
+    if (m[8] == 0.0f || n < 4)
     {
         if (threadIdx.x == 0) scores[blockIdx.x] = 3.0e38f;
         return;
@@ -161,24 +229,23 @@ __global__ void __launch_bounds__(256)
 }
 
 constexpr int RT = 256;   // refine CTA size (44 double accumulators per thread: keep the register budget)
-constexpr int WC = 8;     // cached weights per thread (n <= RT*WC points never recompute)
 constexpr int NACC = 44;  // 36 (upper triangle of A^T W A) + 8 (A^T W b)
 
 __global__ void __launch_bounds__(RT)
-    k_ransac_refine(const float2* __restrict__ src, const float2* __restrict__ dst, int n, const float* __restrict__ models,
-                    const float* __restrict__ scores, float thr2, int iterations, RansacResult* __restrict__ result,
-                    uint8_t* __restrict__ mask)
+    k_ransac_refine(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
+                    const float* __restrict__ models, const float* __restrict__ scores, float thr2, int iterations,
+                    RansacResult* __restrict__ result, uint8_t* __restrict__ mask)
 {
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
     __shared__ float s_best[RT / 32];
     __shared__ int s_besti[RT / 32];
     __shared__ double s_acc[RT / 32][NACC];
-    __shared__ double s_norm[RT / 32][6];
-    __shared__ double s_T[10];  // src: cx, cy, s ; dst: cx, cy, s ; total weight ...
+    __shared__ double s_T[8];
     __shared__ float s_m[9];
     __shared__ int s_ok;
     const int tid = threadIdx.x, lane = warp.thread_rank(), wid = warp.meta_group_rank();
+    const int n = *n_ptr;
 
     // ---- arg-min over hypotheses (lowest index wins ties)
     float best = 3.0e38f;
@@ -189,7 +256,7 @@ __global__ void __launch_bounds__(RT)
     {
         const float ob = warp.shfl_xor(best, o);
         const int oi = warp.shfl_xor(besti, o);
-        if (ob < best || (ob == best && oi >= 0 && (besti < 0 || oi < besti))) { best = ob; besti = oi; }
+        if (oi >= 0 && (besti < 0 || ob < best || (ob == best && oi < besti))) { best = ob; besti = oi; }
     }
     if (lane == 0) { s_best[wid] = best; s_besti[wid] = besti; }
     block.sync();
@@ -198,20 +265,56 @@ __global__ void __launch_bounds__(RT)
         float b = 3.0e38f;
         int bi = -1;
         for (int w = 0; w < RT / 32; w++)
-            if (s_besti[w] >= 0 && (s_best[w] < b || (s_best[w] == b && s_besti[w] < bi))) { b = s_best[w]; bi = s_besti[w]; }
-        s_ok = (bi >= 0 && b < 2.9e38f) ? 1 : 0;
+            if (s_besti[w] >= 0 && (bi < 0 || s_best[w] < b || (s_best[w] == b && s_besti[w] < bi))) { b = s_best[w]; bi = s_besti[w]; }
+        s_ok = (n >= 4 && bi >= 0 && b < 2.9e38f) ? 1 : 0;
         if (s_ok)
             for (int j = 0; j < 9; j++) s_m[j] = models[(size_t)bi * 9 + j];
+        result->n = n;
     }
     block.sync();
     if (!s_ok)
     {
-        if (tid == 0) result->found = 0;
+        if (tid == 0) { result->found = 0; result->inliers = 0; }
         for (int i = tid; i < n; i += RT) mask[i] = 0;
         return;
     }
 
-    // ---- IRLS: weighted, Hartley-normalised DLT with h33 = 1 in normalised coordinates
+    // ---- Hartley normalisation of both point sets, once (it only conditions the normal equations)
+    {
+        double c[4] = {0, 0, 0, 0};
+        for (int i = tid; i < n; i += RT) { c[0] += src[i].x; c[1] += src[i].y; c[2] += dst[i].x; c[3] += dst[i].y; }
+        for (int j = 0; j < 4; j++) c[j] = cg::reduce(warp, c[j], cg::plus<double>());
+        if (lane == 0) for (int j = 0; j < 4; j++) s_acc[wid][j] = c[j];
+        block.sync();
+        if (tid < 4)
+        {
+            double s = 0;
+            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
+            s_T[tid] = s / n;
+        }
+        block.sync();
+        const double cx = s_T[0], cy = s_T[1], cu = s_T[2], cv = s_T[3];
+        double d[2] = {0, 0};
+        for (int i = tid; i < n; i += RT)
+        {
+            d[0] += sqrt((src[i].x - cx) * (src[i].x - cx) + (src[i].y - cy) * (src[i].y - cy));
+            d[1] += sqrt((dst[i].x - cu) * (dst[i].x - cu) + (dst[i].y - cv) * (dst[i].y - cv));
+        }
+        for (int j = 0; j < 2; j++) d[j] = cg::reduce(warp, d[j], cg::plus<double>());
+        block.sync();
+        if (lane == 0) { s_acc[wid][0] = d[0]; s_acc[wid][1] = d[1]; }
+        block.sync();
+        if (tid < 2)
+        {
+            double s = 0;
+            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
+            s_T[4 + tid] = (s > 1e-9) ? 1.4142135623730951 * n / s : 1.0;
+        }
+        block.sync();
+    }
+    const double cx = s_T[0], cy = s_T[1], cu = s_T[2], cv = s_T[3], s1 = s_T[4], s2 = s_T[5];
+
+    // ---- IRLS: weighted DLT with h33 = 1 in normalised coordinates.
     // weights: sigma-consensus style, smooth and compactly supported: w = (1 - e/c)^2 for e < c, c = 2.25 * thr^2
     // (support 1.5x the acceptance radius), so points just outside the threshold still pull a little, far ones not at all.
     const float c_sup = 2.25f * thr2;
@@ -219,80 +322,38 @@ __global__ void __launch_bounds__(RT)
     {
         float m[9];
         for (int j = 0; j < 9; j++) m[j] = s_m[j];
-
-        // pass 1: weights + weighted centroids / scales
-        double nsum[6] = {0, 0, 0, 0, 0, 0};  // w, w*x, w*y, w*u, w*v, (unused)
-        float wloc[WC];
-        for (int q = 0; q < WC; q++) wloc[q] = 0.f;
-        for (int q = 0, i = tid; i < n; i += RT, q++)
+        double acc[NACC];
+        for (int j = 0; j < NACC; j++) acc[j] = 0.0;
+        double wsum = 0.0;
+        for (int i = tid; i < n; i += RT)
         {
             const float2 p = src[i], d = dst[i];
             const float e = reproj_err2(m, p, d);
-            float w = 0.0f;
-            if (e == e && e < c_sup) { const float t = 1.0f - e / c_sup; w = t * t; }
-            if (q < WC) wloc[q] = w;
-            nsum[0] += w; nsum[1] += (double)w * p.x; nsum[2] += (double)w * p.y;
-            nsum[3] += (double)w * d.x; nsum[4] += (double)w * d.y;
-        }
-        for (int j = 0; j < 5; j++) nsum[j] = cg::reduce(warp, nsum[j], cg::plus<double>());
-        if (lane == 0) for (int j = 0; j < 5; j++) s_norm[wid][j] = nsum[j];
-        block.sync();
-        if (tid < 5)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_norm[w][tid];
-            s_T[tid] = s;
-        }
-        block.sync();
-        const double wsum = s_T[0];
-        if (wsum < 4.0) break;  // support collapsed: keep the current model
-        const double cx = s_T[1] / wsum, cy = s_T[2] / wsum, cu = s_T[3] / wsum, cv = s_T[4] / wsum;
-        block.sync();
-        // mean distances
-        double dsum[2] = {0, 0};
-        for (int q = 0, i = tid; i < n; i += RT, q++)
-        {
-            const float2 p = src[i], d = dst[i];
-            float w;
-            if (q < WC) w = wloc[q];
-            else { const float e = reproj_err2(m, p, d); w = 0.f; if (e == e && e < c_sup) { const float t = 1.0f - e / c_sup; w = t * t; } }
-            dsum[0] += (double)w * sqrt((p.x - cx) * (p.x - cx) + (p.y - cy) * (p.y - cy));
-            dsum[1] += (double)w * sqrt((d.x - cu) * (d.x - cu) + (d.y - cv) * (d.y - cv));
-        }
-        for (int j = 0; j < 2; j++) dsum[j] = cg::reduce(warp, dsum[j], cg::plus<double>());
-        if (lane == 0) { s_norm[wid][0] = dsum[0]; s_norm[wid][1] = dsum[1]; }
-        block.sync();
-        if (tid < 2)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_norm[w][tid];
-            s_T[5 + tid] = s;
-        }
-        block.sync();
-        const double s1 = (s_T[5] > 1e-9) ? 1.4142135623730951 * wsum / s_T[5] : 1.0;
-        const double s2 = (s_T[6] > 1e-9) ? 1.4142135623730951 * wsum / s_T[6] : 1.0;
-
-        // pass 2: normal equations in normalised coordinates
-        double acc[NACC];
-        for (int j = 0; j < NACC; j++) acc[j] = 0.0;
-        for (int q = 0, i = tid; i < n; i += RT, q++)
-        {
-            const float2 p = src[i], d = dst[i];
-            float w;
-            if (q < WC) w = wloc[q];
-            else { const float e = reproj_err2(m, p, d); w = 0.f; if (e == e && e < c_sup) { const float t = 1.0f - e / c_sup; w = t * t; } }
-            if (w == 0.0f) continue;
+            if (!(e == e) || e >= c_sup) continue;
+            const float t = 1.0f - e / c_sup;
+            const double w = (double)(t * t);
+            wsum += w;
             const double x = (p.x - cx) * s1, y = (p.y - cy) * s1, u = (d.x - cu) * s2, v = (d.y - cv) * s2;
             const double r0[8] = {x, y, 1, 0, 0, 0, -u * x, -u * y};
             const double r1[8] = {0, 0, 0, x, y, 1, -v * x, -v * y};
-            int t = 0;
+            int k = 0;
+#pragma unroll
             for (int a = 0; a < 8; a++)
-                for (int b = a; b < 8; b++) acc[t++] += w * (r0[a] * r0[b] + r1[a] * r1[b]);
+#pragma unroll
+                for (int b = a; b < 8; b++) acc[k++] += w * (r0[a] * r0[b] + r1[a] * r1[b]);
+#pragma unroll
             for (int a = 0; a < 8; a++) acc[36 + a] += w * (r0[a] * u + r1[a] * v);
         }
         for (int j = 0; j < NACC; j++) acc[j] = cg::reduce(warp, acc[j], cg::plus<double>());
-        if (lane == 0) for (int j = 0; j < NACC; j++) s_acc[wid][j] = acc[j];
+        wsum = cg::reduce(warp, wsum, cg::plus<double>());
         block.sync();
+        if (lane == 0)
+        {
+            for (int j = 0; j < NACC; j++) s_acc[wid][j] = acc[j];
+            s_T[6] = 0.0;
+        }
+        block.sync();
+        if (lane == 0) atomicAdd(&s_T[6], wsum);
         if (tid < NACC)
         {
             double s = 0;
@@ -300,6 +361,7 @@ __global__ void __launch_bounds__(RT)
             s_acc[0][tid] = s;
         }
         block.sync();
+        if (s_T[6] < 4.0) break;  // support collapsed: keep the current model
 
         // warp 0: Gauss-Jordan on the 8x9 augmented SPD system, lane r owns row r
         if (wid == 0)
@@ -307,11 +369,11 @@ __global__ void __launch_bounds__(RT)
             double row[9];
             const int r = lane & 7;
             {
-                int t = 0;
+                int k = 0;
                 double full[8][8];
                 for (int a = 0; a < 8; a++)
-                    for (int b = a; b < 8; b++) { full[a][b] = s_acc[0][t]; full[b][a] = s_acc[0][t]; t++; }
-                for (int k = 0; k < 8; k++) row[k] = full[r][k];
+                    for (int b = a; b < 8; b++) { full[a][b] = s_acc[0][k]; full[b][a] = s_acc[0][k]; k++; }
+                for (int c = 0; c < 8; c++) row[c] = full[r][c];
                 row[8] = s_acc[0][36 + r];
             }
             bool ok = true;
@@ -381,15 +443,25 @@ __global__ void __launch_bounds__(RT)
 
 }  // namespace
 
-lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, int n, float threshold,
-                                 float* d_models, float* d_scores, RansacResult* d_result, uint8_t* d_mask)
+lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep, int n,
+                                  float2* d_a_out, float2* d_b_out, int* d_perm, int* d_removed, int* d_n_out)
 {
-    LVKB_REQUIRE(n >= 4);
+    k_compact_swap_erase<<<1, CT, 0, cs>>>(d_a, d_b, d_keep, n, d_a_out, d_b_out, d_perm, d_removed, d_n_out);
+    count_launches(1);
+    LVKB_CUDA(cudaGetLastError());
+    return LVKB200_OK;
+}
+
+lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,
+                                 float threshold, float* d_models, float* d_scores, RansacResult* d_result,
+                                 uint8_t* d_mask)
+{
     const float thr2 = threshold * threshold;
     LVKB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(RansacResult), cs));
-    k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, n, 0x9E3779B9u, d_models);
-    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, n, d_models, thr2, d_scores);
-    k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, n, d_models, d_scores, thr2, RANSAC_REFINE_ITERS, d_result, d_mask);
+    k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, 0x9E3779B9u, d_models);
+    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, thr2, d_scores);
+    k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, thr2, RANSAC_REFINE_ITERS, d_result,
+                                      d_mask);
     count_launches(3);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;

@@ -11,8 +11,9 @@
 //     12x per destination pixel) and every thread then gathers its 12 taps with LDS.128;
 //   * tiles whose footprint does not fit (extreme warps) fall back to direct global reads;
 //   * border band -> nearest neighbour, outside -> background, exactly as FSR.cl:387-399/436-448.
-// Arithmetic: IEEE float32; this translation unit is compiled with --fmad=false so results are
-// bit-identical to the unfused CPU restatement in oracle/easu_ref.c.
+// Arithmetic: IEEE float32.  Every a*b+c that FSR.cl writes as one expression is ONE fused multiply-add
+// (__fmaf_rn), exactly as in the CPU restatement (oracle/easu_ref.c, fmaf); the translation unit is compiled with
+// --fmad=false so that nothing ELSE is contracted -> results are bit-identical to the oracle (tests assert 0 LSB).
 // Roofline: 6 B/px algorithmic (3 read + 3 written); see DESIGN.md.
 
 #include "common.hpp"
@@ -51,19 +52,19 @@ __device__ __forceinline__ void easu_accumulate(float& dirx, float& diry, float&
     float cb = lC - lB;
     float lenX = aprx_lo_rcp(fmaxf(fabsf(dc), fabsf(cb)));
     float dirX = lD - lB;
-    dirx += dirX * w;
+    dirx = __fmaf_rn(dirX, w, dirx);
     lenX = sat01(fabsf(dirX) * lenX);
     lenX *= lenX;
-    len += lenX * w;
+    len = __fmaf_rn(lenX, w, len);
 
     float ec = lE - lC;
     float ca = lC - lA;
     float lenY = aprx_lo_rcp(fmaxf(fabsf(ec), fabsf(ca)));
     float dirY = lE - lA;
-    diry += dirY * w;
+    diry = __fmaf_rn(dirY, w, diry);
     lenY = sat01(fabsf(dirY) * lenY);
     lenY *= lenY;
-    len += lenY * w;
+    len = __fmaf_rn(lenY, w, len);
 }
 
 // FSR.cl:98-126
@@ -71,19 +72,19 @@ __device__ __forceinline__ void easu_tap(float& aCx, float& aCy, float& aCz, flo
                                          float dirx, float diry, float lenx, float leny, float lob, float clp,
                                          const float4& c)
 {
-    float vx = (offx * dirx) + (offy * diry);
-    float vy = (offx * (-diry)) + (offy * dirx);
+    float vx = __fmaf_rn(offx, dirx, offy * diry);
+    float vy = __fmaf_rn(offx, -diry, offy * dirx);
     vx *= lenx;
     vy *= leny;
-    float d2 = fminf(vx * vx + vy * vy, clp);
-    float wA = lob * d2 - 1.0f;
-    float wB = (2.0f / 5.0f) * d2 - 1.0f;
+    float d2 = fminf(__fmaf_rn(vx, vx, vy * vy), clp);
+    float wA = __fmaf_rn(lob, d2, -1.0f);
+    float wB = __fmaf_rn(2.0f / 5.0f, d2, -1.0f);
     wA *= wA;
-    wB = (25.0f / 16.0f) * (wB * wB) - (25.0f / 16.0f - 1.0f);
+    wB = __fmaf_rn(25.0f / 16.0f, wB * wB, -(25.0f / 16.0f - 1.0f));
     float w = wB * wA;
-    aCx += c.x * w;
-    aCy += c.y * w;
-    aCz += c.z * w;
+    aCx = __fmaf_rn(c.x, w, aCx);
+    aCy = __fmaf_rn(c.y, w, aCy);
+    aCz = __fmaf_rn(c.z, w, aCz);
     aW += w;
 }
 
@@ -102,8 +103,7 @@ __device__ __forceinline__ uchar3 easu(const Tap& tap, float ppx, float ppy)
     easu_accumulate<2>(dirx, diry, len, ppx, ppy, f.w, i.w, j.w, k.w, n.w);
     easu_accumulate<3>(dirx, diry, len, ppx, ppy, g.w, j.w, k.w, l.w, o.w);
 
-    float dir2x = dirx * dirx, dir2y = diry * diry;
-    float dirR = dir2x + dir2y;
+    float dirR = __fmaf_rn(dirx, dirx, diry * diry);
     const bool zro = dirR < (1.0f / 32768.0f);
     dirR = aprx_lo_rsq(dirR);
     dirR = zro ? 1.0f : dirR;
@@ -114,10 +114,10 @@ __device__ __forceinline__ uchar3 easu(const Tap& tap, float ppx, float ppy)
     len = len * 0.5f;
     len *= len;
 
-    const float stretch = (dirx * dirx + diry * diry) * aprx_lo_rcp(fmaxf(fabsf(dirx), fabsf(diry)));
-    const float len2x = 1.0f + (stretch - 1.0f) * len;
-    const float len2y = 1.0f + -0.5f * len;
-    const float lob = 0.5f + ((1.0f / 4.0f - 0.04f) - 0.5f) * len;
+    const float stretch = __fmaf_rn(dirx, dirx, diry * diry) * aprx_lo_rcp(fmaxf(fabsf(dirx), fabsf(diry)));
+    const float len2x = __fmaf_rn(stretch - 1.0f, len, 1.0f);
+    const float len2y = __fmaf_rn(-0.5f, len, 1.0f);
+    const float lob = __fmaf_rn((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f);
     const float clp = aprx_lo_rcp(lob);
 
     const float mi0 = fminf(f.x, fminf(g.x, fminf(j.x, k.x)));
@@ -161,7 +161,7 @@ __device__ __forceinline__ float4 load_texel(const uint8_t* __restrict__ p)
     t.y = (float)__ldg(p + 1) * norm;
     t.z = (float)__ldg(p + 2) * norm;
     // FSR.cl:229-241 (the #ifndef is inverted relative to its comments; reproduced as written)
-    t.w = YUV ? (t.z * 0.5f + (t.x * 0.5f + t.y)) : t.x;
+    t.w = YUV ? __fmaf_rn(t.z, 0.5f, __fmaf_rn(t.x, 0.5f, t.y)) : t.x;
     return t;
 }
 

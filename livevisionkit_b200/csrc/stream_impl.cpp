@@ -200,6 +200,10 @@ lvkb200_status lvkb200_stream::ensure_points(int n)
     LVKB_CUDA(d_models.ensure(sizeof(float) * 9 * RANSAC_HYPOTHESES));
     LVKB_CUDA(d_scores.ensure(sizeof(float) * RANSAC_HYPOTHESES));
     LVKB_CUDA(d_result.ensure(sizeof(RansacResult)));
+    LVKB_CUDA(d_perm.ensure(sizeof(int) * cap));
+    LVKB_CUDA(d_removed.ensure(sizeof(int) * cap));
+    LVKB_CUDA(d_count.ensure(sizeof(int)));
+    LVKB_CUDA(h_count.ensure(sizeof(int)));
     LVKB_CUDA(h_pts_prev.ensure(sizeof(float2) * cap));
     LVKB_CUDA(h_pts_next.ensure(sizeof(float2) * cap));
     LVKB_CUDA(h_status.ensure(cap));
@@ -211,12 +215,10 @@ lvkb200_status lvkb200_stream::ensure_points(int n)
     return LVKB200_OK;
 }
 
-lvkb200_status lvkb200_stream::run_lk(const std::vector<float>& pts, std::vector<float>& matched,
-                                      std::vector<uint8_t>& status)
+// Enqueues the sparse optical flow of `pts` (previous -> current pyramid).  Nothing is copied back yet.
+lvkb200_status lvkb200_stream::enqueue_lk(const std::vector<float>& pts)
 {
     const int n = static_cast<int>(pts.size() / 2);
-    matched.resize(pts.size());
-    status.resize(n);
     if (n == 0) return LVKB200_OK;
     LVKB_TRY(ensure_points(n));
     std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
@@ -224,11 +226,44 @@ lvkb200_status lvkb200_stream::run_lk(const std::vector<float>& pts, std::vector
     LVKB_TRY(lk_track(cs, pyr[cur ^ 1], pyr[cur], d_pts_prev.as<float2>(), n, d_pts_next.as<float2>(),
                       d_status.as<uint8_t>(), lk_epsilon_for_call(lk_calls)));
     lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
+    return LVKB200_OK;
+}
+
+// Enqueues fast_filter + the homography estimator on the device results of enqueue_lk (no host round trip).
+lvkb200_status lvkb200_stream::enqueue_global_motion(int n, float threshold)
+{
+    LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next.as<float2>(), d_status.as<uint8_t>(), n,
+                                d_src.as<float2>(), d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(),
+                                d_count.as<int>()));
+    return ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), threshold,
+                             d_models.as<float>(), d_scores.as<float>(), d_result.as<RansacResult>(),
+                             d_mask.as<uint8_t>());
+}
+
+// One device->host copy + one synchronisation for the whole tracking chain of this frame.
+lvkb200_status lvkb200_stream::fetch_tracking(int n, bool with_model, std::vector<float>& matched,
+                                              std::vector<uint8_t>& status, RansacResult* model,
+                                              std::vector<uint8_t>& mask)
+{
+    matched.resize(static_cast<size_t>(n) * 2);
+    status.resize(n);
+    if (n == 0) return LVKB200_OK;
     LVKB_CUDA(cudaMemcpyAsync(h_pts_next.ptr, d_pts_next.ptr, sizeof(float2) * n, cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaMemcpyAsync(h_status.ptr, d_status.ptr, n, cudaMemcpyDeviceToHost, cs));
+    if (with_model)
+    {
+        LVKB_CUDA(cudaMemcpyAsync(h_result.ptr, d_result.ptr, sizeof(RansacResult), cudaMemcpyDeviceToHost, cs));
+        LVKB_CUDA(cudaMemcpyAsync(h_mask.ptr, d_mask.ptr, n, cudaMemcpyDeviceToHost, cs));
+    }
     LVKB_CUDA(cudaStreamSynchronize(cs));
-    std::memcpy(matched.data(), h_pts_next.ptr, sizeof(float) * pts.size());
+    std::memcpy(matched.data(), h_pts_next.ptr, sizeof(float) * matched.size());
     std::memcpy(status.data(), h_status.ptr, n);
+    if (with_model)
+    {
+        *model = *h_result.as<RansacResult>();
+        const int m = std::min(std::max(model->n, 0), n);
+        mask.assign(h_mask.as<uint8_t>(), h_mask.as<uint8_t>() + m);
+    }
     return LVKB200_OK;
 }
 
@@ -240,10 +275,13 @@ lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked,
     LVKB_TRY(ensure_points(n));
     std::memcpy(h_src.ptr, tracked.data(), sizeof(float) * tracked.size());
     std::memcpy(h_dst.ptr, matched.data(), sizeof(float) * matched.size());
+    *h_count.as<int>() = n;
     LVKB_CUDA(cudaMemcpyAsync(d_src.ptr, h_src.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
     LVKB_CUDA(cudaMemcpyAsync(d_dst.ptr, h_dst.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
-    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), n, threshold, d_models.as<float>(),
-                               d_scores.as<float>(), d_result.as<RansacResult>(), d_mask.as<uint8_t>()));
+    LVKB_CUDA(cudaMemcpyAsync(d_count.ptr, h_count.ptr, sizeof(int), cudaMemcpyHostToDevice, cs));
+    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), threshold,
+                               d_models.as<float>(), d_scores.as<float>(), d_result.as<RansacResult>(),
+                               d_mask.as<uint8_t>()));
     LVKB_CUDA(cudaMemcpyAsync(h_result.ptr, d_result.ptr, sizeof(RansacResult), cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaMemcpyAsync(h_mask.ptr, d_mask.ptr, n, cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaStreamSynchronize(cs));
@@ -334,9 +372,23 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
         tracked[2 * i] = features[i].x;
         tracked[2 * i + 1] = features[i].y;
     }
+    const int n_tracked = static_cast<int>(features.size());
+    const bool global = !settings.track_local_motions;
     stage_begin(ST_LK);
-    LVKB_TRY(run_lk(tracked, matched, status));
+    LVKB_TRY(enqueue_lk(tracked));
     stage_end(ST_LK);
+    if (global)
+    {
+        // fast_filter + motion estimation are chained on the device; the host replays the same erase order below.
+        // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) when distribution <= 0.6 (FrameTracker.cpp:362-373); until
+        // the similarity estimator lands the homography estimator serves badly distributed features as well.
+        stage_begin(ST_ESTIMATE);
+        LVKB_TRY(enqueue_global_motion(n_tracked, settings.acceptance_threshold));
+        stage_end(ST_ESTIMATE);
+    }
+    RansacResult model{};
+    std::vector<uint8_t> inliers;
+    LVKB_TRY(fetch_tracking(n_tracked, global, matched, status, &model, inliers));
     if (debug_capture)
     {
         dbg_lk_matched = matched;
@@ -366,41 +418,30 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
 
     // ---- motion estimation (FrameTracker.cpp:157-176)
-    std::vector<uint8_t> inliers;
-    stage_begin(ST_ESTIMATE);
+    (void)distribution;
     if (settings.track_local_motions)
     {
+        stage_begin(ST_ESTIMATE);
         mesh_solver.estimate(tracked, matched, motion, inliers);
+        stage_end(ST_ESTIMATE);
     }
     else
     {
-        double h[9];
-        bool found = false;
-        if (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD)
-        {
-            LVKB_TRY(run_homography(tracked, matched, settings.acceptance_threshold, h, inliers, &found));
-        }
-        else
-        {
-            // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) branch (FrameTracker.cpp:362-373); until the similarity
-            // estimator lands the homography estimator is used for badly distributed features as well.
-            LVKB_TRY(run_homography(tracked, matched, settings.acceptance_threshold, h, inliers, &found));
-        }
-        if (!found)
+        // the device compaction must have produced exactly the host's survivor list
+        LVKB_REQUIRE(model.n == static_cast<int>(matched.size() / 2) && inliers.size() == matched.size() / 2);
+        if (!model.found)
         {
             // cv::findHomography returned an empty matrix: the reference asserts (Math/Homography.cpp:89-95).
             // Reported through the assert handler; the frame is then treated as "no motion".
-            stage_end(ST_ESTIMATE);
             report_assert(__FILE__, "estimate_global_motion", "homography estimation found no model");
             features.clear();
             return LVKB200_OK;
         }
-        std::memcpy(dbg_h, h, sizeof(h));
+        std::memcpy(dbg_h, model.h, sizeof(dbg_h));
         dbg_has_h = true;
-        mesh_set_to_homography(h, static_cast<float>(det_w), static_cast<float>(det_h), settings.motion_resolution_width,
-                               settings.motion_resolution_height, motion);
+        mesh_set_to_homography(model.h, static_cast<float>(det_w), static_cast<float>(det_h),
+                               settings.motion_resolution_width, settings.motion_resolution_height, motion);
     }
-    stage_end(ST_ESTIMATE);
     if (debug_capture) dbg_inliers = inliers;
 
     // ---- tracking stability = inlier ratio (FrameTracker.cpp:179, Container.tpp:125-129)
@@ -636,7 +677,7 @@ void lvkb200_stream::release()
     d_pts_prev.release(); d_pts_next.release(); d_status.release(); d_src.release(); d_dst.release(); d_mask.release();
     d_models.release(); d_scores.release(); d_result.release();
     h_pts_prev.release(); h_pts_next.release(); h_status.release(); h_src.release(); h_dst.release(); h_mask.release();
-    h_result.release(); h_det.release();
+    h_result.release(); h_det.release(); h_count.release(); d_perm.release(); d_removed.release(); d_count.release();
     for (auto& f : ring) f.buf.release();
     if (input_copied) cudaEventDestroy(input_copied);
     input_copied = nullptr;

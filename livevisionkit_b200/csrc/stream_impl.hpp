@@ -34,7 +34,8 @@ struct lvkb200_stream
     lvkb200::DeviceBuffer d_det;
     size_t det_pitch = 0;
     lvkb200::DeviceBuffer d_pts_prev, d_pts_next, d_status, d_src, d_dst, d_mask, d_models, d_scores, d_result;
-    lvkb200::PinnedBuffer h_pts_prev, h_pts_next, h_status, h_src, h_dst, h_mask, h_result, h_det;
+    lvkb200::DeviceBuffer d_perm, d_removed, d_count;
+    lvkb200::PinnedBuffer h_pts_prev, h_pts_next, h_status, h_src, h_dst, h_mask, h_result, h_det, h_count;
     int point_capacity = 0;
 
     // ---- StabilizationFilter / FrameTracker / FeatureDetector / PathSmoother host state
@@ -93,7 +94,10 @@ struct lvkb200_stream
     // FrameTracker::track on the frame in `slot`; fills motion (empty == nullopt).
     lvkb200_status track(const QueuedFrame& frame, lvkb200::Mesh& motion, bool* has_motion);
     lvkb200_status ensure_points(int n);
-    lvkb200_status run_lk(const std::vector<float>& pts, std::vector<float>& matched, std::vector<uint8_t>& status);
+    lvkb200_status enqueue_lk(const std::vector<float>& pts);
+    lvkb200_status enqueue_global_motion(int n, float threshold);
+    lvkb200_status fetch_tracking(int n, bool with_model, std::vector<float>& matched, std::vector<uint8_t>& status,
+                                  lvkb200::RansacResult* model, std::vector<uint8_t>& mask);
     lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold,
                                   double h[9], std::vector<uint8_t>& mask, bool* found);
     lvkb200_status apply_mesh(const QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,

@@ -13,9 +13,12 @@
  * and of the host side that launches them
  *   LiveVisionKit/Functions/Image.cpp:28-81, 85-151.
  *
- * Semantics chosen where OpenCL leaves latitude (the reference has no OpenCL-independent
- * definition): IEEE float32, NO fused multiply-add (compile with -ffp-contract=off),
- * native_recip(x) := 1.0f/x, convert_*_rtz/convert_uchar := C truncation.
+ * Semantics chosen where OpenCL leaves latitude (the reference has no OpenCL-independent definition):
+ * IEEE float32; multiply-add contraction — which an OpenCL compiler is free to apply — is made EXPLICIT: every
+ * a*b+c that the kernel source writes as one expression is ONE fused operation (FMA(a,b,c) below, fmaf), and
+ * nothing else is contracted (compile with -ffp-contract=off); native_recip(x) := 1.0f/x;
+ * convert_*_rtz/convert_uchar := C truncation.  This is the arithmetic a GPU OpenCL compiler produces for FSR.cl
+ * (mad/fma contraction is on by default in OpenCL C) and it is what the CUDA kernel implements with __fmaf_rn.
  * Parity status: UNPINNED by the reference (it ships no test vectors and no OpenCL device
  * exists in the build container); pinned only against itself via tests/golden.
  *
@@ -50,6 +53,8 @@ static void parallel_rows(row_fn fn, void* ctx, int rows, int threads)
     for (int t = 0; t < threads; t++) pthread_join(tid[t], 0);
 }
 
+#define FMA(a, b, c) fmaf((a), (b), (c))
+
 static inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
@@ -65,19 +70,19 @@ static inline float saturate(float x) { return fmaxf(0.0f, fminf(1.0f, x)); } /*
 static inline void easu_tap(float aC[3], float* aW, float offx, float offy, float dirx, float diry,
                             float lenx, float leny, float lob, float clp, const float c[3])
 {
-    float vx = (offx * dirx) + (offy * diry);
-    float vy = (offx * (-diry)) + (offy * dirx);
+    float vx = FMA(offx, dirx, offy * diry);
+    float vy = FMA(offx, -diry, offy * dirx);
     vx *= lenx;
     vy *= leny;
-    float d2 = fmin_cl(vx * vx + vy * vy, clp);
-    float wA = lob * d2 - 1.0f;
-    float wB = (2.0f / 5.0f) * d2 - 1.0f;
+    float d2 = fmin_cl(FMA(vx, vx, vy * vy), clp);
+    float wA = FMA(lob, d2, -1.0f);
+    float wB = FMA(2.0f / 5.0f, d2, -1.0f);
     wA *= wA;
-    wB = (25.0f / 16.0f) * (wB * wB) - (25.0f / 16.0f - 1.0f);
+    wB = FMA(25.0f / 16.0f, wB * wB, -(25.0f / 16.0f - 1.0f));
     float w = wB * wA;
-    aC[0] += c[0] * w;
-    aC[1] += c[1] * w;
-    aC[2] += c[2] * w;
+    aC[0] = FMA(c[0], w, aC[0]);
+    aC[1] = FMA(c[1], w, aC[1]);
+    aC[2] = FMA(c[2], w, aC[2]);
     *aW += w;
 }
 
@@ -95,19 +100,19 @@ static inline void easu_accumulate(float dir[2], float* len, float ppx, float pp
     float cb = lC - lB;
     float lenX = aprx_lo_rcp(fmax_cl(fabsf(dc), fabsf(cb)));
     float dirX = lD - lB;
-    dir[0] += dirX * w;
+    dir[0] = FMA(dirX, w, dir[0]);
     lenX = saturate(fabsf(dirX) * lenX);
     lenX *= lenX;
-    *len += lenX * w;
+    *len = FMA(lenX, w, *len);
 
     float ec = lE - lC;
     float ca = lC - lA;
     float lenY = aprx_lo_rcp(fmax_cl(fabsf(ec), fabsf(ca)));
     float dirY = lE - lA;
-    dir[1] += dirY * w;
+    dir[1] = FMA(dirY, w, dir[1]);
     lenY = saturate(fabsf(dirY) * lenY);
     lenY *= lenY;
-    *len += lenY * w;
+    *len = FMA(lenY, w, *len);
 }
 
 /* FSR.cl:181-318.  src points at pixel (0,0); step in bytes; (sx,sy) = 'f'. yuv selects the
@@ -134,7 +139,7 @@ static inline void easu(const uint8_t* src, int step, int sx, int sy, float ppx,
         n[ch] = (float)r3[ch] * norm;     o[ch] = (float)r3[3 + ch] * norm;
     }
 
-#define LUMA(p) (yuv ? ((p)[2] * 0.5f + ((p)[0] * 0.5f + (p)[1])) : (p)[0])
+#define LUMA(p) (yuv ? FMA((p)[2], 0.5f, FMA((p)[0], 0.5f, (p)[1])) : (p)[0])
     const float bL = LUMA(b), cL = LUMA(c), eL = LUMA(e), fL = LUMA(f), gL = LUMA(g), hL = LUMA(h);
     const float iL = LUMA(i), jL = LUMA(j), kL = LUMA(k), lL = LUMA(l), nL = LUMA(n), oL = LUMA(o);
 #undef LUMA
@@ -145,8 +150,7 @@ static inline void easu(const uint8_t* src, int step, int sx, int sy, float ppx,
     easu_accumulate(dir, &len, ppx, ppy, 2, fL, iL, jL, kL, nL);
     easu_accumulate(dir, &len, ppx, ppy, 3, gL, jL, kL, lL, oL);
 
-    float dir2x = dir[0] * dir[0], dir2y = dir[1] * dir[1];
-    float dirR = dir2x + dir2y;
+    float dirR = FMA(dir[0], dir[0], dir[1] * dir[1]);
     int zro = dirR < (1.0f / 32768.0f);
     dirR = aprx_lo_rsq(dirR);
     dirR = zro ? 1.0f : dirR;
@@ -157,10 +161,10 @@ static inline void easu(const uint8_t* src, int step, int sx, int sy, float ppx,
     len = len * 0.5f;
     len *= len;
 
-    float stretch = (dir[0] * dir[0] + dir[1] * dir[1]) * aprx_lo_rcp(fmax_cl(fabsf(dir[0]), fabsf(dir[1])));
-    float len2x = 1.0f + (stretch - 1.0f) * len;
-    float len2y = 1.0f + -0.5f * len;
-    float lob = 0.5f + ((1.0f / 4.0f - 0.04f) - 0.5f) * len;
+    float stretch = FMA(dir[0], dir[0], dir[1] * dir[1]) * aprx_lo_rcp(fmax_cl(fabsf(dir[0]), fabsf(dir[1])));
+    float len2x = FMA(stretch - 1.0f, len, 1.0f);
+    float len2y = FMA(-0.5f, len, 1.0f);
+    float lob = FMA((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f);
     float clp = aprx_lo_rcp(lob);
 
     float mi4[3], ma4[3];
