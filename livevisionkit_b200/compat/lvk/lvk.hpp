@@ -1,0 +1,361 @@
+// lvk-compat — C++ mirror of the reference's filter interface for the stabilization path, forwarding to the C-ABI
+// (include/lvkb200.h).  Same names, argument meaning and error behaviour as
+//   LiveVisionKit/Filters/VideoFilter.hpp:32-61          lvk::VideoFilter (apply / alias / timings / filter)
+//   LiveVisionKit/Filters/StabilizationFilter.hpp:28-77  lvk::StabilizationFilterSettings, lvk::StabilizationFilter
+//   LiveVisionKit/Vision/FrameTracker.hpp:31-44, FeatureDetector.hpp:28-37, PathSmoother.hpp:29-39  settings bases
+//   LiveVisionKit/Utility/Configurable.hpp:27-44         lvk::Configurable<T>
+//   LiveVisionKit/Data/VideoFrame.hpp:25-79              lvk::VideoFrame (format, timestamp, width/height)
+//   LiveVisionKit/Directives.hpp:37-95                   lvk::context::assert_handler, LVK_ASSERT
+// The reference's VideoFrame derives from cv::UMat; OpenCV is not available in this image, so VideoFrame here owns /
+// views a plain packed 8-bit buffer (host or CUDA device memory) and cv::Size / cv::Scalar / cv::Rect are replaced by
+// layout-compatible minimal structs in lvk::cvlite (define LVK_COMPAT_USE_OPENCV to use the real ones).
+// Header-only; link with liblvkb200.so.
+#pragma once
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/lvkb200.h"
+
+#ifdef LVK_COMPAT_USE_OPENCV
+#include <opencv2/core.hpp>
+#endif
+
+namespace lvk
+{
+
+#ifdef LVK_COMPAT_USE_OPENCV
+namespace cvlite { using Size = cv::Size; using Size2f = cv::Size2f; using Scalar = cv::Scalar; using Rect = cv::Rect; }
+#else
+namespace cvlite
+{
+    struct Size { int width = 0, height = 0; Size() = default; Size(int w, int h) : width(w), height(h) {}
+                  bool operator==(const Size& o) const { return width == o.width && height == o.height; }
+                  bool operator!=(const Size& o) const { return !(*this == o); } };
+    struct Size2f { float width = 0, height = 0; Size2f() = default; Size2f(float w, float h) : width(w), height(h) {} };
+    struct Scalar { double val[4] = {0, 0, 0, 0}; Scalar() = default;
+                    Scalar(double a, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+                    double operator[](int i) const { return val[i]; } double& operator[](int i) { return val[i]; } };
+    struct Rect { int x = 0, y = 0, width = 0, height = 0; };
+}
+#endif
+
+// ---- Directives.hpp:37-95 ----------------------------------------------------------------------------------------
+namespace context
+{
+    // Directives.cpp:27-42: the default prints and aborts
+    inline std::function<void(std::string file, std::string function, std::string assertion)> assert_handler =
+        [](std::string file, std::string function, std::string assertion) {
+            std::fprintf(stderr, "LiveVisionKit failed %s@%s(..) ` %s ` \n", file.c_str(), function.c_str(), assertion.c_str());
+            std::abort();
+        };
+}
+
+#ifndef LVK_DISABLE_CHECKS
+#define LVK_ASSERT(assertion) \
+    if (!(assertion)) { lvk::context::assert_handler(__FILE__, __func__, #assertion); }
+#else
+#define LVK_ASSERT(assertion)
+#endif
+
+// ---- Data/VideoFrame.hpp:25-79 -------------------------------------------------------------------------------------
+struct VideoFrame
+{
+    enum Format { BGR, BGRA, RGB, RGBA, YUV, GRAY, UNKNOWN };
+
+    uint8_t* data = nullptr;   // packed 8-bit pixels (3 channels for every format the stabilizer accepts)
+    size_t step = 0;           // bytes per row
+    int cols = 0, rows = 0;
+    bool on_device = false;    // true: `data` is CUDA device memory (used in place, never copied through the host)
+    uint64_t timestamp = 0;
+    Format format = UNKNOWN;
+    int& width = cols; int& height = rows;
+
+    VideoFrame() = default;
+    explicit VideoFrame(const uint64_t ts) : timestamp(ts) {}
+    // view onto caller memory (no ownership)
+    VideoFrame(uint8_t* pixels, int w, int h, size_t row_step, Format fmt, uint64_t ts = 0, bool device = false)
+        : data(pixels), step(row_step), cols(w), rows(h), on_device(device), timestamp(ts), format(fmt) {}
+    VideoFrame(const VideoFrame& o) { *this = o; }
+    VideoFrame(VideoFrame&& o) noexcept { *this = std::move(o); }
+    VideoFrame& operator=(const VideoFrame& o)
+    {
+        if (this == &o) return *this;
+        storage = o.storage;
+        if (!o.storage.empty()) data = storage.data(); else data = o.data;
+        step = o.step; cols = o.cols; rows = o.rows; on_device = o.on_device; timestamp = o.timestamp; format = o.format;
+        return *this;
+    }
+    VideoFrame& operator=(VideoFrame&& o) noexcept
+    {
+        if (this == &o) return *this;
+        const bool owned = !o.storage.empty();
+        storage = std::move(o.storage);
+        data = owned ? storage.data() : o.data;
+        step = o.step; cols = o.cols; rows = o.rows; on_device = o.on_device; timestamp = o.timestamp; format = o.format;
+        o.release();
+        return *this;
+    }
+
+    bool empty() const { return data == nullptr || cols <= 0 || rows <= 0; }
+    void release() { storage.clear(); data = nullptr; step = 0; cols = rows = 0; on_device = false; }
+    // cv::UMat::create(rows, cols, CV_8UC3): (re)allocates an owned host buffer when the geometry differs
+    void create(int h, int w, int channels = 3)
+    {
+        if (!storage.empty() && h == rows && w == cols && step == static_cast<size_t>(w) * channels) return;
+        storage.assign(static_cast<size_t>(w) * channels * h, 0);
+        data = storage.data(); step = static_cast<size_t>(w) * channels; cols = w; rows = h; on_device = false;
+    }
+    bool has_known_format() const { return format != UNKNOWN; }
+
+private:
+    std::vector<uint8_t> storage;
+};
+typedef VideoFrame Frame;
+
+// ---- Timing/Stopwatch (subset used through VideoFilter::timings()) ------------------------------------------------------
+class Stopwatch
+{
+public:
+    explicit Stopwatch(size_t history = 1) : m_History(history ? history : 1) {}
+    Stopwatch& start() { m_Start = std::chrono::steady_clock::now(); m_Running = true; return *this; }
+    Stopwatch& stop()
+    {
+        if (!m_Running) return *this;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - m_Start).count();
+        if (m_Samples.size() == m_History) m_Samples.erase(m_Samples.begin());
+        m_Samples.push_back(ms);
+        m_Running = false;
+        return *this;
+    }
+    double elapsed_ms() const { return m_Samples.empty() ? 0.0 : m_Samples.back(); }
+    double average_ms() const
+    {
+        if (m_Samples.empty()) return 0.0;
+        double s = 0; for (double v : m_Samples) s += v;
+        return s / static_cast<double>(m_Samples.size());
+    }
+    void set_history(size_t n) { m_History = n ? n : 1; }
+private:
+    std::chrono::steady_clock::time_point m_Start{};
+    std::vector<double> m_Samples;
+    size_t m_History;
+    bool m_Running = false;
+};
+
+// ---- Utility/Configurable.hpp:27-44 -----------------------------------------------------------------------------------
+template <typename T>
+class Configurable
+{
+public:
+    explicit Configurable(const T& settings = {}) : m_Settings(settings) {}
+    virtual ~Configurable() = default;
+    void configure_default() { configure(T{}); }
+    virtual void configure(const T& settings) = 0;
+    void reconfigure(const std::function<void(T&)>& updater) { T s = m_Settings; updater(s); configure(s); }
+    const T& settings() const { return m_Settings; }
+protected:
+    T m_Settings;
+};
+
+// ---- Filters/VideoFilter.hpp:32-61 -------------------------------------------------------------------------------------
+class VideoFilter
+{
+public:
+    explicit VideoFilter(const std::string& filter_name = "Identity Filter") : m_Alias(filter_name) {}
+    virtual ~VideoFilter() = default;
+    const std::string& alias() const { return m_Alias; }
+
+    // VideoFilter.cpp:46-51 (profile => synchronise the device around filter(), Stopwatch::sync_gpu)
+    void apply(VideoFrame&& input, VideoFrame& output, const bool profile = false)
+    {
+        if (profile) sync_device();
+        m_FrameTimer.start();
+        filter(std::move(input), output);
+        if (profile) sync_device();
+        m_FrameTimer.stop();
+    }
+    // VideoFilter.cpp:55-58
+    void apply(const VideoFrame& input, VideoFrame& output, const bool profile = false) { apply(Frame(input), output, profile); }
+
+    void set_timing_samples(const size_t samples) { m_FrameTimer.set_history(samples); }
+    const Stopwatch& timings() const { return m_FrameTimer; }
+
+protected:
+    virtual void filter(VideoFrame&& input, VideoFrame& output) { output = std::move(input); }  // VideoFilter.cpp:229-233
+    virtual void sync_device() {}
+private:
+    Stopwatch m_FrameTimer;
+    const std::string m_Alias;
+};
+typedef VideoFilter IdentityFilter;
+
+// ---- settings (field names and defaults are the reference's API) -----------------------------------------------------------
+struct FeatureDetectorSettings  // Vision/FeatureDetector.hpp:28-37
+{
+    cvlite::Size detection_resolution = {256, 256};
+    cvlite::Size detection_regions = {2, 2};
+    bool force_detection = false;
+    float max_feature_density = 0.20f;
+    float min_feature_density = 0.05f;
+    float accumulation_rate = 2.0f;
+};
+
+struct FrameTrackerSettings : public FeatureDetectorSettings  // Vision/FrameTracker.hpp:31-44
+{
+    cvlite::Size motion_resolution = {16, 16};
+    bool track_local_motions = true;
+    float temporal_smoothing = 1.0f;
+    float local_smoothing = 20.0f;
+    size_t min_motion_samples = 75;
+    float acceptance_threshold = 8.0f;
+    float uniformity_threshold = 0.20f;
+};
+
+struct PathSmootherSettings  // Vision/PathSmoother.hpp:29-39
+{
+    size_t predictive_samples = 10;
+    cvlite::Size motion_resolution = {2, 2};
+    cvlite::Size2f corrective_limits = {0.1f, 0.1f};
+    float smoothing_steps = 20.0f;
+    float response_rate = 0.04f;
+};
+
+struct StabilizationFilterSettings : public FrameTrackerSettings, public PathSmootherSettings  // StabilizationFilter.hpp:28-39
+{
+    cvlite::Size motion_resolution = {2, 2};
+    cvlite::Scalar background_colour = {255, 0, 255};
+    bool crop_to_stable_region = false;
+    bool stabilize_output = true;
+    float min_scene_quality = 0.8f;
+    float min_tracking_quality = 0.3f;
+};
+
+// ---- Filters/StabilizationFilter.hpp:42-77 ---------------------------------------------------------------------------------
+class StabilizationFilter final : public VideoFilter, public Configurable<StabilizationFilterSettings>
+{
+public:
+    explicit StabilizationFilter(const StabilizationFilterSettings& settings = {}, int cuda_device = 0)
+        : VideoFilter("Stabilization Filter"), m_Device(cuda_device)
+    {
+        install_assert_bridge();
+        const lvkb200_settings pod = to_pod(settings);
+        check(lvkb200_stream_create(m_Device, &pod, &m_Stream), "lvkb200_stream_create");
+        m_Settings = settings;
+        link_motion_resolution();
+    }
+    ~StabilizationFilter() override { if (m_Stream) lvkb200_stream_destroy(m_Stream); }
+    StabilizationFilter(const StabilizationFilter&) = delete;
+    StabilizationFilter& operator=(const StabilizationFilter&) = delete;
+
+    void configure(const StabilizationFilterSettings& settings) override  // StabilizationFilter.cpp:42-65
+    {
+        const lvkb200_settings pod = to_pod(settings);
+        if (check(lvkb200_stream_configure(m_Stream, &pod), "StabilizationFilter::configure"))
+        {
+            m_Settings = settings;
+            link_motion_resolution();
+        }
+    }
+    void restart() { check(lvkb200_stream_restart(m_Stream), "StabilizationFilter::restart"); }
+    bool ready() const { return lvkb200_stream_ready(m_Stream) != 0; }
+    void reset_context() { check(lvkb200_stream_reset_context(m_Stream), "StabilizationFilter::reset_context"); }
+    void draw_trackers() {}      // OBS test-mode overlay (StabilizationFilter.cpp:163-177): not on the hot path
+    void draw_motion_mesh() {}   // (:181-188)
+    size_t frame_delay() const { return static_cast<size_t>(lvkb200_stream_frame_delay(m_Stream)); }
+    cvlite::Rect stable_region() const
+    {
+        cvlite::Rect r;
+        lvkb200_stream_stable_region(m_Stream, m_LastWidth, m_LastHeight, &r.x, &r.y, &r.width, &r.height);
+        return r;
+    }
+    const lvkb200_result& last_result() const { return m_Result; }
+    lvkb200_stream* native_handle() const { return m_Stream; }
+
+private:
+    void filter(VideoFrame&& input, VideoFrame& output) override  // StabilizationFilter.cpp:69-135
+    {
+        LVK_ASSERT(input.has_known_format());
+        LVK_ASSERT(!input.empty());
+        m_LastWidth = input.cols; m_LastHeight = input.rows;
+        // the reference moves `input` into its queue and overwrites `output`; OBS passes the same object for both
+        const bool alias = (&input == &output);
+        VideoFrame* dst = &output;
+        if (!alias && (output.empty() || output.cols != input.cols || output.rows != input.rows || output.on_device != input.on_device))
+        {
+            if (input.on_device) { dst = &m_Scratch; if (m_Scratch.cols != input.cols || m_Scratch.rows != input.rows) m_Scratch.create(input.rows, input.cols); }
+            else output.create(input.rows, input.cols);
+        }
+        const lvkb200_memspace out_space = dst->on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST;
+        const lvkb200_status st = lvkb200_stream_submit(
+            m_Stream, input.data, input.step, input.cols, input.rows, static_cast<lvkb200_format>(input.format),
+            input.timestamp, input.on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST, dst->data, dst->step, out_space, &m_Result);
+        if (!check(st, "StabilizationFilter::filter") || !m_Result.has_output)
+        {
+            output.release();  // StabilizationFilter.cpp:94,134
+            return;
+        }
+        if (dst != &output) output = *dst;
+        output.timestamp = m_Result.out_timestamp;                                   // WarpMesh.cpp:221
+        output.format = static_cast<VideoFrame::Format>(m_Result.out_format);         // WarpMesh.cpp:222
+    }
+    void sync_device() override { lvkb200_stream_sync(m_Stream); }  // Stopwatch::sync_gpu (Timing/Stopwatch.cpp:127-131)
+
+    void link_motion_resolution()  // StabilizationFilter.cpp:57-58
+    {
+        static_cast<PathSmootherSettings&>(m_Settings).motion_resolution = m_Settings.motion_resolution;
+        static_cast<FrameTrackerSettings&>(m_Settings).motion_resolution = m_Settings.motion_resolution;
+    }
+
+    static lvkb200_settings to_pod(const StabilizationFilterSettings& s)
+    {
+        lvkb200_settings p;
+        lvkb200_settings_default(&p);
+        p.detection_resolution_width = s.detection_resolution.width; p.detection_resolution_height = s.detection_resolution.height;
+        p.detection_regions_width = s.detection_regions.width; p.detection_regions_height = s.detection_regions.height;
+        p.force_detection = s.force_detection;
+        p.max_feature_density = s.max_feature_density; p.min_feature_density = s.min_feature_density;
+        p.accumulation_rate = s.accumulation_rate;
+        p.motion_resolution_width = s.motion_resolution.width; p.motion_resolution_height = s.motion_resolution.height;
+        p.track_local_motions = s.track_local_motions;
+        p.temporal_smoothing = s.temporal_smoothing; p.local_smoothing = s.local_smoothing;
+        p.min_motion_samples = s.min_motion_samples;
+        p.acceptance_threshold = s.acceptance_threshold; p.uniformity_threshold = s.uniformity_threshold;
+        p.predictive_samples = s.predictive_samples;
+        p.corrective_limits_width = s.corrective_limits.width; p.corrective_limits_height = s.corrective_limits.height;
+        p.smoothing_steps = s.smoothing_steps; p.response_rate = s.response_rate;
+        for (int i = 0; i < 4; i++) p.background_colour[i] = s.background_colour[i];
+        p.crop_to_stable_region = s.crop_to_stable_region; p.stabilize_output = s.stabilize_output;
+        p.min_scene_quality = s.min_scene_quality; p.min_tracking_quality = s.min_tracking_quality;
+        return p;
+    }
+
+    // FFI status codes become assert_handler calls (SURVEY §8b "Errors")
+    static bool check(lvkb200_status st, const char* where)
+    {
+        if (st == LVKB200_OK) return true;
+        context::assert_handler("lvkb200", where, lvkb200_last_error());
+        return false;
+    }
+    static void install_assert_bridge()
+    {
+        // failed reference preconditions inside the library are reported through status codes + last_error();
+        // check() forwards them, so no C callback is needed (and none may throw across the C boundary).
+        lvkb200_set_assert_handler(nullptr);
+    }
+
+    lvkb200_stream* m_Stream = nullptr;
+    lvkb200_result m_Result{};
+    VideoFrame m_Scratch;
+    int m_Device = 0;
+    int m_LastWidth = 0, m_LastHeight = 0;
+};
+
+}  // namespace lvk

@@ -1,0 +1,65 @@
+// Compiles against the lvk-compat header exactly like a reference caller would (VSFilter.cpp:352-364 /
+// FilterParser.tpp:48,60 style) and runs a few frames through lvk::StabilizationFilter.  Prints one line per frame:
+//   <index> <empty|timestamp> <sum of output bytes>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../livevisionkit_b200/compat/lvk/lvk.hpp"
+
+int main(int argc, char** argv)
+{
+    const int w = 640, h = 360, frames = argc > 1 ? std::atoi(argv[1]) : 14;
+    int failures = 0;
+    lvk::context::assert_handler = [&](std::string file, std::string function, std::string assertion) {
+        std::fprintf(stderr, "assert: %s %s %s\n", file.c_str(), function.c_str(), assertion.c_str());
+        failures++;
+    };
+
+    lvk::StabilizationFilterSettings settings;           // defaults of the reference
+    settings.detection_resolution = {480, 270};          // OBS "Homography" preset (VSFilter.cpp:269-280)
+    settings.detection_regions = {2, 1};
+    settings.max_feature_density = 0.12f;
+    settings.min_feature_density = 0.04f;
+    settings.accumulation_rate = 3.0f;
+    settings.track_local_motions = false;
+    settings.acceptance_threshold = 3.0f;
+    lvk::StabilizationFilter filter(settings);
+    filter.reconfigure([](lvk::StabilizationFilterSettings& s) { s.crop_to_stable_region = false; });
+    if (filter.frame_delay() != 10 || filter.alias() != "Stabilization Filter") return 2;
+
+    std::vector<uint8_t> pixels(static_cast<size_t>(w) * h * 3);
+    for (int i = 0; i < frames; i++)
+    {
+        // deterministic textured frame, shifted by i pixels
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+            {
+                const int xs = x + 2 * i, ys = y + i;
+                const uint8_t v = static_cast<uint8_t>(((xs / 16 + ys / 16) % 2) * 120 + ((xs * 7 + ys * 13) % 61) + 40);
+                uint8_t* p = &pixels[(static_cast<size_t>(y) * w + x) * 3];
+                p[0] = v; p[1] = static_cast<uint8_t>(v * 9 / 10); p[2] = static_cast<uint8_t>(v * 8 / 10);
+            }
+        lvk::VideoFrame input(pixels.data(), w, h, static_cast<size_t>(w) * 3, lvk::VideoFrame::BGR, 1000 + i);
+        lvk::VideoFrame output;
+        filter.apply(input, output, /*profile=*/i == frames - 1);
+        if (output.empty())
+            std::printf("%d empty 0\n", i);
+        else
+        {
+            unsigned long long sum = 0;
+            for (int y = 0; y < output.rows; y++)
+                for (size_t b = 0; b < static_cast<size_t>(output.cols) * 3; b++) sum += output.data[y * output.step + b];
+            std::printf("%d %llu %llu\n", i, static_cast<unsigned long long>(output.timestamp), sum);
+            if (output.format != lvk::VideoFrame::BGR) return 3;
+        }
+    }
+    // error behaviour: a failed precondition reaches the assert handler instead of throwing
+    lvk::StabilizationFilterSettings bad = settings;
+    bad.min_tracking_quality = 2.0f;  // LVK_ASSERT_01 (StabilizationFilter.cpp:44)
+    const int before = failures;
+    filter.configure(bad);
+    if (failures != before + 1) return 4;
+    std::printf("timing_ms %.3f\n", filter.timings().elapsed_ms());
+    return 0;
+}
