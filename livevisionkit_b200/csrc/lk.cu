@@ -14,8 +14,12 @@
 // One warp tracks one feature through all levels in a single launch: 121 window pixels = 4 per lane, patch kept in
 // registers, warp-shuffle reductions for A11/A12/A22/b1/b2.  Compiled with --fmad=false (the CPU path has no FMA).
 
+#include <cooperative_groups.h>
+
 #include "common.hpp"
 #include "lk.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace lvkb200
 {
@@ -98,6 +102,82 @@ __global__ void k_scharr(ScharrArg a)
         out.y = (short)((t1r + t1l) * 3 + t1c * 10);
     }
     a.deriv[l][(size_t)py * a.deriv_pitch[l] + px] = out;
+}
+
+// Whole pyramid + derivative planes of one detection image in ONE cooperative launch (grid-wide barriers between
+// the dependent levels) instead of levels+2 tiny dependent launches: the chain is latency-, not bandwidth-bound.
+struct PyrArg
+{
+    const uint8_t* det;
+    size_t det_pitch;
+    uint8_t* img[LK_MAX_LEVELS];
+    short2* deriv[LK_MAX_LEVELS];
+    size_t img_pitch[LK_MAX_LEVELS];
+    size_t deriv_pitch[LK_MAX_LEVELS];
+    int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
+    int levels;
+};
+
+__global__ void __launch_bounds__(256) k_pyramid_fused(PyrArg a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    {
+        const int pw = a.w[0] + 2 * P, ph = a.h[0] + 2 * P;
+        for (int i = tid; i < pw * ph; i += nth)
+        {
+            const int py = i / pw, px = i - py * pw;
+            const int x = reflect101(px - P, a.w[0]), y = reflect101(py - P, a.h[0]);
+            a.img[0][(size_t)py * a.img_pitch[0] + px] = __ldg(a.det + (size_t)y * a.det_pitch + x);
+        }
+    }
+    grid.sync();
+    for (int l = 1; l < a.levels; l++)
+    {
+        const int w = a.w[l], h = a.h[l], pw = w + 2 * P, ph = h + 2 * P;
+        const uint8_t* prev = a.img[l - 1];
+        const size_t pp = a.img_pitch[l - 1];
+        for (int i = tid; i < pw * ph; i += nth)
+        {
+            const int py = i / pw, px = i - py * pw;
+            const int x = reflect101(px - P, w), y = reflect101(py - P, h);
+            const uint8_t* base = prev + (size_t)(2 * y - 2 + P) * pp + (2 * x - 2 + P);
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < 5; j++)
+            {
+                const uint8_t* r = base + (size_t)j * pp;
+                const int row = (int)r[0] + 4 * (int)r[1] + 6 * (int)r[2] + 4 * (int)r[3] + (int)r[4];
+                const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+                sum += kj * row;
+            }
+            a.img[l][(size_t)py * a.img_pitch[l] + px] = (uint8_t)((sum + 128) >> 8);
+        }
+        grid.sync();
+    }
+    for (int l = 0; l < a.levels; l++)
+    {
+        const int w = a.w[l], h = a.h[l], pw = w + 2 * P, ph = h + 2 * P;
+        const size_t s = a.img_pitch[l];
+        for (int i = tid; i < pw * ph; i += nth)
+        {
+            const int py = i / pw, px = i - py * pw;
+            short2 out = make_short2(0, 0);
+            const int x = px - P, y = py - P;
+            if (x >= 0 && x < w && y >= 0 && y < h)
+            {
+                const uint8_t* c = a.img[l] + (size_t)py * s + px;
+                const int u0 = c[-(ptrdiff_t)s - 1], u1 = c[-(ptrdiff_t)s], u2 = c[-(ptrdiff_t)s + 1];
+                const int m0 = c[-1], m2 = c[1];
+                const int d0 = c[s - 1], d1 = c[s], d2 = c[s + 1];
+                const int t0l = (u0 + d0) * 3 + m0 * 10, t0r = (u2 + d2) * 3 + m2 * 10;
+                const int t1l = d0 - u0, t1c = d1 - u1, t1r = d2 - u2;
+                out.x = (short)(t0r - t0l);
+                out.y = (short)((t1r + t1l) * 3 + t1c * 10);
+            }
+            a.deriv[l][(size_t)py * a.deriv_pitch[l] + px] = out;
+        }
+    }
 }
 
 struct LkArg
@@ -216,7 +296,10 @@ __global__ void __launch_bounds__(128)
             iw11 = 16384 - iw00 - iw01 - iw10;
 
             const uint8_t* J = Jbase + (size_t)(iny + P) * ipitch + (inx + P);
-            long long sb1 = 0, sb2 = 0;
+            // per-lane partial sums fit int32 (4 products of |diff| <= 8160 by |I'| <= 4080); the warp total does not,
+            // so it is reduced exactly as two REDUX halves (hi = arithmetic >> 16, lo = low 16 bits) instead of a
+            // 5-step 64-bit shuffle chain: the iteration is latency-bound and this is its longest dependent chain
+            int pb1 = 0, pb2 = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++)
             {
@@ -225,16 +308,14 @@ __global__ void __launch_bounds__(128)
                     const uint8_t* s = J + (size_t)wy[q] * ipitch + wx[q];
                     const int diff = descale((int)s[0] * iw00 + (int)s[1] * iw01 + (int)s[ipitch] * iw10 +
                                                  (int)s[ipitch + 1] * iw11, 9) - Ival[q];
-                    sb1 += (long long)(diff * Ix[q]);
-                    sb2 += (long long)(diff * Iy[q]);
+                    pb1 += diff * Ix[q];
+                    pb2 += diff * Iy[q];
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                sb1 += __shfl_xor_sync(0xffffffffu, sb1, o);
-                sb2 += __shfl_xor_sync(0xffffffffu, sb2, o);
-            }
+            const long long sb1 = ((long long)__reduce_add_sync(0xffffffffu, pb1 >> 16) << 16) +
+                                  (long long)__reduce_add_sync(0xffffffffu, pb1 & 0xffff);
+            const long long sb2 = ((long long)__reduce_add_sync(0xffffffffu, pb2 >> 16) << 16) +
+                                  (long long)__reduce_add_sync(0xffffffffu, pb2 & 0xffff);
             const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
             const float2 delta = make_float2((A12 * b2 - A22 * b1) * Dt, (A12 * b1 - A11 * b2) * Dt);
             nextPt.x += delta.x;
@@ -301,6 +382,41 @@ void LkPyramid::release()
 
 lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_pitch)
 {
+    // ---- fast path: one cooperative launch for the whole pyramid
+    static int coop_blocks = -1;  // co-resident 256-thread CTAs of k_pyramid_fused on this device (0 = unsupported)
+    if (coop_blocks < 0)
+    {
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pyramid_fused, 256, 0);
+        coop_blocks = (coop && per_sm > 0) ? sms * std::min(per_sm, 2) : 0;
+        cudaGetLastError();
+    }
+    if (coop_blocks > 0)
+    {
+        PyrArg pa{};
+        pa.det = det;
+        pa.det_pitch = det_pitch;
+        pa.levels = levels;
+        for (int l = 0; l < levels; l++)
+        {
+            pa.img[l] = img[l].as<uint8_t>();
+            pa.deriv[l] = deriv[l].as<short2>();
+            pa.img_pitch[l] = img_pitch[l];
+            pa.deriv_pitch[l] = deriv_pitch[l];
+            pa.w[l] = w[l];
+            pa.h[l] = h[l];
+        }
+        void* args[] = {&pa};
+        LVKB_CUDA(cudaLaunchCooperativeKernel((const void*)k_pyramid_fused, dim3(coop_blocks), dim3(256), args, 0, cs));
+        count_launches(1);
+        valid = true;
+        return LVKB200_OK;
+    }
+
+    // ---- fallback: one launch per level (devices without cooperative launch)
     const dim3 blk(32, 8);
     {
         const dim3 grid(div_up(w[0] + 2 * P, 32), div_up(h[0] + 2 * P, 8));

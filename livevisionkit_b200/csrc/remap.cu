@@ -270,10 +270,20 @@ __global__ void __launch_bounds__(TILE_W* TILE_H)
 
     if (staged)
     {
-        for (int idx = threadIdx.x; idx < bw * bh; idx += TILE_W * TILE_H)
+        // thread (tx, ty) stages columns tx and tx+32 of rows ty, ty+8, ty+16 (SRC_W <= 64, SRC_H <= 24): no integer
+        // division, lanes read consecutive pixels of one row
+        static_assert(SRC_W <= 2 * TILE_W && SRC_H <= 3 * TILE_H, "staging pattern covers the tile");
+        const uint8_t* p0 = src + (size_t)(y0 + ty) * src_pitch + 3 * (x0 + tx);
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++)
         {
-            const int r = idx / bw, c = idx - r * bw;
-            tile[r * SRC_W + c] = load_texel<YUV>(src + (size_t)(y0 + r) * src_pitch + 3 * (x0 + c));
+            const int r = ty + TILE_H * rr;
+            if (r < bh)
+            {
+                const uint8_t* p = p0 + (size_t)(TILE_H * rr) * src_pitch;
+                if (tx < bw) tile[r * SRC_W + tx] = load_texel<YUV>(p);
+                if (tx + TILE_W < bw) tile[r * SRC_W + tx + TILE_W] = load_texel<YUV>(p + 3 * TILE_W);
+            }
         }
     }
     __syncthreads();
