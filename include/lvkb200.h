@@ -197,6 +197,10 @@ lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB
  * so keeping them costs no synchronisation inside submit. */
 lvkb200_status lvkb200_stream_stage_totals_us(lvkb200_stream* s, double totals[LVKB200_STAGE_COUNT],
                                               uint64_t counts[LVKB200_STAGE_COUNT], int reset);
+/* VideoFilter::apply(..., profile) (Filters/VideoFilter.cpp:46-51): with profiling on, every stage is bracketed by
+ * CUDA events and the tracking chain runs as individual launches; off (default) the chain replays as one CUDA graph
+ * and only the remap kernel is timed. */
+lvkb200_status lvkb200_stream_set_profiling(lvkb200_stream* s, int enable);
 /* Number of CUDA kernels this library has launched in this process (all streams). */
 uint64_t lvkb200_kernel_launch_count(void);
 

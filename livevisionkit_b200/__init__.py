@@ -204,6 +204,9 @@ class Stream:
         _capi.check(self._lib.lvkb200_stream_stage_totals_us(self._h, t, n, int(reset)))
         return dict(zip(STAGE_NAMES, [float(v) for v in t])), dict(zip(STAGE_NAMES, [int(v) for v in n]))
 
+    def set_profiling(self, enable: bool = True):
+        _capi.check(self._lib.lvkb200_stream_set_profiling(self._h, int(enable)))
+
     def set_debug_capture(self, enable: bool = True):
         _capi.check(self._lib.lvkb200_stream_set_debug_capture(self._h, int(enable)))
 

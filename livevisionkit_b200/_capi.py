@@ -77,6 +77,7 @@ SYMBOLS = {
     "lvkb200_stream_debug_fetch": (C.c_int, [_vp, _i, _vp, _sz, C.POINTER(_sz)]),
     "lvkb200_stream_stage_times_us": (C.c_int, [_vp, _fp]),
     "lvkb200_stream_stage_totals_us": (C.c_int, [_vp, _dp, C.POINTER(C.c_uint64), _i]),
+    "lvkb200_stream_set_profiling": (C.c_int, [_vp, _i]),
     "lvkb200_kernel_launch_count": (C.c_uint64, []),
     "lvkb200_remap_homography": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _dp, _u8p, _i]),
     "lvkb200_remap_mesh": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _fp, _i, _i, _u8p, _i]),

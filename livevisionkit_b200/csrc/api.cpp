@@ -319,6 +319,13 @@ lvkb200_status lvkb200_warp_mesh_apply(lvkb200_stream* s, const void* src, size_
 
 // ---- remaining stage-level entry points ------------------------------------------------------------------------------
 
+lvkb200_status lvkb200_stream_set_profiling(lvkb200_stream* s, int enable)
+{
+    LVKB_REQUIRE(s != nullptr);
+    s->profile_stages = enable != 0;
+    return LVKB200_OK;
+}
+
 lvkb200_status lvkb200_stream_set_debug_capture(lvkb200_stream* s, int enable)
 {
     LVKB_REQUIRE(s != nullptr);
@@ -420,12 +427,19 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
         cuda_ok(dst.ensure(count));
     }
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dp.ptr, points, sizeof(float2) * count, cudaMemcpyHostToDevice, s->cs));
-    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dq.as<float2>(), dst.as<uint8_t>(),
-                                         lk_epsilon_for_call(std::max(call_index, 0)));
+    DeviceBuffer dprm;
+    TrackParams hprm{};
+    hprm.n = count;
+    hprm.lk_epsilon_sq = lk_epsilon_for_call(std::max(call_index, 0));
+    if (st == LVKB200_OK) cuda_ok(dprm.ensure(sizeof(TrackParams)));
+    if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dprm.ptr, &hprm, sizeof(hprm), cudaMemcpyHostToDevice, s->cs));
+    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dprm.as<TrackParams>(), dq.as<float2>(),
+                                         dst.as<uint8_t>());
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(matched, dq.ptr, sizeof(float2) * count, cudaMemcpyDeviceToHost, s->cs));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(status, dst.ptr, count, cudaMemcpyDeviceToHost, s->cs));
     cuda_ok(cudaStreamSynchronize(s->cs));
     pp.release(); pn.release(); dprev.release(); dnext.release(); dp.release(); dq.release(); dst.release();
+    dprm.release();
     return st;
 }
 

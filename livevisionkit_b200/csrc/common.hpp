@@ -51,6 +51,18 @@ void report_assert(const char* file, const char* function, const char* assertion
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Per-frame scalars of the tracking chain (LK -> swap-erase compaction -> RANSAC).  They live in DEVICE memory and
+// are refreshed by one small H2D copy, so the chain's kernels have frame-independent arguments and the whole chain
+// can be replayed as one CUDA graph.
+struct TrackParams
+{
+    int n;                  // points handed to the optical flow this frame
+    int reserved;
+    double lk_epsilon_sq;   // stopping epsilon of this calc() call (see lk_epsilon_for_call)
+    float threshold_sq;     // acceptance threshold^2 of the motion estimator
+    float reserved2;
+};
+
 // Process-wide count of kernels launched by this library (bench.py reports it as gpu_launches).
 void count_launches(int n);
 uint64_t launch_count();

@@ -194,11 +194,12 @@ struct LkArg
 __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 
 __global__ void __launch_bounds__(128)
-    k_lk_track(LkArg a, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
-               uint8_t* __restrict__ status, double epsilon_sq)
+    k_lk_track(LkArg a, const float2* __restrict__ prev_pts, const TrackParams* __restrict__ prm,
+               float2* __restrict__ next_pts, uint8_t* __restrict__ status)
 {
     const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pt >= n) return;
+    if (pt >= prm->n) return;
+    const double epsilon_sq = prm->lk_epsilon_sq;
     const int lane = threadIdx.x & 31;
     const float2 p0 = prev_pts[pt];
     const float half = 5.0f;       // (winSize - 1) * 0.5
@@ -461,9 +462,11 @@ double lk_epsilon_for_call(int call_index)
     return eps;
 }
 
-lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts, int n,
-                        float2* d_next_pts, uint8_t* d_status, double epsilon_sq)
+lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts,
+                        int max_points, const TrackParams* d_params, float2* d_next_pts, uint8_t* d_status)
 {
+    // The grid covers max_points; warps beyond the frame's actual count (d_params->n) exit at once.
+    const int n = max_points;
     if (n <= 0) return LVKB200_OK;
     LVKB_REQUIRE(prev.levels == next.levels && prev.levels > 0 && prev.w[0] == next.w[0] && prev.h[0] == next.h[0]);
     LkArg a{};
@@ -478,7 +481,7 @@ lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid&
         a.h[l] = prev.h[l];
     }
     a.max_level = prev.levels - 1;
-    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, n, d_next_pts, d_status, epsilon_sq);
+    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, d_params, d_next_pts, d_status);
     count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;

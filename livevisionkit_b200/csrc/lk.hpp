@@ -29,7 +29,8 @@ struct LkPyramid
 double lk_epsilon_for_call(int call_index);
 
 // Tracks n points from `prev` to `next` (device arrays of float2 / uint8).
-lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts, int n,
-                        float2* d_next_pts, uint8_t* d_status, double epsilon_sq);
+// The launch covers max_points; the frame's real count and stopping epsilon are read from d_params (device).
+lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts,
+                        int max_points, const TrackParams* d_params, float2* d_next_pts, uint8_t* d_status);
 
 }  // namespace lvkb200

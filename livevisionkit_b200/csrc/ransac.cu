@@ -47,12 +47,14 @@ constexpr int HYP = RANSAC_HYPOTHESES;
 constexpr int CT = 1024;
 
 __global__ void __launch_bounds__(CT)
-    k_compact_swap_erase(const float2* __restrict__ a, const float2* __restrict__ b, const uint8_t* __restrict__ keep, int n,
+    k_compact_swap_erase(const float2* __restrict__ a, const float2* __restrict__ b, const uint8_t* __restrict__ keep,
+                         const TrackParams* __restrict__ prm,
                          float2* __restrict__ a_out, float2* __restrict__ b_out, int* __restrict__ perm,
                          int* __restrict__ removed, int* __restrict__ n_out)
 {
     __shared__ int warp_tot[CT / 32];
     __shared__ int s_base, s_size;
+    const int n = prm->n;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
@@ -197,8 +199,9 @@ __device__ __forceinline__ float reproj_err2(const float m[9], float2 p, float2 
 
 __global__ void __launch_bounds__(256)
     k_ransac_score(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                   const float* __restrict__ models, float thr2, float* __restrict__ scores)
+                   const float* __restrict__ models, const TrackParams* __restrict__ prm, float* __restrict__ scores)
 {
+    const float thr2 = prm->threshold_sq;
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
     __shared__ float m[9];
@@ -233,9 +236,11 @@ constexpr int NACC = 44;  // 36 (upper triangle of A^T W A) + 8 (A^T W b)
 
 __global__ void __launch_bounds__(RT)
     k_ransac_refine(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                    const float* __restrict__ models, const float* __restrict__ scores, float thr2, int iterations,
-                    RansacResult* __restrict__ result, uint8_t* __restrict__ mask)
+                    const float* __restrict__ models, const float* __restrict__ scores,
+                    const TrackParams* __restrict__ prm, int iterations, RansacResult* __restrict__ result,
+                    uint8_t* __restrict__ mask)
 {
+    const float thr2 = prm->threshold_sq;
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
     __shared__ float s_best[RT / 32];
@@ -443,24 +448,24 @@ __global__ void __launch_bounds__(RT)
 
 }  // namespace
 
-lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep, int n,
-                                  float2* d_a_out, float2* d_b_out, int* d_perm, int* d_removed, int* d_n_out)
+lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,
+                                  const TrackParams* d_params, float2* d_a_out, float2* d_b_out, int* d_perm,
+                                  int* d_removed, int* d_n_out)
 {
-    k_compact_swap_erase<<<1, CT, 0, cs>>>(d_a, d_b, d_keep, n, d_a_out, d_b_out, d_perm, d_removed, d_n_out);
+    k_compact_swap_erase<<<1, CT, 0, cs>>>(d_a, d_b, d_keep, d_params, d_a_out, d_b_out, d_perm, d_removed, d_n_out);
     count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;
 }
 
 lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,
-                                 float threshold, float* d_models, float* d_scores, RansacResult* d_result,
-                                 uint8_t* d_mask)
+                                 const TrackParams* d_params, float* d_models, float* d_scores,
+                                 RansacResult* d_result, uint8_t* d_mask)
 {
-    const float thr2 = threshold * threshold;
     LVKB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(RansacResult), cs));
     k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, 0x9E3779B9u, d_models);
-    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, thr2, d_scores);
-    k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, thr2, RANSAC_REFINE_ITERS, d_result,
+    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, d_params, d_scores);
+    k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, d_params, RANSAC_REFINE_ITERS, d_result,
                                       d_mask);
     count_launches(3);
     LVKB_CUDA(cudaGetLastError());

@@ -20,12 +20,13 @@ struct RansacResult
 
 // fast_filter on the device: keeps a[i], b[i] where keep[i] != 0, in the reference's swap-erase order.
 // d_perm / d_removed: scratch of n ints each.  *d_n_out receives the surviving count.
-lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep, int n,
-                                  float2* d_a_out, float2* d_b_out, int* d_perm, int* d_removed, int* d_n_out);
+lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,
+                                  const TrackParams* d_params, float2* d_a_out, float2* d_b_out, int* d_perm,
+                                  int* d_removed, int* d_n_out);
 
 // All pointers are device memory (the count too).  d_models: HYP*9 floats, d_scores: HYP floats.
 lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,
-                                 float threshold, float* d_models, float* d_scores, RansacResult* d_result,
-                                 uint8_t* d_mask);
+                                 const TrackParams* d_params, float* d_models, float* d_scores,
+                                 RansacResult* d_result, uint8_t* d_mask);
 
 }  // namespace lvkb200

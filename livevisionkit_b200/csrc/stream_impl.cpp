@@ -83,6 +83,9 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
         grid.reset();
         frame_initialized = false;
         pyr[0].valid = pyr[1].valid = false;
+        if (cs) cudaStreamSynchronize(cs);
+        destroy_graphs();   // the pyramids will be re-allocated for the new detection resolution
+        point_capacity = 0;  // and the point capacity follows the new suppression grid
     }
     configured = true;
     return LVKB200_OK;
@@ -120,6 +123,8 @@ void lvkb200_stream::stable_region(int fw, int fh, int* x, int* y, int* w, int* 
 
 void lvkb200_stream::stage_begin(int stage)
 {
+    // Only the roofline kernel (remap) is timed unconditionally; the other stages are timed when profiling is on.
+    if (!profile_stages && stage != ST_REMAP) return;
     cudaEvent_t* ev = stage_ev[stage_parity][stage];
     if (!ev[0])
     {
@@ -130,7 +135,11 @@ void lvkb200_stream::stage_begin(int stage)
     stage_used[stage_parity][stage] = true;
 }
 
-void lvkb200_stream::stage_end(int stage) { cudaEventRecord(stage_ev[stage_parity][stage][1], cs); }
+void lvkb200_stream::stage_end(int stage)
+{
+    if (!profile_stages && stage != ST_REMAP) return;
+    cudaEventRecord(stage_ev[stage_parity][stage][1], cs);
+}
 
 // Adds the (completed) stage durations recorded in slot `parity` to the running totals and frees the slot.
 void lvkb200_stream::harvest_stage_times(int parity)
@@ -189,58 +198,119 @@ lvkb200_status lvkb200_stream::stage_times(float* times)
 lvkb200_status lvkb200_stream::ensure_points(int n)
 {
     if (n <= point_capacity) return LVKB200_OK;
-    const int cap = std::max(n, 4096);
+    // capacity = the detector's maximum feature count (so the tracking graph is captured once), rounded up
+    const int want = std::max(n, static_cast<int>(grid.max_feature_capacity()));
+    const int cap = (std::max(want, 256) + 63) / 64 * 64;
     LVKB_CUDA(cudaStreamSynchronize(cs));
+    destroy_graphs();
+    off_status = sizeof(float2) * static_cast<size_t>(cap);
+    off_mask = off_status + static_cast<size_t>(cap);
+    off_result = align_up(off_mask + static_cast<size_t>(cap), 16);
+    track_out_bytes = off_result + sizeof(RansacResult);
+    LVKB_CUDA(d_track_out.ensure(track_out_bytes));
+    LVKB_CUDA(h_track_out.ensure(track_out_bytes));
     LVKB_CUDA(d_pts_prev.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(d_pts_next.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(d_status.ensure(cap));
     LVKB_CUDA(d_src.ensure(sizeof(float2) * cap));
     LVKB_CUDA(d_dst.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(d_mask.ensure(cap));
     LVKB_CUDA(d_models.ensure(sizeof(float) * 9 * RANSAC_HYPOTHESES));
     LVKB_CUDA(d_scores.ensure(sizeof(float) * RANSAC_HYPOTHESES));
-    LVKB_CUDA(d_result.ensure(sizeof(RansacResult)));
     LVKB_CUDA(d_perm.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_removed.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_count.ensure(sizeof(int)));
+    LVKB_CUDA(d_params.ensure(sizeof(TrackParams)));
     LVKB_CUDA(h_count.ensure(sizeof(int)));
+    LVKB_CUDA(h_params.ensure(sizeof(TrackParams)));
     LVKB_CUDA(h_pts_prev.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(h_pts_next.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(h_status.ensure(cap));
     LVKB_CUDA(h_src.ensure(sizeof(float2) * cap));
     LVKB_CUDA(h_dst.ensure(sizeof(float2) * cap));
-    LVKB_CUDA(h_mask.ensure(cap));
-    LVKB_CUDA(h_result.ensure(sizeof(RansacResult)));
+    std::memset(h_pts_prev.ptr, 0, sizeof(float2) * cap);
     point_capacity = cap;
     return LVKB200_OK;
 }
 
-// Enqueues the sparse optical flow of `pts` (previous -> current pyramid).  Nothing is copied back yet.
-lvkb200_status lvkb200_stream::enqueue_lk(const std::vector<float>& pts)
+void lvkb200_stream::destroy_graphs()
 {
-    const int n = static_cast<int>(pts.size() / 2);
-    if (n == 0) return LVKB200_OK;
-    LVKB_TRY(ensure_points(n));
-    std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
-    LVKB_CUDA(cudaMemcpyAsync(d_pts_prev.ptr, h_pts_prev.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
-    LVKB_TRY(lk_track(cs, pyr[cur ^ 1], pyr[cur], d_pts_prev.as<float2>(), n, d_pts_next.as<float2>(),
-                      d_status.as<uint8_t>(), lk_epsilon_for_call(lk_calls)));
-    lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
+    for (auto& row : track_graph)
+        for (auto& g : row)
+        {
+            if (g) cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+}
+
+// The device work of the tracking chain, in stream order on `cs` (either captured into a graph or executed eagerly):
+// params + points H2D -> LK -> [swap-erase compaction -> RANSAC] -> ONE D2H of all results.
+lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, int max_points, bool with_events)
+{
+    const TrackParams* prm = d_params.as<TrackParams>();
+    LVKB_CUDA(cudaMemcpyAsync(d_params.ptr, h_params.ptr, sizeof(TrackParams), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_pts_prev.ptr, h_pts_prev.ptr, sizeof(float2) * max_points, cudaMemcpyHostToDevice, cs));
+    if (with_events) stage_begin(ST_LK);
+    LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], d_pts_prev.as<float2>(), max_points, prm, d_pts_next(), d_status()));
+    if (with_events) stage_end(ST_LK);
+    if (global)
+    {
+        // fast_filter + motion estimation chained on the device; the host replays the same erase order afterwards.
+        // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) when distribution <= 0.6 (FrameTracker.cpp:362-373); until
+        // the similarity estimator lands the homography estimator serves badly distributed features as well.
+        if (with_events) stage_begin(ST_ESTIMATE);
+        LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next(), d_status(), prm, d_src.as<float2>(),
+                                    d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(), d_count.as<int>()));
+        LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), prm,
+                                   d_models.as<float>(), d_scores.as<float>(), d_result(), d_mask()));
+        if (with_events) stage_end(ST_ESTIMATE);
+    }
+    LVKB_CUDA(cudaMemcpyAsync(h_track_out.ptr, d_track_out.ptr, track_out_bytes, cudaMemcpyDeviceToHost, cs));
     return LVKB200_OK;
 }
 
-// Enqueues fast_filter + the homography estimator on the device results of enqueue_lk (no host round trip).
-lvkb200_status lvkb200_stream::enqueue_global_motion(int n, float threshold)
+// Enqueues the tracking chain for this frame's points (previous -> current pyramid).
+lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, bool global, float threshold)
 {
-    LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next.as<float2>(), d_status.as<uint8_t>(), n,
-                                d_src.as<float2>(), d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(),
-                                d_count.as<int>()));
-    return ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), threshold,
-                             d_models.as<float>(), d_scores.as<float>(), d_result.as<RansacResult>(),
-                             d_mask.as<uint8_t>());
+    const int n = static_cast<int>(pts.size() / 2);
+    LVKB_TRY(ensure_points(n));
+    TrackParams* hp = h_params.as<TrackParams>();
+    hp->n = n;
+    hp->lk_epsilon_sq = lk_epsilon_for_call(lk_calls);
+    hp->threshold_sq = threshold * threshold;
+    lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
+    std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
+
+    if (!use_graphs || profile_stages)
+        return record_tracking_chain(cur, global, point_capacity, profile_stages);
+
+    cudaGraphExec_t& exec = track_graph[cur][global ? 1 : 0];
+    if (!exec)
+    {
+        const uint64_t launches_before = launch_count();
+        cudaGraph_t graph = nullptr;
+        LVKB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const lvkb200_status st = record_tracking_chain(cur, global, point_capacity, false);
+        const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+        count_launches(-static_cast<int>(launch_count() - launches_before));  // counted per replay instead
+        if (st != LVKB200_OK || e != cudaSuccess || !graph)
+        {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            use_graphs = false;  // fall back to eager launches for the rest of this stream's life
+            return record_tracking_chain(cur, global, point_capacity, false);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess)
+        {
+            exec = nullptr;
+            cudaGetLastError();
+            use_graphs = false;
+            return record_tracking_chain(cur, global, point_capacity, false);
+        }
+    }
+    LVKB_CUDA(cudaGraphLaunch(exec, cs));
+    count_launches(global ? 5 : 1);
+    return LVKB200_OK;
 }
 
-// One device->host copy + one synchronisation for the whole tracking chain of this frame.
+// Waits for the tracking chain (its results already sit in pinned host memory: the copy is part of the chain).
 lvkb200_status lvkb200_stream::fetch_tracking(int n, bool with_model, std::vector<float>& matched,
                                               std::vector<uint8_t>& status, RansacResult* model,
                                               std::vector<uint8_t>& mask)
@@ -248,21 +318,15 @@ lvkb200_status lvkb200_stream::fetch_tracking(int n, bool with_model, std::vecto
     matched.resize(static_cast<size_t>(n) * 2);
     status.resize(n);
     if (n == 0) return LVKB200_OK;
-    LVKB_CUDA(cudaMemcpyAsync(h_pts_next.ptr, d_pts_next.ptr, sizeof(float2) * n, cudaMemcpyDeviceToHost, cs));
-    LVKB_CUDA(cudaMemcpyAsync(h_status.ptr, d_status.ptr, n, cudaMemcpyDeviceToHost, cs));
-    if (with_model)
-    {
-        LVKB_CUDA(cudaMemcpyAsync(h_result.ptr, d_result.ptr, sizeof(RansacResult), cudaMemcpyDeviceToHost, cs));
-        LVKB_CUDA(cudaMemcpyAsync(h_mask.ptr, d_mask.ptr, n, cudaMemcpyDeviceToHost, cs));
-    }
     LVKB_CUDA(cudaStreamSynchronize(cs));
-    std::memcpy(matched.data(), h_pts_next.ptr, sizeof(float) * matched.size());
-    std::memcpy(status.data(), h_status.ptr, n);
+    const uint8_t* base = h_track_out.as<uint8_t>();
+    std::memcpy(matched.data(), base, sizeof(float) * matched.size());
+    std::memcpy(status.data(), base + off_status, n);
     if (with_model)
     {
-        *model = *h_result.as<RansacResult>();
+        std::memcpy(model, base + off_result, sizeof(RansacResult));
         const int m = std::min(std::max(model->n, 0), n);
-        mask.assign(h_mask.as<uint8_t>(), h_mask.as<uint8_t>() + m);
+        mask.assign(base + off_mask, base + off_mask + m);
     }
     return LVKB200_OK;
 }
@@ -276,19 +340,25 @@ lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked,
     std::memcpy(h_src.ptr, tracked.data(), sizeof(float) * tracked.size());
     std::memcpy(h_dst.ptr, matched.data(), sizeof(float) * matched.size());
     *h_count.as<int>() = n;
+    TrackParams* hp = h_params.as<TrackParams>();
+    hp->n = n;
+    hp->lk_epsilon_sq = 0.0;
+    hp->threshold_sq = threshold * threshold;
+    LVKB_CUDA(cudaMemcpyAsync(d_params.ptr, h_params.ptr, sizeof(TrackParams), cudaMemcpyHostToDevice, cs));
     LVKB_CUDA(cudaMemcpyAsync(d_src.ptr, h_src.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
     LVKB_CUDA(cudaMemcpyAsync(d_dst.ptr, h_dst.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
     LVKB_CUDA(cudaMemcpyAsync(d_count.ptr, h_count.ptr, sizeof(int), cudaMemcpyHostToDevice, cs));
-    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), threshold,
-                               d_models.as<float>(), d_scores.as<float>(), d_result.as<RansacResult>(),
-                               d_mask.as<uint8_t>()));
-    LVKB_CUDA(cudaMemcpyAsync(h_result.ptr, d_result.ptr, sizeof(RansacResult), cudaMemcpyDeviceToHost, cs));
-    LVKB_CUDA(cudaMemcpyAsync(h_mask.ptr, d_mask.ptr, n, cudaMemcpyDeviceToHost, cs));
+    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(),
+                               d_params.as<TrackParams>(), d_models.as<float>(), d_scores.as<float>(), d_result(),
+                               d_mask()));
+    LVKB_CUDA(cudaMemcpyAsync(h_track_out.ptr, d_track_out.ptr, track_out_bytes, cudaMemcpyDeviceToHost, cs));
     LVKB_CUDA(cudaStreamSynchronize(cs));
-    const RansacResult* r = h_result.as<RansacResult>();
-    *found = r->found != 0;
-    mask.assign(h_mask.as<uint8_t>(), h_mask.as<uint8_t>() + n);
-    std::memcpy(h, r->h, sizeof(double) * 9);
+    const uint8_t* base = h_track_out.as<uint8_t>();
+    RansacResult r;
+    std::memcpy(&r, base + off_result, sizeof(r));
+    *found = r.found != 0;
+    mask.assign(base + off_mask, base + off_mask + n);
+    std::memcpy(h, r.h, sizeof(double) * 9);
     return LVKB200_OK;
 }
 
@@ -374,18 +444,7 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
     const int n_tracked = static_cast<int>(features.size());
     const bool global = !settings.track_local_motions;
-    stage_begin(ST_LK);
-    LVKB_TRY(enqueue_lk(tracked));
-    stage_end(ST_LK);
-    if (global)
-    {
-        // fast_filter + motion estimation are chained on the device; the host replays the same erase order below.
-        // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) when distribution <= 0.6 (FrameTracker.cpp:362-373); until
-        // the similarity estimator lands the homography estimator serves badly distributed features as well.
-        stage_begin(ST_ESTIMATE);
-        LVKB_TRY(enqueue_global_motion(n_tracked, settings.acceptance_threshold));
-        stage_end(ST_ESTIMATE);
-    }
+    LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold));
     RansacResult model{};
     std::vector<uint8_t> inliers;
     LVKB_TRY(fetch_tracking(n_tracked, global, matched, status, &model, inliers));
@@ -674,10 +733,12 @@ void lvkb200_stream::release()
 {
     stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
-    d_pts_prev.release(); d_pts_next.release(); d_status.release(); d_src.release(); d_dst.release(); d_mask.release();
-    d_models.release(); d_scores.release(); d_result.release();
-    h_pts_prev.release(); h_pts_next.release(); h_status.release(); h_src.release(); h_dst.release(); h_mask.release();
-    h_result.release(); h_det.release(); h_count.release(); d_perm.release(); d_removed.release(); d_count.release();
+    destroy_graphs();
+    d_pts_prev.release(); d_src.release(); d_dst.release(); d_models.release(); d_scores.release();
+    d_track_out.release(); h_track_out.release(); d_params.release(); h_params.release();
+    h_pts_prev.release(); h_src.release(); h_dst.release();
+    h_det.release(); h_count.release(); d_perm.release(); d_removed.release(); d_count.release();
+    point_capacity = 0;
     for (auto& f : ring) f.buf.release();
     if (input_copied) cudaEventDestroy(input_copied);
     input_copied = nullptr;

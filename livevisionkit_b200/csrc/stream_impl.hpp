@@ -33,10 +33,29 @@ struct lvkb200_stream
     int cur = 0;  // pyr[cur] = current frame, pyr[cur ^ 1] = previous frame
     lvkb200::DeviceBuffer d_det;
     size_t det_pitch = 0;
-    lvkb200::DeviceBuffer d_pts_prev, d_pts_next, d_status, d_src, d_dst, d_mask, d_models, d_scores, d_result;
-    lvkb200::DeviceBuffer d_perm, d_removed, d_count;
-    lvkb200::PinnedBuffer h_pts_prev, h_pts_next, h_status, h_src, h_dst, h_mask, h_result, h_det, h_count;
+    lvkb200::DeviceBuffer d_pts_prev, d_src, d_dst, d_models, d_scores;
+    lvkb200::DeviceBuffer d_perm, d_removed, d_count, d_params;
+    // results of the tracking chain, contiguous so that ONE device->host copy brings them back:
+    // [matched float2 x cap | status u8 x cap | mask u8 x cap | pad | RansacResult]
+    lvkb200::DeviceBuffer d_track_out;
+    lvkb200::PinnedBuffer h_track_out, h_pts_prev, h_src, h_dst, h_det, h_count, h_params;
+    size_t off_status = 0, off_mask = 0, off_result = 0, track_out_bytes = 0;
     int point_capacity = 0;
+    float2* d_pts_next() const { return d_track_out.as<float2>(); }
+    uint8_t* d_status() const { return d_track_out.as<uint8_t>() + off_status; }
+    uint8_t* d_mask() const { return d_track_out.as<uint8_t>() + off_mask; }
+    lvkb200::RansacResult* d_result() const
+    {
+        return reinterpret_cast<lvkb200::RansacResult*>(d_track_out.as<uint8_t>() + off_result);
+    }
+    // The tracking chain (H2D params+points -> LK -> swap-erase -> RANSAC -> one D2H) replayed as ONE CUDA graph per
+    // (frame parity, estimator): ~10 API calls and their inter-kernel gaps become one launch.
+    cudaGraphExec_t track_graph[2][2] = {};
+    bool use_graphs = true;
+    bool profile_stages = false;  // per-stage CUDA events (eager path); off by default
+    void destroy_graphs();
+    lvkb200_status enqueue_tracking(const std::vector<float>& pts, bool global, float threshold);
+    lvkb200_status record_tracking_chain(int parity, bool global, int max_points, bool with_events);
 
     // ---- StabilizationFilter / FrameTracker / FeatureDetector / PathSmoother host state
     lvkb200::FeatureGrid grid;
@@ -94,8 +113,6 @@ struct lvkb200_stream
     // FrameTracker::track on the frame in `slot`; fills motion (empty == nullopt).
     lvkb200_status track(const QueuedFrame& frame, lvkb200::Mesh& motion, bool* has_motion);
     lvkb200_status ensure_points(int n);
-    lvkb200_status enqueue_lk(const std::vector<float>& pts);
-    lvkb200_status enqueue_global_motion(int n, float threshold);
     lvkb200_status fetch_tracking(int n, bool with_model, std::vector<float>& matched, std::vector<uint8_t>& status,
                                   lvkb200::RansacResult* model, std::vector<uint8_t>& mask);
     lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold,
