@@ -162,6 +162,11 @@ def main():
     from tools.synth import Clip
 
     rank, local, world = _dist_env()
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (e.g. NCCL's version banner)
+    # is diverted to stderr, and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -290,7 +295,8 @@ def main():
             except Exception as e:  # the baseline must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -252,6 +252,13 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
 lvkb200_status lvkb200_find_homography(lvkb200_stream* s, const float* src_points, const float* dst_points,
                                        int count, float threshold, double h_out[9], uint8_t* mask);
 
+/* FrameTracker::estimate_global_motion's cv::estimateAffinePartial2D(..., cv::RANSAC, threshold, 50) branch, taken
+ * when the feature distribution is <= 0.6 (Vision/FrameTracker.cpp:37,171,362-373).  h_out = the 2x3 similarity
+ * [a -b tx; b a ty] promoted to 3x3 (Homography::FromAffineMatrix, Math/Homography.cpp:44-57); mask = inliers of the
+ * best minimal model, the transform = least squares over them. */
+lvkb200_status lvkb200_estimate_affine_partial(lvkb200_stream* s, const float* src_points, const float* dst_points,
+                                               int count, float threshold, double h_out[9], uint8_t* mask);
+
 /* FrameTracker::estimate_local_motions (Vision/FrameTracker.cpp:200-321): least-squares motion mesh.
  * mesh_state: in/out m_OptimizedMesh (2*cols*rows floats); offsets_out rows*cols float2; mask per point. */
 lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream* s, const float* tracked, const float* matched,

@@ -305,6 +305,18 @@ class Stream:
                                                       mask.ctypes.data_as(C.POINTER(C.c_uint8))))
         return H.reshape(3, 3), mask
 
+    def estimate_affine_partial(self, src_points, dst_points, threshold: float):
+        a, b = _f32(src_points, (-1, 2)), _f32(dst_points, (-1, 2))
+        n = a.shape[0]
+        H = np.zeros(9, dtype=np.float64)
+        mask = np.zeros(n, dtype=np.uint8)
+        _capi.check(self._lib.lvkb200_estimate_affine_partial(self._h, a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                              b.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                                              float(threshold),
+                                                              H.ctypes.data_as(C.POINTER(C.c_double)),
+                                                              mask.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return H.reshape(3, 3), mask
+
     def estimate_local_motions(self, tracked, matched, mesh_state):
         a, b = _f32(tracked, (-1, 2)), _f32(matched, (-1, 2))
         n = a.shape[0]

@@ -86,6 +86,7 @@ SYMBOLS = {
     "lvkb200_fast_detect": (C.c_int, [_vp, _u8p, _i, _i, _i, _i, _i, _i, _i, C.POINTER(KeyPoint), _i, C.POINTER(_i)]),
     "lvkb200_lk_track": (C.c_int, [_vp, _u8p, _u8p, _i, _i, _fp, _i, _i, _fp, _u8p]),
     "lvkb200_find_homography": (C.c_int, [_vp, _fp, _fp, _i, C.c_float, _dp, _u8p]),
+    "lvkb200_estimate_affine_partial": (C.c_int, [_vp, _fp, _fp, _i, C.c_float, _dp, _u8p]),
     "lvkb200_estimate_local_motions": (C.c_int, [_vp, _fp, _fp, _i, _fp, _fp, _u8p]),
 }
 

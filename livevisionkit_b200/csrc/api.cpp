@@ -453,11 +453,31 @@ lvkb200_status lvkb200_find_homography(lvkb200_stream* s, const float* src_point
     std::vector<float> b(dst_points, dst_points + 2 * static_cast<size_t>(count));
     std::vector<uint8_t> m;
     bool found = false;
-    LVKB_TRY(s->run_homography(a, b, threshold, h_out, m, &found));
+    LVKB_TRY(s->run_homography(a, b, threshold, 0, h_out, m, &found));
     std::memcpy(mask, m.data(), count);
     if (!found)
     {
         set_error("find_homography: no model (degenerate correspondences)");
+        return LVKB200_ERR_NO_MODEL;
+    }
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_estimate_affine_partial(lvkb200_stream* s, const float* src_points, const float* dst_points,
+                                               int count, float threshold, double h_out[9], uint8_t* mask)
+{
+    LVKB_REQUIRE(s != nullptr && src_points != nullptr && dst_points != nullptr && h_out != nullptr && mask != nullptr);
+    LVKB_REQUIRE(count >= 4);  // FrameTracker.cpp:335
+    LVKB_CUDA(cudaSetDevice(s->device));
+    std::vector<float> a(src_points, src_points + 2 * static_cast<size_t>(count));
+    std::vector<float> b(dst_points, dst_points + 2 * static_cast<size_t>(count));
+    std::vector<uint8_t> m;
+    bool found = false;
+    LVKB_TRY(s->run_homography(a, b, threshold, 1, h_out, m, &found));
+    std::memcpy(mask, m.data(), count);
+    if (!found)
+    {
+        set_error("estimate_affine_partial: no model (degenerate correspondences)");
         return LVKB200_ERR_NO_MODEL;
     }
     return LVKB200_OK;

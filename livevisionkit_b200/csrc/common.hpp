@@ -57,7 +57,7 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 struct TrackParams
 {
     int n;                  // points handed to the optical flow this frame
-    int reserved;
+    int model;              // 0 = homography (cv::findHomography), 1 = 4-dof similarity (cv::estimateAffinePartial2D)
     double lk_epsilon_sq;   // stopping epsilon of this calc() call (see lk_epsilon_for_call)
     float threshold_sq;     // acceptance threshold^2 of the motion estimator
     float reserved2;

@@ -131,13 +131,31 @@ __device__ __forceinline__ bool square_to_quad(const double qx[4], const double 
 
 __global__ void __launch_bounds__(128)
     k_ransac_hypotheses(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                        uint32_t seed, float* __restrict__ models)
+                        const TrackParams* __restrict__ prm, uint32_t seed, float* __restrict__ models)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= HYP) return;
     const int n = *n_ptr;
     float* out = models + (size_t)k * 9;
     out[8] = 0.0f;  // invalid until proven otherwise
+    if (prm->model == 1)
+    {
+        // cv::estimateAffinePartial2D minimal model: 2 correspondences -> similarity [a -b tx; b a ty]
+        if (n < 2) return;
+        const int i0 = (int)(hash32(seed ^ hash32((uint32_t)k * 977u)) % (uint32_t)n);
+        int i1 = (int)(hash32(seed ^ hash32((uint32_t)k * 977u + 1u)) % (uint32_t)(n - 1));
+        if (i1 >= i0) i1++;
+        const double x0 = src[i0].x, y0 = src[i0].y, x1 = src[i1].x, y1 = src[i1].y;
+        const double u0 = dst[i0].x, v0 = dst[i0].y, u1 = dst[i1].x, v1 = dst[i1].y;
+        const double dx = x1 - x0, dy = y1 - y0, du = u1 - u0, dv = v1 - v0;
+        const double den = dx * dx + dy * dy;
+        if (den < 1.0 || (du * du + dv * dv) < 1.0) return;  // coincident points: degenerate sample
+        const double a = (dx * du + dy * dv) / den, b = (dx * dv - dy * du) / den;
+        out[0] = (float)a; out[1] = (float)(-b); out[2] = (float)(u0 - (a * x0 - b * y0));
+        out[3] = (float)b; out[4] = (float)a; out[5] = (float)(v0 - (b * x0 + a * y0));
+        out[6] = 0.0f; out[7] = 0.0f; out[8] = 1.0f;
+        return;
+    }
     if (n < 4) return;
 
     int idx[4];
@@ -281,6 +299,64 @@ __global__ void __launch_bounds__(RT)
     {
         if (tid == 0) { result->found = 0; result->inliers = 0; }
         for (int i = tid; i < n; i += RT) mask[i] = 0;
+        return;
+    }
+
+    if (prm->model == 1)
+    {
+        // cv::estimateAffinePartial2D: the mask is the inlier set of the best minimal model (RANSACPointSetRegistrator),
+        // the returned transform is the least-squares similarity over those inliers (what its LM refinement converges
+        // to for this linear model).  Centred closed form: a = S(x'u'+y'v')/S(x'^2+y'^2), b = S(x'v'-y'u')/S(..).
+        float m[9];
+        for (int j = 0; j < 9; j++) m[j] = s_m[j];
+        double c[5] = {0, 0, 0, 0, 0};
+        for (int i = tid; i < n; i += RT)
+        {
+            const float e = reproj_err2(m, src[i], dst[i]);
+            const bool in = e < thr2;
+            mask[i] = in ? 1 : 0;
+            if (in) { c[0] += 1.0; c[1] += src[i].x; c[2] += src[i].y; c[3] += dst[i].x; c[4] += dst[i].y; }
+        }
+        for (int j = 0; j < 5; j++) c[j] = cg::reduce(warp, c[j], cg::plus<double>());
+        if (lane == 0) for (int j = 0; j < 5; j++) s_acc[wid][j] = c[j];
+        block.sync();
+        if (tid < 5)
+        {
+            double s = 0;
+            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
+            s_T[tid] = s;
+        }
+        block.sync();
+        const double cnt = s_T[0];
+        const double cx = s_T[1] / fmax(cnt, 1.0), cy = s_T[2] / fmax(cnt, 1.0);
+        const double cu = s_T[3] / fmax(cnt, 1.0), cv = s_T[4] / fmax(cnt, 1.0);
+        double q[3] = {0, 0, 0};
+        for (int i = tid; i < n; i += RT)
+        {
+            if (!mask[i]) continue;
+            const double x = src[i].x - cx, y = src[i].y - cy, u = dst[i].x - cu, v = dst[i].y - cv;
+            q[0] += x * x + y * y; q[1] += x * u + y * v; q[2] += x * v - y * u;
+        }
+        for (int j = 0; j < 3; j++) q[j] = cg::reduce(warp, q[j], cg::plus<double>());
+        block.sync();
+        if (lane == 0) for (int j = 0; j < 3; j++) s_acc[wid][j] = q[j];
+        block.sync();
+        if (tid == 0)
+        {
+            double s[3] = {0, 0, 0};
+            for (int w = 0; w < RT / 32; w++) for (int j = 0; j < 3; j++) s[j] += s_acc[w][j];
+            double a = m[0], b = m[3], tx = m[2], ty = m[5];
+            if (cnt >= 2.0 && s[0] > 1e-9)
+            {
+                a = s[1] / s[0]; b = s[2] / s[0];
+                tx = cu - (a * cx - b * cy); ty = cv - (b * cx + a * cy);
+            }
+            result->h[0] = a; result->h[1] = -b; result->h[2] = tx;
+            result->h[3] = b; result->h[4] = a; result->h[5] = ty;
+            result->h[6] = 0.0; result->h[7] = 0.0; result->h[8] = 1.0;
+            result->inliers = (int)cnt;
+            result->found = 1;
+        }
         return;
     }
 
@@ -463,7 +539,7 @@ lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const flo
                                  RansacResult* d_result, uint8_t* d_mask)
 {
     LVKB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(RansacResult), cs));
-    k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, 0x9E3779B9u, d_models);
+    k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, d_params, 0x9E3779B9u, d_models);
     k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, d_params, d_scores);
     k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, d_params, RANSAC_REFINE_ITERS, d_result,
                                       d_mask);

@@ -251,8 +251,7 @@ lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, in
     if (global)
     {
         // fast_filter + motion estimation chained on the device; the host replays the same erase order afterwards.
-        // TODO(K6b): cv::estimateAffinePartial2D(RANSAC) when distribution <= 0.6 (FrameTracker.cpp:362-373); until
-        // the similarity estimator lands the homography estimator serves badly distributed features as well.
+        // The model (homography / partial affine, FrameTracker.cpp:167-176) is selected by TrackParams::model.
         if (with_events) stage_begin(ST_ESTIMATE);
         LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next(), d_status(), prm, d_src.as<float2>(),
                                     d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(), d_count.as<int>()));
@@ -265,12 +264,13 @@ lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, in
 }
 
 // Enqueues the tracking chain for this frame's points (previous -> current pyramid).
-lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, bool global, float threshold)
+lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, bool global, float threshold, int model)
 {
     const int n = static_cast<int>(pts.size() / 2);
     LVKB_TRY(ensure_points(n));
     TrackParams* hp = h_params.as<TrackParams>();
     hp->n = n;
+    hp->model = model;
     hp->lk_epsilon_sq = lk_epsilon_for_call(lk_calls);
     hp->threshold_sq = threshold * threshold;
     lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
@@ -332,7 +332,8 @@ lvkb200_status lvkb200_stream::fetch_tracking(int n, bool with_model, std::vecto
 }
 
 lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked, const std::vector<float>& matched,
-                                              float threshold, double h[9], std::vector<uint8_t>& mask, bool* found)
+                                              float threshold, int model, double h[9], std::vector<uint8_t>& mask,
+                                              bool* found)
 {
     const int n = static_cast<int>(tracked.size() / 2);
     LVKB_REQUIRE(n >= 4);  // FrameTracker.cpp:335
@@ -342,6 +343,7 @@ lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked,
     *h_count.as<int>() = n;
     TrackParams* hp = h_params.as<TrackParams>();
     hp->n = n;
+    hp->model = model;
     hp->lk_epsilon_sq = 0.0;
     hp->threshold_sq = threshold * threshold;
     LVKB_CUDA(cudaMemcpyAsync(d_params.ptr, h_params.ptr, sizeof(TrackParams), cudaMemcpyHostToDevice, cs));
@@ -444,7 +446,9 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
     const int n_tracked = static_cast<int>(features.size());
     const bool global = !settings.track_local_motions;
-    LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold));
+    // FrameTracker.cpp:167-176: homography when the features are well distributed, partial affine otherwise
+    const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
+    LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold, model_kind));
     RansacResult model{};
     std::vector<uint8_t> inliers;
     LVKB_TRY(fetch_tracking(n_tracked, global, matched, status, &model, inliers));
@@ -477,7 +481,6 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
 
     // ---- motion estimation (FrameTracker.cpp:157-176)
-    (void)distribution;
     if (settings.track_local_motions)
     {
         stage_begin(ST_ESTIMATE);

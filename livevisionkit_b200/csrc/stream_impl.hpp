@@ -54,7 +54,7 @@ struct lvkb200_stream
     bool use_graphs = true;
     bool profile_stages = false;  // per-stage CUDA events (eager path); off by default
     void destroy_graphs();
-    lvkb200_status enqueue_tracking(const std::vector<float>& pts, bool global, float threshold);
+    lvkb200_status enqueue_tracking(const std::vector<float>& pts, bool global, float threshold, int model);
     lvkb200_status record_tracking_chain(int parity, bool global, int max_points, bool with_events);
 
     // ---- StabilizationFilter / FrameTracker / FeatureDetector / PathSmoother host state
@@ -115,7 +115,7 @@ struct lvkb200_stream
     lvkb200_status ensure_points(int n);
     lvkb200_status fetch_tracking(int n, bool with_model, std::vector<float>& matched, std::vector<uint8_t>& status,
                                   lvkb200::RansacResult* model, std::vector<uint8_t>& mask);
-    lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold,
+    lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold, int model,
                                   double h[9], std::vector<uint8_t>& mask, bool* found);
     lvkb200_status apply_mesh(const QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,
                               lvkb200_memspace out_space);

@@ -247,6 +247,69 @@ def test_homography_pure_translation(gpu_stream):
     assert np.allclose(H, [[1, 0, 3], [0, 1, -2], [0, 0, 1]], atol=1e-4)
 
 
+@pytest.mark.parametrize("noise,outliers", [(0.0, 0.0), (0.1, 0.2), (0.3, 0.35)])
+def test_affine_partial_contract(gpu_stream, noise, outliers):
+    """cv::estimateAffinePartial2D(RANSAC, thr, 50) branch (FrameTracker.cpp:362-373)."""
+    rng = np.random.default_rng(int(noise * 100) + int(outliers * 1000) + 7)
+    n, thr = 900, 3.0
+    p = np.stack([rng.uniform(5, 475, n), rng.uniform(5, 265, n)], axis=1).astype(np.float32)
+    ang, sc = np.deg2rad(0.6), 1.004
+    A = np.array([[sc * np.cos(ang), -sc * np.sin(ang), 2.2], [sc * np.sin(ang), sc * np.cos(ang), -1.4]])
+    q = (p @ A[:, :2].T + A[:, 2]).astype(np.float32) + rng.normal(0, noise, (n, 2)).astype(np.float32)
+    n_out = int(outliers * n)
+    q[:n_out] += rng.uniform(-50, 50, (n_out, 2)).astype(np.float32)
+    Ac, mc = cv2.estimateAffinePartial2D(p.reshape(-1, 1, 2), q.reshape(-1, 1, 2), None, cv2.RANSAC, thr, 50)
+    Hg, mg = gpu_stream.estimate_affine_partial(p, q, thr)
+    mc = mc.reshape(-1).astype(np.uint8)
+    # a similarity: [a -b tx; b a ty; 0 0 1]
+    assert abs(Hg[0, 0] - Hg[1, 1]) < 1e-12 and abs(Hg[0, 1] + Hg[1, 0]) < 1e-12 and (Hg[2] == [0, 0, 1]).all()
+    Hc = np.eye(3)
+    Hc[:2] = Ac
+    e_c = np.linalg.norm(p @ Hc[:2, :2].T + Hc[:2, 2] - q, axis=1)
+    e_g = np.linalg.norm(p @ Hg[:2, :2].T + Hg[:2, 2] - q, axis=1)
+    borderline = (np.abs(e_c - thr) < 0.5) | (np.abs(e_g - thr) < 0.5)
+    hard = (mc != mg) & ~borderline
+    disp = _corner_disp(Hc, Hg, 480, 270)
+    truth = np.eye(3)
+    truth[:2] = A
+    print(f"affine noise={noise} outliers={outliers}: inliers cv2 {int(mc.sum())} gpu {int(mg.sum())}, mismatches "
+          f"{int((mc != mg).sum())} ({int(hard.sum())} not borderline), corner disp vs cv2 {disp:.4f} px; vs truth cv2 "
+          f"{_corner_disp(Hc, truth, 480, 270):.4f} gpu {_corner_disp(Hg, truth, 480, 270):.4f}")
+    assert hard.sum() == 0
+    assert disp <= (1e-3 if noise == 0.0 else 0.25)
+
+
+def test_pipeline_takes_the_affine_branch_on_clustered_features(oracle):
+    """Features confined to one corner -> distribution <= 0.6 -> estimateAffinePartial2D branch, vs the oracle."""
+    import livevisionkit_b200 as L
+    from livevisionkit_b200 import _capi as K
+    from tools.synth import Clip
+    clip = Clip((960, 540), "shake", frames=6, seed=3)
+    so = oracle.StabilizationSettings.obs_homography_preset()
+    so.uniformity_threshold = 0.0
+    sg = L.StabilizationFilterSettings.obs_homography_preset()
+    sg.uniformity_threshold = 0.0
+    ref, flt = oracle.StabilizationFilter(so), L.StabilizationFilter(sg, 0)
+    flt.stream.set_debug_capture(True)
+    took_affine = False
+    for i in range(6):
+        f = clip[i].copy()
+        f[:, 400:] = 90   # flatten everything except the left part of the frame: corners only on the left
+        f[300:, :] = 90
+        ref.apply(f, oracle.BGR, i)
+        flt.apply(L.VideoFrame(f, i, L.BGR))
+        tr = ref.trace
+        if "H" in tr and tr["distribution"] <= np.float32(0.6):
+            took_affine = True
+            Hg = flt.stream.debug_fetch(K.DBG_HOMOGRAPHY, np.float64).reshape(3, 3)
+            assert (Hg[2] == [0, 0, 1]).all() and abs(Hg[0, 0] - Hg[1, 1]) < 1e-12  # a similarity, like the oracle's
+            assert (tr["H"][2] == [0, 0, 1]).all()
+            assert _corner_disp(Hg, tr["H"], 200, 150) <= 0.25
+            inl = flt.stream.debug_fetch(K.DBG_INLIERS, np.uint8)
+            assert len(inl) == len(tr["inliers"]) and (inl != tr["inliers"]).mean() < 0.02
+    assert took_affine, "the clip never produced a badly distributed feature set"
+
+
 def test_local_motions_vs_oracle(gpu_stream, oracle):
     import livevisionkit_b200 as L
     s = L.Stream(L.StabilizationFilterSettings(), 0)  # defaults: 256x256, 2x2 mesh, local motions
