@@ -156,6 +156,24 @@ lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_
                                      void* out, size_t out_pitch, lvkb200_memspace out_space, lvkb200_result* res);
 lvkb200_status lvkb200_stream_sync(lvkb200_stream* s);
 
+/* Pipelined operation — VideoFilter::stream(cap, callback, profile) (Filters/VideoFilter.cpp:62-209) overlaps input,
+ * filtering and output with three host threads and bounded queues.  The GPU analogue uses two extra CUDA streams:
+ *   lvkb200_stream_prefetch(next frame)   starts the host->device upload of the NEXT input (host memory, ideally
+ *                                         pinned) while the current frame is processed; the following submit of the
+ *                                         same pointer adopts the uploaded buffer.  The caller must keep the frame
+ *                                         unmodified until that submit returns.
+ *   lvkb200_stream_submit_async(...)      == lvkb200_stream_submit, except that a HOST output is downloaded on the
+ *                                         copy-out stream after the call returns; *ticket (0 when there is no
+ *                                         output) identifies it.
+ *   lvkb200_stream_wait_output(ticket)    returns once that output has landed in the caller's buffer.
+ * Results are identical to lvkb200_stream_submit; only the copies overlap. */
+lvkb200_status lvkb200_stream_prefetch(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height);
+lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                           lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
+                                           void* out, size_t out_pitch, lvkb200_memspace out_space,
+                                           lvkb200_result* res, uint64_t* ticket);
+lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket);
+
 /* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
  * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for
  * the later one.  The per-stage analogue of Stopwatch (Timing/Stopwatch.cpp:42-64) for the bench harness. */

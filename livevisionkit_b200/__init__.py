@@ -184,6 +184,57 @@ class Stream:
                                                     ospace, C.byref(res)))
         return res
 
+    def __call__(self, frames, callback, outputs=None) -> int:
+        """Pipelined VideoFilter::stream: see StabilizationFilter.stream_frames."""
+        frames = list(frames)
+        if not frames:
+            return 0
+        if outputs is None:
+            outputs = [np.empty_like(frames[0].data) for _ in range(3)]
+        if len(outputs) < 3:
+            raise ValueError("stream() needs at least 3 output buffers")
+        pending, delivered = None, 0
+        for i, f in enumerate(frames):
+            if i + 1 < len(frames):
+                self.prefetch(frames[i + 1].data)
+            out = outputs[i % len(outputs)]
+            res, ticket = self.submit_async(f.data, out, f.format, f.timestamp)
+            if pending is not None:
+                self.wait_output(pending[0])
+                delivered += 1
+                keep_going = callback(pending[1])
+                pending = None
+                if keep_going is False:
+                    return delivered
+            if res.has_output:
+                pending = (ticket, VideoFrame(out, int(res.out_timestamp), int(res.out_format)))
+        if pending is not None:
+            self.wait_output(pending[0])
+            delivered += 1
+            callback(pending[1])
+        return delivered
+
+    def prefetch(self, frame):
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        if space != _capi.MEM_HOST or ch != 3:
+            raise ValueError("prefetch takes packed 8UC3 host frames")
+        _capi.check(self._lib.lvkb200_stream_prefetch(self._h, ptr, pitch, w, h))
+
+    def submit_async(self, frame, out, fmt: int = BGR, timestamp: int = 0):
+        """-> (Result, ticket).  Like submit(); a host `out` is filled after the call (see wait_output)."""
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        optr, opitch, oh, ow, och, ospace = _buffer_info(out)
+        if (oh, ow, och) != (h, w, ch):
+            raise ValueError("output buffer must match the input frame")
+        res = _capi.Result()
+        ticket = C.c_uint64(0)
+        _capi.check(self._lib.lvkb200_stream_submit_async(self._h, ptr, pitch, w, h, fmt, timestamp, space, optr,
+                                                          opitch, ospace, C.byref(res), C.byref(ticket)))
+        return res, int(ticket.value)
+
+    def wait_output(self, ticket: int):
+        _capi.check(self._lib.lvkb200_stream_wait_output(self._h, ticket))
+
     def event_record(self, index: int):
         _capi.check(self._lib.lvkb200_stream_event_record(self._h, index))
 
@@ -363,6 +414,16 @@ class StabilizationFilter:
 
     def stable_region(self, width: int, height: int):
         return self.stream.stable_region(width, height)
+
+    def stream_frames(self, frames, callback, outputs=None) -> int:
+        """lvk::VideoFilter::stream(input, callback, profile) (Filters/VideoFilter.cpp:62-209); also reachable as
+        `filter.stream(frames, callback)` because the `stream` attribute is callable.  Pushes every frame of
+        `frames` (a sequence of VideoFrame with HOST data) through the filter and hands each non-empty output to
+        `callback(VideoFrame) -> bool` (False stops the stream, like the reference).  The reference overlaps input,
+        filtering and output with three threads; here the upload of frame t+1 and the download of output t-1 overlap
+        the processing of frame t on separate CUDA streams.  `outputs`: optional list of >= 3 reusable host buffers
+        (pinned memory makes the copies truly asynchronous).  Returns the number of outputs delivered."""
+        return self.stream(frames, callback, outputs)  # Stream.__call__ (the attribute doubles as the method)
 
     def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
         """`output`: optional preallocated buffer (numpy or CUDA tensor) receiving the result."""

@@ -236,6 +236,36 @@ lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_
     return s->submit(frame, pitch, width, height, format, timestamp, frame_space, out, out_pitch, out_space, res);
 }
 
+lvkb200_status lvkb200_stream_prefetch(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->prefetch(frame, pitch, width, height);
+}
+
+lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                           lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
+                                           void* out, size_t out_pitch, lvkb200_memspace out_space,
+                                           lvkb200_result* res, uint64_t* ticket)
+{
+    LVKB_REQUIRE(s != nullptr && frame != nullptr && res != nullptr && ticket != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    s->deferred_output = true;
+    s->last_ticket = 0;
+    const lvkb200_status st = s->submit(frame, pitch, width, height, format, timestamp, frame_space, out, out_pitch,
+                                        out_space, res);
+    s->deferred_output = false;
+    *ticket = (st == LVKB200_OK && res->has_output) ? s->last_ticket : 0;
+    return st;
+}
+
+lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->wait_output(ticket);
+}
+
 lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item which, void* buffer, size_t capacity,
                                           size_t* size)
 {

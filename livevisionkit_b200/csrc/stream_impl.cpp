@@ -548,7 +548,22 @@ lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& of
     p.height = src.h;
     p.yuv = src.format == LVKB200_YUV;  // Image.cpp:100
     for (int k = 0; k < 3; k++) p.bg[k] = static_cast<uint8_t>(settings.background_colour[k]);  // Image.cpp:136-141
-    LVKB_TRY(stage_frame_out(out, out_pitch, src.w, src.h, 3, out_space, &p.dst, &p.dst_pitch));
+    const bool deferred = deferred_output && out_space == LVKB200_MEM_HOST;
+    int slot = 0;
+    if (deferred)
+    {
+        // pipelined output: remap into one of two device staging buffers; the copy-out stream downloads it while
+        // the next frame is being processed (lvkb200_stream_wait_output waits for that download)
+        LVKB_TRY(ensure_pipeline());
+        last_ticket = ++async_tickets;
+        slot = static_cast<int>(last_ticket & 1);
+        p.dst_pitch = align_up(static_cast<size_t>(src.w) * 3, 16);
+        LVKB_CUDA(async_out[slot].ensure(p.dst_pitch * src.h));
+        p.dst = async_out[slot].as<uint8_t>();
+        if (async_out_used[slot]) LVKB_CUDA(cudaStreamWaitEvent(cs, async_out_done[slot], 0));  // its last download
+    }
+    else
+        LVKB_TRY(stage_frame_out(out, out_pitch, src.w, src.h, 3, out_space, &p.dst, &p.dst_pitch));
     stage_begin(ST_REMAP);
     if (settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2)
     {
@@ -567,7 +582,68 @@ lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& of
         LVKB_CUDA(launch_remap_mesh(cs, p, dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
     }
     stage_end(ST_REMAP);
+    if (ring_reads_done) LVKB_CUDA(cudaEventRecord(ring_reads_done, cs));
+    if (deferred)
+    {
+        LVKB_CUDA(cudaEventRecord(async_remap_done[slot], cs));
+        LVKB_CUDA(cudaStreamWaitEvent(cs_out, async_remap_done[slot], 0));
+        LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(src.w) * 3, src.h,
+                                    cudaMemcpyDeviceToHost, cs_out));
+        LVKB_CUDA(cudaEventRecord(async_out_done[slot], cs_out));
+        async_out_used[slot] = true;
+        return LVKB200_OK;
+    }
     return finish_frame_out(out, out_pitch, src.w, src.h, 3, out_space);
+}
+
+lvkb200_status lvkb200_stream::ensure_pipeline()
+{
+    if (cs_in) return LVKB200_OK;
+    LVKB_CUDA(cudaStreamCreateWithFlags(&cs_in, cudaStreamNonBlocking));
+    LVKB_CUDA(cudaStreamCreateWithFlags(&cs_out, cudaStreamNonBlocking));
+    LVKB_CUDA(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
+    LVKB_CUDA(cudaEventCreateWithFlags(&ring_reads_done, cudaEventDisableTiming));
+    LVKB_CUDA(cudaEventRecord(ring_reads_done, cs));
+    for (int k = 0; k < 2; k++)
+    {
+        LVKB_CUDA(cudaEventCreateWithFlags(&async_remap_done[k], cudaEventDisableTiming));
+        LVKB_CUDA(cudaEventCreateWithFlags(&async_out_done[k], cudaEventDisableTiming));
+    }
+    return LVKB200_OK;
+}
+
+// Starts the upload of the NEXT input frame (host memory) on the copy-in stream; the following submit of the same
+// pointer adopts the uploaded buffer instead of copying.
+lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int width, int height)
+{
+    LVKB_REQUIRE(frame != nullptr && width > 0 && height > 0);
+    const size_t row = static_cast<size_t>(width) * 3;
+    LVKB_REQUIRE(pitch >= row);
+    LVKB_TRY(ensure_pipeline());
+    prefetch_slot.pitch = align_up(row, 16);
+    prefetch_slot.w = width;
+    prefetch_slot.h = height;
+    if (prefetch_slot.buf.capacity < prefetch_slot.pitch * height)
+    {
+        LVKB_CUDA(cudaStreamSynchronize(cs));  // the buffer being replaced may still be read by a queued remap
+        LVKB_CUDA(prefetch_slot.buf.ensure(prefetch_slot.pitch * height));
+    }
+    // the spare buffer was a ring buffer until the last swap: wait for the last kernel that read ring memory
+    LVKB_CUDA(cudaStreamWaitEvent(cs_in, ring_reads_done, 0));
+    LVKB_CUDA(cudaMemcpy2DAsync(prefetch_slot.buf.ptr, prefetch_slot.pitch, frame, pitch, row, height,
+                                cudaMemcpyHostToDevice, cs_in));
+    LVKB_CUDA(cudaEventRecord(prefetch_done, cs_in));
+    prefetched_ptr = frame;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::wait_output(uint64_t ticket)
+{
+    if (ticket == 0 || !cs_out) return LVKB200_OK;
+    LVKB_REQUIRE(ticket <= async_tickets);
+    // waits for the most recent download recorded on that staging slot (>= the ticket's own download)
+    LVKB_CUDA(cudaEventSynchronize(async_out_done[ticket & 1]));
+    return LVKB200_OK;
 }
 
 lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width, int height, lvkb200_format format,
@@ -602,19 +678,33 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
         ring_size++;
     }
     QueuedFrame& q = ring[slot];
-    q.pitch = align_up(row, 16);
-    LVKB_CUDA(q.buf.ensure(q.pitch * height));
+    const bool prefetched = frame_space == LVKB200_MEM_HOST && prefetched_ptr == frame && prefetch_slot.w == width &&
+                            prefetch_slot.h == height && prefetch_slot.pitch == align_up(row, 16);
+    if (prefetched)
+    {
+        // lvkb200_stream_prefetch already uploaded this frame into the spare buffer on the copy-in stream:
+        // adopt that buffer (O(1) swap) and make this stream wait for the upload instead of copying again.
+        std::swap(q.buf, prefetch_slot.buf);
+        q.pitch = prefetch_slot.pitch;
+        LVKB_CUDA(cudaStreamWaitEvent(cs, prefetch_done, 0));
+        prefetched_ptr = nullptr;
+    }
+    else
+    {
+        q.pitch = align_up(row, 16);
+        LVKB_CUDA(q.buf.ensure(q.pitch * height));
+        LVKB_CUDA(cudaMemcpy2DAsync(q.buf.ptr, q.pitch, frame, pitch, row, height,
+                                    frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+    }
     q.w = width; q.h = height; q.format = format; q.timestamp = timestamp;
-    LVKB_CUDA(cudaMemcpy2DAsync(q.buf.ptr, q.pitch, frame, pitch, row, height,
-                                frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
     // The caller keeps ownership of its buffer: host memory must have been consumed before we return.
     struct InputGuard
     {
         lvkb200_stream* s;
         bool host;
         ~InputGuard() { if (host && s->input_copied) cudaEventSynchronize(s->input_copied); }
-    } input_guard{this, frame_space == LVKB200_MEM_HOST};
-    if (frame_space == LVKB200_MEM_HOST)
+    } input_guard{this, frame_space == LVKB200_MEM_HOST && !prefetched};
+    if (frame_space == LVKB200_MEM_HOST && !prefetched)
     {
         if (!input_copied) LVKB_CUDA(cudaEventCreateWithFlags(&input_copied, cudaEventDisableTiming));
         LVKB_CUDA(cudaEventRecord(input_copied, cs));
@@ -745,6 +835,24 @@ void lvkb200_stream::release()
     for (auto& f : ring) f.buf.release();
     if (input_copied) cudaEventDestroy(input_copied);
     input_copied = nullptr;
+    if (cs_in) cudaStreamSynchronize(cs_in);
+    if (cs_out) cudaStreamSynchronize(cs_out);
+    prefetch_slot.buf.release();
+    for (int k = 0; k < 2; k++)
+    {
+        async_out[k].release();
+        if (async_remap_done[k]) cudaEventDestroy(async_remap_done[k]);
+        if (async_out_done[k]) cudaEventDestroy(async_out_done[k]);
+        async_remap_done[k] = async_out_done[k] = nullptr;
+        async_out_used[k] = false;
+    }
+    if (prefetch_done) cudaEventDestroy(prefetch_done);
+    if (ring_reads_done) cudaEventDestroy(ring_reads_done);
+    prefetch_done = ring_reads_done = nullptr;
+    if (cs_in) cudaStreamDestroy(cs_in);
+    if (cs_out) cudaStreamDestroy(cs_out);
+    cs_in = cs_out = nullptr;
+    prefetched_ptr = nullptr;
     for (auto& e : user_events)
     {
         if (e) cudaEventDestroy(e);

@@ -80,6 +80,24 @@ struct lvkb200_stream
     size_t ring_start = 0, ring_size = 0;
     cudaEvent_t input_copied = nullptr;  // the caller's (host) frame has been consumed
 
+    // ---- pipelined operation (the GPU analogue of VideoFilter::stream's three threads, Filters/VideoFilter.cpp:62-209):
+    // a copy-in stream uploads the NEXT host frame into a spare buffer while this frame is processed, and a copy-out
+    // stream downloads the PREVIOUS output from one of two staging buffers.
+    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+    QueuedFrame prefetch_slot;
+    const void* prefetched_ptr = nullptr;
+    cudaEvent_t prefetch_done = nullptr;    // recorded on cs_in after the upload
+    cudaEvent_t ring_reads_done = nullptr;  // recorded on cs after the last kernel that read a ring buffer (remap)
+    lvkb200::DeviceBuffer async_out[2];
+    cudaEvent_t async_remap_done[2] = {}, async_out_done[2] = {};
+    bool async_out_used[2] = {false, false};
+    uint64_t async_tickets = 0;
+    bool deferred_output = false;  // set for the duration of a submit_async call
+    uint64_t last_ticket = 0;
+    lvkb200_status prefetch(const void* frame, size_t pitch, int width, int height);
+    lvkb200_status wait_output(uint64_t ticket);
+    lvkb200_status ensure_pipeline();
+
     // ---- per-stage CUDA events of the last submit (ingest, pyramid, fast, lk, estimate, remap)
     // Double-buffered by frame parity so that totals can be harvested two frames late without any extra sync.
     cudaEvent_t stage_ev[2][LVKB200_STAGE_COUNT][2] = {};

@@ -131,6 +131,35 @@ def test_host_and_device_frames_agree(oracle):
             assert (va.data == vb.data.cpu().numpy()).all() and va.timestamp == vb.timestamp == i - 10
 
 
+def test_pipelined_stream_equals_apply(oracle):
+    """VideoFilter::stream analogue (prefetch + submit_async + wait_output on extra CUDA streams) must deliver exactly
+    what the synchronous apply() delivers, frame for frame."""
+    torch = pytest.importorskip("torch")
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    clip = Clip("720p", "shake", frames=26)
+    s = L.StabilizationFilterSettings.obs_homography_preset()
+    ref = L.StabilizationFilter(s, 0)
+    expected = []
+    for i in range(26):
+        v = ref.apply(L.VideoFrame(clip[i], 100 + i, L.BGR))
+        if not v.empty():
+            expected.append((v.timestamp, v.data.copy()))
+    pipe = L.StabilizationFilter(s, 0)
+    frames = [L.VideoFrame(torch.from_numpy(clip[i]).pin_memory(), 100 + i, L.BGR) for i in range(26)]
+    outs = [torch.empty_like(frames[0].data).pin_memory() for _ in range(3)]
+    got = []
+    n = pipe.stream(frames, lambda vf: got.append((vf.timestamp, vf.data.numpy().copy())), outs)
+    assert n == len(expected) == 16
+    for (te, de), (tg, dg) in zip(expected, got):
+        assert te == tg and (de == dg).all()
+    # early stop: the callback returning False ends the stream like the reference's
+    pipe2 = L.StabilizationFilter(s, 0)
+    seen = []
+    n2 = pipe2.stream(frames, lambda vf: (seen.append(vf.timestamp), len(seen) < 3)[1], outs)
+    assert n2 == 3 and seen == [100, 101, 102]
+
+
 def test_stabilize_output_off_is_a_pure_delay(oracle):
     import livevisionkit_b200 as L
     from tools.synth import Clip
