@@ -42,6 +42,20 @@ namespace
 constexpr int HYP = RANSAC_HYPOTHESES;
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Zero-copy transfers of the chain's tiny inputs/outputs (params, <= 2 601 points, status/mask/model): a kernel
+// reads/writes MAPPED pinned host memory directly.  A cudaMemcpyAsync would queue on the copy engines behind the
+// multi-megabyte frame upload/download of the neighbouring frames (pipelined operation) and stall the whole chain.
+
+__global__ void __launch_bounds__(256)
+    k_transfer2(const uint4* __restrict__ src0, uint4* __restrict__ dst0, int n0, const uint4* __restrict__ src1,
+                uint4* __restrict__ dst1, int n1)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < n0; i += nth) dst0[i] = src0[i];
+    for (int i = tid; i < n1; i += nth) dst1[i] = src1[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // fast_filter: for k = n-1 .. 0: if !keep[k]: data[k] = data.back(); data.pop_back()
 
 constexpr int CT = 1024;
@@ -523,6 +537,18 @@ __global__ void __launch_bounds__(RT)
 }
 
 }  // namespace
+
+lvkb200_status zero_copy_transfer(cudaStream_t cs, const void* src0, void* dst0, size_t bytes0, const void* src1,
+                                  void* dst1, size_t bytes1)
+{
+    // all pointers 16-byte aligned, sizes rounded up to 16 by the caller's allocations
+    const int n0 = static_cast<int>((bytes0 + 15) / 16), n1 = static_cast<int>((bytes1 + 15) / 16);
+    k_transfer2<<<8, 256, 0, cs>>>(static_cast<const uint4*>(src0), static_cast<uint4*>(dst0), n0,
+                                   static_cast<const uint4*>(src1), static_cast<uint4*>(dst1), n1);
+    count_launches(1);
+    LVKB_CUDA(cudaGetLastError());
+    return LVKB200_OK;
+}
 
 lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,
                                   const TrackParams* d_params, float2* d_a_out, float2* d_b_out, int* d_perm,

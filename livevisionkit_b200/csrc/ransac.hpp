@@ -18,6 +18,11 @@ struct RansacResult
     int pad;
 };
 
+// Copies two small blocks with a kernel (sources/destinations may be mapped pinned host memory): keeps the tracking
+// chain off the copy engines.  Pointers must be 16-byte aligned and the allocations padded to multiples of 16 bytes.
+lvkb200_status zero_copy_transfer(cudaStream_t cs, const void* src0, void* dst0, size_t bytes0, const void* src1,
+                                  void* dst1, size_t bytes1);
+
 // fast_filter on the device: keeps a[i], b[i] where keep[i] != 0, in the reference's swap-erase order.
 // d_perm / d_removed: scratch of n ints each.  *d_n_out receives the surviving count.
 lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,

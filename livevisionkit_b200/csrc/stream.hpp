@@ -44,9 +44,18 @@ struct PinnedBuffer
         if (ptr) cudaFreeHost(ptr);
         ptr = nullptr;
         capacity = 0;
-        cudaError_t e = cudaMallocHost(&ptr, bytes);
+        // mapped: kernels may read/write it directly over PCIe (zero-copy), bypassing the copy engines
+        cudaError_t e = cudaHostAlloc(&ptr, bytes, cudaHostAllocMapped);
         if (e == cudaSuccess) capacity = bytes;
         return e;
+    }
+    // Device-side address of this host allocation (zero-copy access).
+    template <typename T>
+    T* device_view() const
+    {
+        void* d = nullptr;
+        if (!ptr || cudaHostGetDevicePointer(&d, ptr, 0) != cudaSuccess) return nullptr;
+        return static_cast<T*>(d);
     }
     void release()
     {

@@ -206,7 +206,7 @@ lvkb200_status lvkb200_stream::ensure_points(int n)
     off_status = sizeof(float2) * static_cast<size_t>(cap);
     off_mask = off_status + static_cast<size_t>(cap);
     off_result = align_up(off_mask + static_cast<size_t>(cap), 16);
-    track_out_bytes = off_result + sizeof(RansacResult);
+    track_out_bytes = align_up(off_result + sizeof(RansacResult), 16);  // moved as whole 16-byte words
     LVKB_CUDA(d_track_out.ensure(track_out_bytes));
     LVKB_CUDA(h_track_out.ensure(track_out_bytes));
     LVKB_CUDA(d_pts_prev.ensure(sizeof(float2) * cap));
@@ -217,9 +217,9 @@ lvkb200_status lvkb200_stream::ensure_points(int n)
     LVKB_CUDA(d_perm.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_removed.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_count.ensure(sizeof(int)));
-    LVKB_CUDA(d_params.ensure(sizeof(TrackParams)));
+    LVKB_CUDA(d_params.ensure(align_up(sizeof(TrackParams), 16)));
     LVKB_CUDA(h_count.ensure(sizeof(int)));
-    LVKB_CUDA(h_params.ensure(sizeof(TrackParams)));
+    LVKB_CUDA(h_params.ensure(align_up(sizeof(TrackParams), 16)));
     LVKB_CUDA(h_pts_prev.ensure(sizeof(float2) * cap));
     LVKB_CUDA(h_src.ensure(sizeof(float2) * cap));
     LVKB_CUDA(h_dst.ensure(sizeof(float2) * cap));
@@ -243,8 +243,13 @@ void lvkb200_stream::destroy_graphs()
 lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, int max_points, bool with_events)
 {
     const TrackParams* prm = d_params.as<TrackParams>();
-    LVKB_CUDA(cudaMemcpyAsync(d_params.ptr, h_params.ptr, sizeof(TrackParams), cudaMemcpyHostToDevice, cs));
-    LVKB_CUDA(cudaMemcpyAsync(d_pts_prev.ptr, h_pts_prev.ptr, sizeof(float2) * max_points, cudaMemcpyHostToDevice, cs));
+    // inputs come straight out of mapped pinned memory (a kernel, not the copy engine: see k_transfer2)
+    const void* hp = h_params.device_view<void>();
+    const void* hpts = h_pts_prev.device_view<void>();
+    void* hout = h_track_out.device_view<void>();
+    LVKB_REQUIRE(hp != nullptr && hpts != nullptr && hout != nullptr);
+    LVKB_TRY(zero_copy_transfer(cs, hp, d_params.ptr, sizeof(TrackParams), hpts, d_pts_prev.ptr,
+                                sizeof(float2) * max_points));
     if (with_events) stage_begin(ST_LK);
     LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], d_pts_prev.as<float2>(), max_points, prm, d_pts_next(), d_status()));
     if (with_events) stage_end(ST_LK);
@@ -259,7 +264,8 @@ lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, in
                                    d_models.as<float>(), d_scores.as<float>(), d_result(), d_mask()));
         if (with_events) stage_end(ST_ESTIMATE);
     }
-    LVKB_CUDA(cudaMemcpyAsync(h_track_out.ptr, d_track_out.ptr, track_out_bytes, cudaMemcpyDeviceToHost, cs));
+    // results go straight into mapped pinned memory; visible to the host after the stream synchronisation
+    LVKB_TRY(zero_copy_transfer(cs, d_track_out.ptr, hout, track_out_bytes, nullptr, nullptr, 0));
     return LVKB200_OK;
 }
 
@@ -306,7 +312,7 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
         }
     }
     LVKB_CUDA(cudaGraphLaunch(exec, cs));
-    count_launches(global ? 5 : 1);
+    count_launches(global ? 7 : 3);  // transfer-in, LK, [compact, hypotheses, score, refine], transfer-out
     return LVKB200_OK;
 }
 
