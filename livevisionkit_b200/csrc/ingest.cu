@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(THREADS)
                        const int2* __restrict__ ytab, const float* __restrict__ yw, int yt, int fast, float fast_scale,
                        uint8_t* __restrict__ dst, size_t dst_pitch)
 {
-    __shared__ uint8_t gray[MAX_SH * MAX_SW];
+    __shared__ __align__(16) uint8_t gray[MAX_SH * MAX_SW];
     __shared__ float buf[DT_H * MAX_YT * DT_W];
 
     const int dx0 = blockIdx.x * DT_W, dy0 = blockIdx.y * DT_H;
@@ -49,9 +49,30 @@ __global__ void __launch_bounds__(THREADS)
     const int sy0 = yf.x, sh = yl.x + yl.y - yf.x;
 
     // ---- stage 1: gray source footprint -> smem (coalesced along x)
-    for (int idx = threadIdx.x; idx < sw * sh; idx += THREADS)
+    // Fast path for packed 3-byte pixels on 4-byte aligned rows: 4 pixels = 12 bytes = three 32-bit loads per thread
+    // (4x fewer load instructions than byte loads), one 32-bit shared store.
+    const bool vec4 = (px_stride == 3) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0) &&
+                      (((size_t)sx0 * 3) & 3) == 0 && !(c1 == 0 && c2 == 0);
+    if (vec4)
     {
-        const int r = idx / sw, c = idx - r * sw;
+        const int groups = sw >> 2;  // whole groups of 4 pixels; the <= 3 pixel tail falls through to the byte loop
+        for (int idx = threadIdx.x; idx < groups * sh; idx += THREADS)
+        {
+            const int r = idx / groups, gidx = idx - r * groups;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (size_t)(sy0 + r) * pitch + (size_t)sx0 * 3) + 3 * gidx;
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            const int g0 = (c0 * (int)(w0 & 255) + c1 * (int)((w0 >> 8) & 255) + c2 * (int)((w0 >> 16) & 255) + (1 << 14)) >> 15;
+            const int g1 = (c0 * (int)(w0 >> 24) + c1 * (int)(w1 & 255) + c2 * (int)((w1 >> 8) & 255) + (1 << 14)) >> 15;
+            const int g2 = (c0 * (int)((w1 >> 16) & 255) + c1 * (int)(w1 >> 24) + c2 * (int)(w2 & 255) + (1 << 14)) >> 15;
+            const int g3 = (c0 * (int)((w2 >> 8) & 255) + c1 * (int)((w2 >> 16) & 255) + c2 * (int)(w2 >> 24) + (1 << 14)) >> 15;
+            *reinterpret_cast<uint32_t*>(&gray[r * MAX_SW + 4 * gidx]) = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+        }
+    }
+    const int c_begin = vec4 ? (sw & ~3) : 0;
+    const int tail = sw - c_begin;
+    for (int idx = threadIdx.x; idx < tail * sh; idx += THREADS)
+    {
+        const int r = idx / tail, c = c_begin + (idx - r * tail);
         const uint8_t* p = src + (size_t)(sy0 + r) * pitch + (size_t)(sx0 + c) * px_stride;
         int g;
         if (c1 == 0 && c2 == 0)

@@ -607,7 +607,7 @@ lvkb200_status lvkb200_stream::ensure_pipeline()
     if (cs_in) return LVKB200_OK;
     LVKB_CUDA(cudaStreamCreateWithFlags(&cs_in, cudaStreamNonBlocking));
     LVKB_CUDA(cudaStreamCreateWithFlags(&cs_out, cudaStreamNonBlocking));
-    LVKB_CUDA(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
+    for (auto& e : prefetch_done) LVKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     LVKB_CUDA(cudaEventCreateWithFlags(&ring_reads_done, cudaEventDisableTiming));
     LVKB_CUDA(cudaEventRecord(ring_reads_done, cs));
     for (int k = 0; k < 2; k++)
@@ -626,20 +626,22 @@ lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int wid
     const size_t row = static_cast<size_t>(width) * 3;
     LVKB_REQUIRE(pitch >= row);
     LVKB_TRY(ensure_pipeline());
-    prefetch_slot.pitch = align_up(row, 16);
-    prefetch_slot.w = width;
-    prefetch_slot.h = height;
-    if (prefetch_slot.buf.capacity < prefetch_slot.pitch * height)
+    const int k = prefetch_next;
+    prefetch_next ^= 1;
+    QueuedFrame& ps = prefetch_slot[k];
+    ps.pitch = align_up(row, 16);
+    ps.w = width;
+    ps.h = height;
+    if (ps.buf.capacity < ps.pitch * height)
     {
         LVKB_CUDA(cudaStreamSynchronize(cs));  // the buffer being replaced may still be read by a queued remap
-        LVKB_CUDA(prefetch_slot.buf.ensure(prefetch_slot.pitch * height));
+        LVKB_CUDA(ps.buf.ensure(ps.pitch * height));
     }
     // the spare buffer was a ring buffer until the last swap: wait for the last kernel that read ring memory
     LVKB_CUDA(cudaStreamWaitEvent(cs_in, ring_reads_done, 0));
-    LVKB_CUDA(cudaMemcpy2DAsync(prefetch_slot.buf.ptr, prefetch_slot.pitch, frame, pitch, row, height,
-                                cudaMemcpyHostToDevice, cs_in));
-    LVKB_CUDA(cudaEventRecord(prefetch_done, cs_in));
-    prefetched_ptr = frame;
+    LVKB_CUDA(cudaMemcpy2DAsync(ps.buf.ptr, ps.pitch, frame, pitch, row, height, cudaMemcpyHostToDevice, cs_in));
+    LVKB_CUDA(cudaEventRecord(prefetch_done[k], cs_in));
+    prefetched_ptr[k] = frame;
     return LVKB200_OK;
 }
 
@@ -684,16 +686,20 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
         ring_size++;
     }
     QueuedFrame& q = ring[slot];
-    const bool prefetched = frame_space == LVKB200_MEM_HOST && prefetched_ptr == frame && prefetch_slot.w == width &&
-                            prefetch_slot.h == height && prefetch_slot.pitch == align_up(row, 16);
+    int pk = -1;
+    for (int k = 0; k < 2 && frame_space == LVKB200_MEM_HOST; k++)
+        if (prefetched_ptr[k] == frame && prefetch_slot[k].w == width && prefetch_slot[k].h == height &&
+            prefetch_slot[k].pitch == align_up(row, 16))
+            pk = k;
+    const bool prefetched = pk >= 0;
     if (prefetched)
     {
-        // lvkb200_stream_prefetch already uploaded this frame into the spare buffer on the copy-in stream:
+        // lvkb200_stream_prefetch already uploaded this frame into a spare buffer on the copy-in stream:
         // adopt that buffer (O(1) swap) and make this stream wait for the upload instead of copying again.
-        std::swap(q.buf, prefetch_slot.buf);
-        q.pitch = prefetch_slot.pitch;
-        LVKB_CUDA(cudaStreamWaitEvent(cs, prefetch_done, 0));
-        prefetched_ptr = nullptr;
+        std::swap(q.buf, prefetch_slot[pk].buf);
+        q.pitch = prefetch_slot[pk].pitch;
+        LVKB_CUDA(cudaStreamWaitEvent(cs, prefetch_done[pk], 0));
+        prefetched_ptr[pk] = nullptr;
     }
     else
     {
@@ -843,7 +849,7 @@ void lvkb200_stream::release()
     input_copied = nullptr;
     if (cs_in) cudaStreamSynchronize(cs_in);
     if (cs_out) cudaStreamSynchronize(cs_out);
-    prefetch_slot.buf.release();
+    for (auto& ps : prefetch_slot) ps.buf.release();
     for (int k = 0; k < 2; k++)
     {
         async_out[k].release();
@@ -852,13 +858,17 @@ void lvkb200_stream::release()
         async_remap_done[k] = async_out_done[k] = nullptr;
         async_out_used[k] = false;
     }
-    if (prefetch_done) cudaEventDestroy(prefetch_done);
+    for (auto& e : prefetch_done)
+    {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     if (ring_reads_done) cudaEventDestroy(ring_reads_done);
-    prefetch_done = ring_reads_done = nullptr;
+    ring_reads_done = nullptr;
     if (cs_in) cudaStreamDestroy(cs_in);
     if (cs_out) cudaStreamDestroy(cs_out);
     cs_in = cs_out = nullptr;
-    prefetched_ptr = nullptr;
+    prefetched_ptr[0] = prefetched_ptr[1] = nullptr;
     for (auto& e : user_events)
     {
         if (e) cudaEventDestroy(e);

@@ -84,9 +84,11 @@ struct lvkb200_stream
     // a copy-in stream uploads the NEXT host frame into a spare buffer while this frame is processed, and a copy-out
     // stream downloads the PREVIOUS output from one of two staging buffers.
     cudaStream_t cs_in = nullptr, cs_out = nullptr;
-    QueuedFrame prefetch_slot;
-    const void* prefetched_ptr = nullptr;
-    cudaEvent_t prefetch_done = nullptr;    // recorded on cs_in after the upload
+    // two spare buffers: the caller prefetches frame t+1 BEFORE submitting frame t, so two uploads are outstanding
+    QueuedFrame prefetch_slot[2];
+    const void* prefetched_ptr[2] = {nullptr, nullptr};
+    cudaEvent_t prefetch_done[2] = {nullptr, nullptr};  // recorded on cs_in after each upload
+    int prefetch_next = 0;
     cudaEvent_t ring_reads_done = nullptr;  // recorded on cs after the last kernel that read a ring buffer (remap)
     lvkb200::DeviceBuffer async_out[2];
     cudaEvent_t async_remap_done[2] = {}, async_out_done[2] = {};
