@@ -152,7 +152,7 @@ void lvkb200_stream_destroy(lvkb200_stream* s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->cs) cudaStreamSynchronize(s->cs);
+    s->sync_all();
     s->release();
     if (s->cs) cudaStreamDestroy(s->cs);
     delete s;
@@ -202,8 +202,7 @@ lvkb200_status lvkb200_stream_sync(lvkb200_stream* s)
 {
     LVKB_REQUIRE(s != nullptr);
     LVKB_CUDA(cudaSetDevice(s->device));
-    LVKB_CUDA(cudaStreamSynchronize(s->cs));
-    return LVKB200_OK;
+    return s->sync_all();
 }
 
 lvkb200_status lvkb200_stream_event_record(lvkb200_stream* s, int index)
@@ -211,6 +210,7 @@ lvkb200_status lvkb200_stream_event_record(lvkb200_stream* s, int index)
     LVKB_REQUIRE(s != nullptr && index >= 0 && index < LVKB200_EVENT_SLOTS);
     LVKB_CUDA(cudaSetDevice(s->device));
     if (!s->user_events[index]) LVKB_CUDA(cudaEventCreate(&s->user_events[index]));
+    LVKB_TRY(s->join_remap(s->cs));  // the event covers the output remaps queued so far (they run on their own stream)
     LVKB_CUDA(cudaEventRecord(s->user_events[index], s->cs));
     return LVKB200_OK;
 }
@@ -418,7 +418,7 @@ lvkb200_status lvkb200_fast_detect(lvkb200_stream* s, const uint8_t* image, int 
     if (st == LVKB200_OK) st = det.prepare(width, height);
     const FastRegion rg{roi_x, roi_y, roi_w, roi_h, threshold};
     if (st == LVKB200_OK) st = det.launch(s->cs, dimg.as<uint8_t>(), pitch, &rg, 1);
-    if (st == LVKB200_OK) st = det.fetch(s->cs, pts);
+    if (st == LVKB200_OK) st = det.fetch(pts);
     cudaStreamSynchronize(s->cs);
     if (st == LVKB200_OK)
     {

@@ -243,10 +243,9 @@ lvkb200_status FastDetector::prepare(int width, int height)
     LVKB_CUDA(d_row_x.ensure(sizeof(uint16_t) * FAST_MAX_REGIONS * (size_t)max_rows * row_cap));
     LVKB_CUDA(d_row_s.ensure(sizeof(uint8_t) * FAST_MAX_REGIONS * (size_t)max_rows * row_cap));
     LVKB_CUDA(d_row_count.ensure(sizeof(int) * FAST_MAX_REGIONS * (size_t)max_rows));
-    LVKB_CUDA(d_out.ensure(sizeof(FastPoint) * FAST_MAX_REGIONS * (size_t)out_cap));
-    LVKB_CUDA(d_out_count.ensure(sizeof(int) * FAST_MAX_REGIONS));
     LVKB_CUDA(h_count.ensure(sizeof(int) * FAST_MAX_REGIONS));
     LVKB_CUDA(h_out.ensure(sizeof(FastPoint) * FAST_MAX_REGIONS * (size_t)out_cap));
+    if (!done) LVKB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     w = width;
     h = height;
     return LVKB200_OK;
@@ -254,8 +253,10 @@ lvkb200_status FastDetector::prepare(int width, int height)
 
 void FastDetector::release()
 {
-    d_score.release(); d_row_x.release(); d_row_s.release(); d_row_count.release(); d_out.release();
-    d_out_count.release(); h_count.release(); h_out.release();
+    d_score.release(); d_row_x.release(); d_row_s.release(); d_row_count.release();
+    h_count.release(); h_out.release();
+    if (done) cudaEventDestroy(done);
+    done = nullptr;
     w = h = 0;
 }
 
@@ -280,28 +281,21 @@ lvkb200_status FastDetector::launch(cudaStream_t cs, const uint8_t* img, size_t 
                                                    d_row_count.as<int>());
     k_fast_gather<<<n, 256, sizeof(int) * (max_rows + 1), cs>>>(arg, max_rows, row_cap, d_row_x.as<uint16_t>(),
                                                                 d_row_s.as<uint8_t>(), d_row_count.as<int>(), out_cap,
-                                                                d_out.as<FastPoint>(), d_out_count.as<int>());
+                                                                h_out.device_view<FastPoint>(),
+                                                                h_count.device_view<int>());
     count_launches(3);
     LVKB_CUDA(cudaGetLastError());
+    LVKB_CUDA(cudaEventRecord(done, cs));
     launched = n;
     return LVKB200_OK;
 }
 
-lvkb200_status FastDetector::fetch(cudaStream_t cs, std::vector<std::vector<FastPoint>>& out)
+lvkb200_status FastDetector::fetch(std::vector<std::vector<FastPoint>>& out)
 {
     const int n = launched;
     out.resize(n);
-    LVKB_CUDA(cudaMemcpyAsync(h_count.ptr, d_out_count.ptr, sizeof(int) * n, cudaMemcpyDeviceToHost, cs));
-    LVKB_CUDA(cudaStreamSynchronize(cs));
+    LVKB_CUDA(cudaEventSynchronize(done));
     const int* cnt = h_count.as<int>();
-    for (int i = 0; i < n; i++)
-    {
-        const int c = std::min(cnt[i], out_cap);
-        if (c > 0)
-            LVKB_CUDA(cudaMemcpyAsync(h_out.as<FastPoint>() + (size_t)i * out_cap, d_out.as<FastPoint>() + (size_t)i * out_cap,
-                                      sizeof(FastPoint) * c, cudaMemcpyDeviceToHost, cs));
-    }
-    LVKB_CUDA(cudaStreamSynchronize(cs));
     for (int i = 0; i < n; i++)
     {
         const int c = std::min(cnt[i], out_cap);

@@ -5,13 +5,31 @@
 #include "stream_impl.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "host_math.hpp"
 
 using namespace lvkb200;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr uint64_t HOST_TRACE_SKIP = 40;
+
+static inline double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void lvkb200_stream::host_tick(int phase)
+{
+    if (!host_trace) return;
+    const double t = now_us();
+    if (phase >= 0 && host_frames > HOST_TRACE_SKIP) host_us[phase] += t - host_mark;  // skip the start-up frames
+    host_mark = t;
+}
 
 constexpr float QA_UPDATE_RATE = 0.1f;  // StabilizationFilter.cpp:29
 constexpr float QA_BLEND_STEP = 0.05f;  // StabilizationFilter.cpp:30
@@ -50,6 +68,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     // StabilizationFilter.cpp:51-52: disabling the stabilization resets the context
     if (configured && settings.stabilize_output && !s.stabilize_output) LVKB_TRY(reset_context());
 
+    if (!configured) host_trace = std::getenv("LVKB200_HOST_TRACE") != nullptr;
     const bool det_changed = !configured || s.detection_resolution_width != settings.detection_resolution_width ||
                              s.detection_resolution_height != settings.detection_resolution_height;
     settings = s;
@@ -60,7 +79,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     const size_t capacity = static_cast<size_t>(s.predictive_samples) + 1;
     if (ring.size() != capacity)
     {
-        if (cs) LVKB_CUDA(cudaStreamSynchronize(cs));
+        LVKB_TRY(sync_all());
         std::vector<QueuedFrame> fresh(capacity);
         const size_t keep = std::min(ring_size, capacity);
         for (size_t i = 0; i < keep; i++)
@@ -121,7 +140,27 @@ void lvkb200_stream::stable_region(int fw, int fh, int* x, int* y, int* w, int* 
     *h = static_cast<int>(std::lrintf(smoother.margin_h * static_cast<float>(fh)));
 }
 
-void lvkb200_stream::stage_begin(int stage)
+lvkb200_status lvkb200_stream::wait_frame_buffers_free(cudaStream_t stream)
+{
+    // remap n-1 (the latest) reads spare_buf only; every other frame buffer was last read by remap n-2 or earlier
+    if (remaps_launched >= 2) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[remaps_launched & 1], 0));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::join_remap(cudaStream_t stream)
+{
+    if (remaps_launched >= 1) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[(remaps_launched - 1) & 1], 0));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::sync_all()
+{
+    if (cs) LVKB_CUDA(cudaStreamSynchronize(cs));
+    if (cs_remap) LVKB_CUDA(cudaStreamSynchronize(cs_remap));
+    return LVKB200_OK;
+}
+
+void lvkb200_stream::stage_begin(int stage, cudaStream_t on)
 {
     // Only the roofline kernel (remap) is timed unconditionally; the other stages are timed when profiling is on.
     if (!profile_stages && stage != ST_REMAP) return;
@@ -131,14 +170,14 @@ void lvkb200_stream::stage_begin(int stage)
         cudaEventCreate(&ev[0]);
         cudaEventCreate(&ev[1]);
     }
-    cudaEventRecord(ev[0], cs);
+    cudaEventRecord(ev[0], on ? on : cs);
     stage_used[stage_parity][stage] = true;
 }
 
-void lvkb200_stream::stage_end(int stage)
+void lvkb200_stream::stage_end(int stage, cudaStream_t on)
 {
     if (!profile_stages && stage != ST_REMAP) return;
-    cudaEventRecord(stage_ev[stage_parity][stage][1], cs);
+    cudaEventRecord(stage_ev[stage_parity][stage][1], on ? on : cs);
 }
 
 // Adds the (completed) stage durations recorded in slot `parity` to the running totals and frees the slot.
@@ -161,7 +200,7 @@ void lvkb200_stream::harvest_stage_times(int parity)
 
 lvkb200_status lvkb200_stream::stage_totals(double* totals, uint64_t* counts, bool reset)
 {
-    LVKB_CUDA(cudaStreamSynchronize(cs));
+    LVKB_TRY(sync_all());
     harvest_stage_times(0);
     harvest_stage_times(1);
     for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
@@ -180,7 +219,7 @@ lvkb200_status lvkb200_stream::stage_totals(double* totals, uint64_t* counts, bo
 lvkb200_status lvkb200_stream::stage_times(float* times)
 {
     // durations of the LAST submit (slot of the previous parity), read without consuming them
-    LVKB_CUDA(cudaStreamSynchronize(cs));
+    LVKB_TRY(sync_all());
     const int p = stage_parity;
     for (int i = 0; i < LVKB200_STAGE_COUNT; i++)
     {
@@ -396,9 +435,24 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     stage_begin(ST_INGEST);
     LVKB_TRY(ingest.launch(cs, frame.buf.as<uint8_t>(), frame.pitch, frame.format, d_det.as<uint8_t>(), det_pitch));
     stage_end(ST_INGEST);
+    // FAST reads the detection image only, the pyramid is needed by LK only: FAST goes first and the pyramid is
+    // queued behind it, so it is built while the host waits for and digests the FAST keypoints.
+    const bool can_track = frame_initialized && pyr[cur ^ 1].valid;
+    std::vector<FastRegion> regions;
+    std::vector<int> region_index;
+    std::vector<std::vector<FastPoint>> fast_points;
+    if (can_track)
+    {
+        grid.plan_detection(regions, region_index);  // FeatureDetector::detect (FrameTracker.cpp:127)
+        stage_begin(ST_FAST);
+        if (!regions.empty())
+            LVKB_TRY(fast.launch(cs, d_det.as<uint8_t>(), det_pitch, regions.data(), static_cast<int>(regions.size())));
+        stage_end(ST_FAST);
+    }
     stage_begin(ST_PYRAMID);
     LVKB_TRY(pyr[cur].build(cs, d_det.as<uint8_t>(), det_pitch));
     stage_end(ST_PYRAMID);
+    host_tick(HP_ENQ_DETECT);
 
     if (debug_capture)
     {
@@ -409,26 +463,14 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
 
     // ---- we need at least two frames (FrameTracker.cpp:120-124)
-    if (!frame_initialized || !pyr[cur ^ 1].valid)
+    if (!can_track)
     {
         frame_initialized = true;
         return LVKB200_OK;
     }
 
-    // ---- FeatureDetector::detect (FrameTracker.cpp:127)
-    std::vector<FastRegion> regions;
-    std::vector<int> region_index;
-    std::vector<std::vector<FastPoint>> fast_points;
-    grid.plan_detection(regions, region_index);
-    stage_begin(ST_FAST);
-    if (!regions.empty())
-    {
-        LVKB_TRY(fast.launch(cs, d_det.as<uint8_t>(), det_pitch, regions.data(), static_cast<int>(regions.size())));
-        stage_end(ST_FAST);
-        LVKB_TRY(fast.fetch(cs, fast_points));
-    }
-    else
-        stage_end(ST_FAST);
+    if (!regions.empty()) LVKB_TRY(fast.fetch(fast_points));
+    host_tick(HP_WAIT_FAST);
     const float distribution = grid.finish_detection(region_index, fast_points, features, dbg_fast_counts);
     if (debug_capture)
     {
@@ -454,10 +496,13 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     const bool global = !settings.track_local_motions;
     // FrameTracker.cpp:167-176: homography when the features are well distributed, partial affine otherwise
     const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
+    host_tick(HP_DETECT);
     LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold, model_kind));
+    host_tick(HP_ENQ_TRACK);
     RansacResult model{};
     std::vector<uint8_t> inliers;
     LVKB_TRY(fetch_tracking(n_tracked, global, matched, status, &model, inliers));
+    host_tick(HP_WAIT_TRACK);
     if (debug_capture)
     {
         dbg_lk_matched = matched;
@@ -543,10 +588,11 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     return LVKB200_OK;
 }
 
-lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& offsets, void* out, size_t out_pitch,
+lvkb200_status lvkb200_stream::apply_mesh(QueuedFrame& src, const Mesh& offsets, void* out, size_t out_pitch,
                                           lvkb200_memspace out_space)
 {
     // WarpMesh::apply — Math/WarpMesh.cpp:183-223
+    LVKB_TRY(ensure_pipeline());
     RemapParams p{};
     p.src = src.buf.as<uint8_t>();
     p.src_pitch = src.pitch;
@@ -560,18 +606,28 @@ lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& of
     {
         // pipelined output: remap into one of two device staging buffers; the copy-out stream downloads it while
         // the next frame is being processed (lvkb200_stream_wait_output waits for that download)
-        LVKB_TRY(ensure_pipeline());
         last_ticket = ++async_tickets;
         slot = static_cast<int>(last_ticket & 1);
         p.dst_pitch = align_up(static_cast<size_t>(src.w) * 3, 16);
         LVKB_CUDA(async_out[slot].ensure(p.dst_pitch * src.h));
         p.dst = async_out[slot].as<uint8_t>();
-        if (async_out_used[slot]) LVKB_CUDA(cudaStreamWaitEvent(cs, async_out_done[slot], 0));  // its last download
+        if (async_out_used[slot]) LVKB_CUDA(cudaStreamWaitEvent(cs_remap, async_out_done[slot], 0));  // its last download
     }
     else
         LVKB_TRY(stage_frame_out(out, out_pitch, src.w, src.h, 3, out_space, &p.dst, &p.dst_pitch));
-    stage_begin(ST_REMAP);
-    if (settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2)
+    const bool homography = settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2;
+    const float* dmesh = nullptr;
+    if (!homography)
+    {
+        // the mesh staging buffers are shared with the previous remap: order this upload (on cs) behind it
+        LVKB_TRY(join_remap(cs));
+        LVKB_TRY(upload_mesh(offsets.data(), settings.motion_resolution_width, settings.motion_resolution_height, &dmesh));
+    }
+    // everything queued on cs so far (the source frame's upload, the mesh upload) precedes the remap
+    LVKB_CUDA(cudaEventRecord(chain_point, cs));
+    LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
+    stage_begin(ST_REMAP, cs_remap);
+    if (homography)
     {
         double t[9];
         LVKB_REQUIRE(mesh2x2_to_transform(offsets.data(), src.w, src.h, t));
@@ -579,19 +635,17 @@ lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& of
         dbg_has_t = true;
         float tf[9];
         for (int k = 0; k < 9; k++) tf[k] = static_cast<float>(t[k]);
-        LVKB_CUDA(launch_remap_homography(cs, p, tf));
+        LVKB_CUDA(launch_remap_homography(cs_remap, p, tf));
     }
     else
-    {
-        const float* dmesh = nullptr;
-        LVKB_TRY(upload_mesh(offsets.data(), settings.motion_resolution_width, settings.motion_resolution_height, &dmesh));
-        LVKB_CUDA(launch_remap_mesh(cs, p, dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
-    }
-    stage_end(ST_REMAP);
-    if (ring_reads_done) LVKB_CUDA(cudaEventRecord(ring_reads_done, cs));
+        LVKB_CUDA(launch_remap_mesh(cs_remap, p, dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
+    stage_end(ST_REMAP, cs_remap);
+    LVKB_CUDA(cudaEventRecord(remap_done[remaps_launched & 1], cs_remap));
+    remaps_launched++;
+    std::swap(src.buf, spare_buf);  // park the buffer this remap reads; the slot gets the previously parked one
     if (deferred)
     {
-        LVKB_CUDA(cudaEventRecord(async_remap_done[slot], cs));
+        LVKB_CUDA(cudaEventRecord(async_remap_done[slot], cs_remap));
         LVKB_CUDA(cudaStreamWaitEvent(cs_out, async_remap_done[slot], 0));
         LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(src.w) * 3, src.h,
                                     cudaMemcpyDeviceToHost, cs_out));
@@ -599,6 +653,8 @@ lvkb200_status lvkb200_stream::apply_mesh(const QueuedFrame& src, const Mesh& of
         async_out_used[slot] = true;
         return LVKB200_OK;
     }
+    if (out_space == LVKB200_MEM_DEVICE) return LVKB200_OK;  // ordered by lvkb200_stream_sync / _event_record
+    LVKB_TRY(join_remap(cs));
     return finish_frame_out(out, out_pitch, src.w, src.h, 3, out_space);
 }
 
@@ -608,10 +664,11 @@ lvkb200_status lvkb200_stream::ensure_pipeline()
     LVKB_CUDA(cudaStreamCreateWithFlags(&cs_in, cudaStreamNonBlocking));
     LVKB_CUDA(cudaStreamCreateWithFlags(&cs_out, cudaStreamNonBlocking));
     for (auto& e : prefetch_done) LVKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    LVKB_CUDA(cudaEventCreateWithFlags(&ring_reads_done, cudaEventDisableTiming));
-    LVKB_CUDA(cudaEventRecord(ring_reads_done, cs));
+    LVKB_CUDA(cudaStreamCreateWithFlags(&cs_remap, cudaStreamNonBlocking));
+    LVKB_CUDA(cudaEventCreateWithFlags(&chain_point, cudaEventDisableTiming));
     for (int k = 0; k < 2; k++)
     {
+        LVKB_CUDA(cudaEventCreateWithFlags(&remap_done[k], cudaEventDisableTiming));
         LVKB_CUDA(cudaEventCreateWithFlags(&async_remap_done[k], cudaEventDisableTiming));
         LVKB_CUDA(cudaEventCreateWithFlags(&async_out_done[k], cudaEventDisableTiming));
     }
@@ -634,11 +691,11 @@ lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int wid
     ps.h = height;
     if (ps.buf.capacity < ps.pitch * height)
     {
-        LVKB_CUDA(cudaStreamSynchronize(cs));  // the buffer being replaced may still be read by a queued remap
+        LVKB_TRY(sync_all());  // the buffer being replaced may still be read by a queued remap
         LVKB_CUDA(ps.buf.ensure(ps.pitch * height));
     }
-    // the spare buffer was a ring buffer until the last swap: wait for the last kernel that read ring memory
-    LVKB_CUDA(cudaStreamWaitEvent(cs_in, ring_reads_done, 0));
+    // this buffer was a ring buffer until the last swap: wait for the last remap that could have read it
+    LVKB_TRY(wait_frame_buffers_free(cs_in));
     LVKB_CUDA(cudaMemcpy2DAsync(ps.buf.ptr, ps.pitch, frame, pitch, row, height, cudaMemcpyHostToDevice, cs_in));
     LVKB_CUDA(cudaEventRecord(prefetch_done[k], cs_in));
     prefetched_ptr[k] = frame;
@@ -666,6 +723,11 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     LVKB_REQUIRE(format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV);
     const size_t row = static_cast<size_t>(width) * 3;
     LVKB_REQUIRE(pitch >= row);
+    if (host_trace)
+    {
+        host_frames++;
+        host_tick(HP_OUTSIDE);  // time since the previous submit returned (the caller's own work, prefetch, wait_output)
+    }
     stage_parity ^= 1;
     harvest_stage_times(stage_parity);  // this slot holds the events of two submits ago: long complete
     dbg_has_h = dbg_has_t = false;
@@ -705,6 +767,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     {
         q.pitch = align_up(row, 16);
         LVKB_CUDA(q.buf.ensure(q.pitch * height));
+        LVKB_TRY(wait_frame_buffers_free(cs));  // the remaps run on their own stream
         LVKB_CUDA(cudaMemcpy2DAsync(q.buf.ptr, q.pitch, frame, pitch, row, height,
                                     frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
     }
@@ -742,10 +805,18 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
             }
             else
             {
+                // the pass-through copy follows the same protocol as a remap (own stream, parked source buffer)
+                LVKB_TRY(ensure_pipeline());
+                LVKB_CUDA(cudaEventRecord(chain_point, cs));
+                LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
                 LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, oldest.buf.ptr, oldest.pitch, static_cast<size_t>(oldest.w) * 3,
                                             oldest.h,
-                                            out_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
-                if (out_space == LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(cs));
+                                            out_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                            cs_remap));
+                LVKB_CUDA(cudaEventRecord(remap_done[remaps_launched & 1], cs_remap));
+                remaps_launched++;
+                std::swap(oldest.buf, spare_buf);
+                if (out_space == LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(cs_remap));
             }
             res->has_output = 1;
             res->out_timestamp = oldest.timestamp;
@@ -759,7 +830,9 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     // ---- track the motion of the incoming frame (StabilizationFilter.cpp:98-99)
     Mesh motion;
     bool has_motion = false;
+    host_tick(HP_UPLOAD);
     LVKB_TRY(track(q, motion, &has_motion));
+    host_tick(HP_POST);
     const size_t elems = static_cast<size_t>(settings.motion_resolution_width) * settings.motion_resolution_height * 2;
     if (!has_motion) motion.assign(elems, 0.0f);  // m_NullMotion
     if (debug_capture) dbg_motion = motion;
@@ -778,6 +851,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     // ---- path smoothing (StabilizationFilter.cpp:121)
     Mesh correction;
     smoother.next(motion, correction);
+    host_tick(HP_SMOOTH);
 
     if (ready())
     {
@@ -789,6 +863,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
         if (debug_capture) dbg_correction = correction;
         LVKB_REQUIRE(out != nullptr);
         LVKB_TRY(apply_mesh(next_frame, correction, out, out_pitch, out_space));
+        host_tick(HP_REMAP);
         res->has_output = 1;
         res->out_timestamp = next_frame.timestamp;
         res->out_format = next_frame.format;
@@ -836,6 +911,21 @@ lvkb200_status lvkb200_stream::debug_fetch(lvkb200_debug_item which, void* buffe
 
 void lvkb200_stream::release()
 {
+    if (host_trace && host_frames > HOST_TRACE_SKIP)
+    {
+        static const char* names[HP_COUNT] = {"upload", "enq_detect", "wait_fast", "detect", "enq_track",
+                                              "wait_track", "post", "smooth", "remap", "outside"};
+        const double frames = static_cast<double>(host_frames - HOST_TRACE_SKIP);
+        std::fprintf(stderr, "[lvkb200 host trace] %.0f frames, us/frame:", frames);
+        double sum = 0.0;
+        for (int i = 0; i < HP_COUNT; i++)
+        {
+            std::fprintf(stderr, " %s=%.1f", names[i], host_us[i] / frames);
+            sum += host_us[i];
+        }
+        std::fprintf(stderr, " total=%.1f\n", sum / frames);
+        host_frames = 0;
+    }
     stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
     destroy_graphs();
@@ -863,11 +953,20 @@ void lvkb200_stream::release()
         if (e) cudaEventDestroy(e);
         e = nullptr;
     }
-    if (ring_reads_done) cudaEventDestroy(ring_reads_done);
-    ring_reads_done = nullptr;
+    if (cs_remap) cudaStreamSynchronize(cs_remap);
+    spare_buf.release();
+    for (auto& e : remap_done)
+    {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
+    remaps_launched = 0;
+    if (chain_point) cudaEventDestroy(chain_point);
+    chain_point = nullptr;
     if (cs_in) cudaStreamDestroy(cs_in);
     if (cs_out) cudaStreamDestroy(cs_out);
-    cs_in = cs_out = nullptr;
+    if (cs_remap) cudaStreamDestroy(cs_remap);
+    cs_in = cs_out = cs_remap = nullptr;
     prefetched_ptr[0] = prefetched_ptr[1] = nullptr;
     for (auto& e : user_events)
     {

@@ -89,7 +89,18 @@ struct lvkb200_stream
     const void* prefetched_ptr[2] = {nullptr, nullptr};
     cudaEvent_t prefetch_done[2] = {nullptr, nullptr};  // recorded on cs_in after each upload
     int prefetch_next = 0;
-    cudaEvent_t ring_reads_done = nullptr;  // recorded on cs after the last kernel that read a ring buffer (remap)
+    // The output remap runs on its OWN stream: it depends only on a frame uploaded `predictive_samples` submits ago and
+    // on the host-computed correction, so it overlaps the next frame's (latency-bound) tracking chain on `cs`.
+    // Frame buffers rotate through `spare_buf`: the buffer the latest remap reads is parked there, so every buffer an
+    // upload can target was last read by the remap BEFORE the latest one (wait_frame_buffers_free).
+    cudaStream_t cs_remap = nullptr;
+    cudaEvent_t remap_done[2] = {nullptr, nullptr};  // remap number n records remap_done[n & 1] on cs_remap
+    uint64_t remaps_launched = 0;
+    cudaEvent_t chain_point = nullptr;  // recorded on cs before a remap is queued: uploads on cs have been issued
+    lvkb200::DeviceBuffer spare_buf;
+    lvkb200_status wait_frame_buffers_free(cudaStream_t stream);
+    lvkb200_status join_remap(cudaStream_t stream);  // makes `stream` wait for every remap queued so far
+    lvkb200_status sync_all();                       // host waits for cs and cs_remap
     lvkb200::DeviceBuffer async_out[2];
     cudaEvent_t async_remap_done[2] = {}, async_out_done[2] = {};
     bool async_out_used[2] = {false, false};
@@ -109,6 +120,16 @@ struct lvkb200_stream
     uint64_t stage_count[LVKB200_STAGE_COUNT] = {};
     void harvest_stage_times(int parity);
     lvkb200_status stage_totals(double* totals, uint64_t* counts, bool reset);
+
+    // ---- host-side timeline of submit (LVKB200_HOST_TRACE=1): where the CPU thread spends its time per frame;
+    // printed to stderr when the stream is destroyed.  Diagnostic only.
+    enum HostPhase { HP_UPLOAD, HP_ENQ_DETECT, HP_WAIT_FAST, HP_DETECT, HP_ENQ_TRACK, HP_WAIT_TRACK, HP_POST,
+                     HP_SMOOTH, HP_REMAP, HP_OUTSIDE, HP_COUNT };
+    bool host_trace = false;
+    double host_us[HP_COUNT] = {};
+    uint64_t host_frames = 0;
+    double host_mark = 0.0;
+    void host_tick(int phase);  // adds the time since the previous tick to `phase`
 
     // ---- debug taps of the last submit
     std::vector<uint8_t> dbg_det, dbg_lk_status, dbg_inliers;
@@ -137,10 +158,10 @@ struct lvkb200_stream
                                   lvkb200::RansacResult* model, std::vector<uint8_t>& mask);
     lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold, int model,
                                   double h[9], std::vector<uint8_t>& mask, bool* found);
-    lvkb200_status apply_mesh(const QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,
+    lvkb200_status apply_mesh(QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,
                               lvkb200_memspace out_space);
-    void stage_begin(int stage);
-    void stage_end(int stage);
+    void stage_begin(int stage, cudaStream_t on = nullptr);  // nullptr == cs
+    void stage_end(int stage, cudaStream_t on = nullptr);
 
     // Makes a device view of a caller frame: device memory is used in place, host memory is copied
     // (async, on this stream) into stage_in with a 16-byte aligned pitch.
