@@ -193,25 +193,31 @@ class Stream:
             outputs = [np.empty_like(frames[0].data) for _ in range(3)]
         if len(outputs) < 3:
             raise ValueError("stream() needs at least 3 output buffers")
-        pending, delivered = None, 0
+        # Two outputs stay in flight: output t's remap is launched inside submit t+1 (beside that frame's LK + RANSAC,
+        # see lvkb200_stream_submit_async) and its download overlaps frame t+2, so it is collected after submit t+2.
+        pending, delivered = [], 0
         for i, f in enumerate(frames):
             if i + 1 < len(frames):
                 self.prefetch(frames[i + 1].data)
             out = outputs[i % len(outputs)]
             res, ticket = self.submit_async(f.data, out, f.format, f.timestamp)
-            if pending is not None:
-                self.wait_output(pending[0])
-                delivered += 1
-                keep_going = callback(pending[1])
-                pending = None
-                if keep_going is False:
-                    return delivered
             if res.has_output:
-                pending = (ticket, VideoFrame(out, int(res.out_timestamp), int(res.out_format)))
-        if pending is not None:
-            self.wait_output(pending[0])
+                pending.append((ticket, VideoFrame(out, int(res.out_timestamp), int(res.out_format))))
+            while len(pending) > 2:
+                tk, vf = pending.pop(0)
+                self.wait_output(tk)
+                delivered += 1
+                if callback(vf) is False:
+                    for tk, _ in pending:  # let the queued downloads finish before the buffers are handed back
+                        self.wait_output(tk)
+                    return delivered
+        for tk, vf in pending:
+            self.wait_output(tk)
             delivered += 1
-            callback(pending[1])
+            if callback(vf) is False:
+                break
+        for tk, _ in pending:
+            self.wait_output(tk)
         return delivered
 
     def prefetch(self, frame):

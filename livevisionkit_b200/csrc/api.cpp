@@ -140,7 +140,11 @@ lvkb200_status lvkb200_stream_create(int device, const lvkb200_settings* setting
     LVKB_CUDA(cudaSetDevice(device));
     std::unique_ptr<lvkb200_stream> s(new lvkb200_stream());
     s->device = device;
-    LVKB_CUDA(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
+    // The tracking chain is a string of small latency-bound kernels on the frame's critical path; the remap of the
+    // previous output (own stream, default priority) fills the machine: the chain's CTAs go first whenever slots free.
+    int prio_least = 0, prio_greatest = 0;
+    LVKB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    LVKB_CUDA(cudaStreamCreateWithPriority(&s->cs, cudaStreamNonBlocking, prio_greatest));
     lvkb200_settings def;
     lvkb200_settings_default(&def);
     LVKB_TRY(s->configure(settings ? *settings : def));

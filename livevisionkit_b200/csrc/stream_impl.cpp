@@ -35,7 +35,8 @@ constexpr float QA_UPDATE_RATE = 0.1f;  // StabilizationFilter.cpp:29
 constexpr float QA_BLEND_STEP = 0.05f;  // StabilizationFilter.cpp:30
 constexpr float HOMOGRAPHY_DISTRIBUTION_THRESHOLD = 0.6f;  // FrameTracker.cpp:37
 
-enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_FAST, ST_LK, ST_ESTIMATE, ST_REMAP };
+enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_FAST, ST_LK, ST_ESTIMATE, ST_REMAP, ST_XFER_IN, ST_XFER_OUT };
+static_assert(ST_XFER_OUT + 1 == LVKB200_STAGE_COUNT, "stage table out of step with lvkb200.h");
 
 lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
 {
@@ -142,19 +143,23 @@ void lvkb200_stream::stable_region(int fw, int fh, int* x, int* y, int* w, int* 
 
 lvkb200_status lvkb200_stream::wait_frame_buffers_free(cudaStream_t stream)
 {
-    // remap n-1 (the latest) reads spare_buf only; every other frame buffer was last read by remap n-2 or earlier
-    if (remaps_launched >= 2) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[remaps_launched & 1], 0));
+    // The latest remap issued (launched or still held back) reads spare_buf only; every other frame buffer was last
+    // read by the one before it or earlier.
+    const uint64_t issued = remaps_launched + (pending.active ? 1 : 0);
+    if (issued >= 2) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[(issued - 2) & 1], 0));
     return LVKB200_OK;
 }
 
 lvkb200_status lvkb200_stream::join_remap(cudaStream_t stream)
 {
+    LVKB_TRY(flush_remap());
     if (remaps_launched >= 1) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[(remaps_launched - 1) & 1], 0));
     return LVKB200_OK;
 }
 
 lvkb200_status lvkb200_stream::sync_all()
 {
+    LVKB_TRY(flush_remap());
     if (cs) LVKB_CUDA(cudaStreamSynchronize(cs));
     if (cs_remap) LVKB_CUDA(cudaStreamSynchronize(cs_remap));
     return LVKB200_OK;
@@ -287,8 +292,10 @@ lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, in
     const void* hpts = h_pts_prev.device_view<void>();
     void* hout = h_track_out.device_view<void>();
     LVKB_REQUIRE(hp != nullptr && hpts != nullptr && hout != nullptr);
+    if (with_events) stage_begin(ST_XFER_IN);
     LVKB_TRY(zero_copy_transfer(cs, hp, d_params.ptr, sizeof(TrackParams), hpts, d_pts_prev.ptr,
                                 sizeof(float2) * max_points));
+    if (with_events) stage_end(ST_XFER_IN);
     if (with_events) stage_begin(ST_LK);
     LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], d_pts_prev.as<float2>(), max_points, prm, d_pts_next(), d_status()));
     if (with_events) stage_end(ST_LK);
@@ -304,7 +311,9 @@ lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, in
         if (with_events) stage_end(ST_ESTIMATE);
     }
     // results go straight into mapped pinned memory; visible to the host after the stream synchronisation
+    if (with_events) stage_begin(ST_XFER_OUT);
     LVKB_TRY(zero_copy_transfer(cs, d_track_out.ptr, hout, track_out_bytes, nullptr, nullptr, 0));
+    if (with_events) stage_end(ST_XFER_OUT);
     return LVKB200_OK;
 }
 
@@ -498,6 +507,7 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
     host_tick(HP_DETECT);
     LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold, model_kind));
+    LVKB_TRY(flush_remap());  // the previous output's remap runs beside LK + RANSAC (see apply_mesh)
     host_tick(HP_ENQ_TRACK);
     RansacResult model{};
     std::vector<uint8_t> inliers;
@@ -593,69 +603,96 @@ lvkb200_status lvkb200_stream::apply_mesh(QueuedFrame& src, const Mesh& offsets,
 {
     // WarpMesh::apply — Math/WarpMesh.cpp:183-223
     LVKB_TRY(ensure_pipeline());
-    RemapParams p{};
+    LVKB_TRY(flush_remap());  // at most one remap is held back
+    PendingRemap& pr = pending;
+    RemapParams& p = pr.p;
+    p = RemapParams{};
     p.src = src.buf.as<uint8_t>();
     p.src_pitch = src.pitch;
     p.width = src.w;
     p.height = src.h;
     p.yuv = src.format == LVKB200_YUV;  // Image.cpp:100
     for (int k = 0; k < 3; k++) p.bg[k] = static_cast<uint8_t>(settings.background_colour[k]);  // Image.cpp:136-141
-    const bool deferred = deferred_output && out_space == LVKB200_MEM_HOST;
-    int slot = 0;
-    if (deferred)
+    pr.async_host_out = deferred_output && out_space == LVKB200_MEM_HOST;
+    pr.slot = 0;
+    pr.out = out;
+    pr.out_pitch = out_pitch;
+    pr.out_space = out_space;
+    if (pr.async_host_out)
     {
         // pipelined output: remap into one of two device staging buffers; the copy-out stream downloads it while
-        // the next frame is being processed (lvkb200_stream_wait_output waits for that download)
+        // the next frames are being processed (lvkb200_stream_wait_output waits for that download)
         last_ticket = ++async_tickets;
-        slot = static_cast<int>(last_ticket & 1);
+        pr.ticket = last_ticket;
+        pr.slot = static_cast<int>(last_ticket & 1);
         p.dst_pitch = align_up(static_cast<size_t>(src.w) * 3, 16);
-        LVKB_CUDA(async_out[slot].ensure(p.dst_pitch * src.h));
-        p.dst = async_out[slot].as<uint8_t>();
-        if (async_out_used[slot]) LVKB_CUDA(cudaStreamWaitEvent(cs_remap, async_out_done[slot], 0));  // its last download
+        LVKB_CUDA(async_out[pr.slot].ensure(p.dst_pitch * src.h));
+        p.dst = async_out[pr.slot].as<uint8_t>();
     }
     else
         LVKB_TRY(stage_frame_out(out, out_pitch, src.w, src.h, 3, out_space, &p.dst, &p.dst_pitch));
-    const bool homography = settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2;
-    const float* dmesh = nullptr;
-    if (!homography)
-    {
-        // the mesh staging buffers are shared with the previous remap: order this upload (on cs) behind it
-        LVKB_TRY(join_remap(cs));
-        LVKB_TRY(upload_mesh(offsets.data(), settings.motion_resolution_width, settings.motion_resolution_height, &dmesh));
-    }
-    // everything queued on cs so far (the source frame's upload, the mesh upload) precedes the remap
-    LVKB_CUDA(cudaEventRecord(chain_point, cs));
-    LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
-    stage_begin(ST_REMAP, cs_remap);
-    if (homography)
+    pr.homography = settings.motion_resolution_width == 2 && settings.motion_resolution_height == 2;
+    pr.dmesh = nullptr;
+    if (pr.homography)
     {
         double t[9];
         LVKB_REQUIRE(mesh2x2_to_transform(offsets.data(), src.w, src.h, t));
         std::memcpy(dbg_t, t, sizeof(t));
         dbg_has_t = true;
-        float tf[9];
-        for (int k = 0; k < 9; k++) tf[k] = static_cast<float>(t[k]);
-        LVKB_CUDA(launch_remap_homography(cs_remap, p, tf));
+        for (int k = 0; k < 9; k++) pr.tf[k] = static_cast<float>(t[k]);
     }
     else
-        LVKB_CUDA(launch_remap_mesh(cs_remap, p, dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
+    {
+        // the mesh staging buffers are shared with the previous remap: order this upload (on cs) behind it
+        LVKB_TRY(join_remap(cs));
+        LVKB_TRY(upload_mesh(offsets.data(), settings.motion_resolution_width, settings.motion_resolution_height, &pr.dmesh));
+    }
+    pr.active = true;
+    std::swap(src.buf, spare_buf);  // park the buffer this remap reads; the slot gets the previously parked one
+    // Hold the launch back when nobody waits for the pixels inside this call: the remap fills every SM for ~50 us, and
+    // queued right now it would share them with the NEXT frame's ingest/pyramid/FAST (also issue-bound: both slow down).
+    // Launched behind the next frame's LK + RANSAC graph instead, it runs while those few latency-bound warps leave
+    // the machine idle.  Flushed by the next submit, lvkb200_stream_sync/_event_record/_wait_output.
+    const bool hold = pr.homography && (out_space == LVKB200_MEM_DEVICE || pr.async_host_out) && !profile_stages &&
+                      !debug_capture;
+    if (hold) return LVKB200_OK;
+    LVKB_TRY(flush_remap());
+    if (out_space == LVKB200_MEM_DEVICE || pr.async_host_out) return LVKB200_OK;
+    LVKB_TRY(join_remap(cs));
+    return finish_frame_out(out, out_pitch, p.width, p.height, 3, out_space);
+}
+
+// Launches the held-back remap (if any) on cs_remap, and the download of its result when the output is host memory
+// of a pipelined submit.
+lvkb200_status lvkb200_stream::flush_remap()
+{
+    if (!pending.active) return LVKB200_OK;
+    PendingRemap& pr = pending;
+    pr.active = false;
+    const RemapParams& p = pr.p;
+    if (pr.async_host_out && async_out_used[pr.slot])
+        LVKB_CUDA(cudaStreamWaitEvent(cs_remap, async_out_done[pr.slot], 0));  // the staging buffer's last download
+    // everything queued on cs so far (the source frame's upload, the mesh upload) precedes the remap
+    LVKB_CUDA(cudaEventRecord(chain_point, cs));
+    LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
+    stage_begin(ST_REMAP, cs_remap);
+    if (pr.homography)
+        LVKB_CUDA(launch_remap_homography(cs_remap, p, pr.tf));
+    else
+        LVKB_CUDA(launch_remap_mesh(cs_remap, p, pr.dmesh, settings.motion_resolution_width, settings.motion_resolution_height));
     stage_end(ST_REMAP, cs_remap);
     LVKB_CUDA(cudaEventRecord(remap_done[remaps_launched & 1], cs_remap));
     remaps_launched++;
-    std::swap(src.buf, spare_buf);  // park the buffer this remap reads; the slot gets the previously parked one
-    if (deferred)
+    if (pr.async_host_out)
     {
-        LVKB_CUDA(cudaEventRecord(async_remap_done[slot], cs_remap));
-        LVKB_CUDA(cudaStreamWaitEvent(cs_out, async_remap_done[slot], 0));
-        LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(src.w) * 3, src.h,
+        LVKB_CUDA(cudaEventRecord(async_remap_done[pr.slot], cs_remap));
+        LVKB_CUDA(cudaStreamWaitEvent(cs_out, async_remap_done[pr.slot], 0));
+        LVKB_CUDA(cudaMemcpy2DAsync(pr.out, pr.out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(p.width) * 3, p.height,
                                     cudaMemcpyDeviceToHost, cs_out));
-        LVKB_CUDA(cudaEventRecord(async_out_done[slot], cs_out));
-        async_out_used[slot] = true;
-        return LVKB200_OK;
+        LVKB_CUDA(cudaEventRecord(async_out_done[pr.slot], cs_out));
+        async_out_used[pr.slot] = true;
     }
-    if (out_space == LVKB200_MEM_DEVICE) return LVKB200_OK;  // ordered by lvkb200_stream_sync / _event_record
-    LVKB_TRY(join_remap(cs));
-    return finish_frame_out(out, out_pitch, src.w, src.h, 3, out_space);
+    return LVKB200_OK;
 }
 
 lvkb200_status lvkb200_stream::ensure_pipeline()
@@ -706,6 +743,7 @@ lvkb200_status lvkb200_stream::wait_output(uint64_t ticket)
 {
     if (ticket == 0 || !cs_out) return LVKB200_OK;
     LVKB_REQUIRE(ticket <= async_tickets);
+    if (pending.active && pending.async_host_out && pending.ticket <= ticket) LVKB_TRY(flush_remap());  // still held back
     // waits for the most recent download recorded on that staging slot (>= the ticket's own download)
     LVKB_CUDA(cudaEventSynchronize(async_out_done[ticket & 1]));
     return LVKB200_OK;
@@ -788,6 +826,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     if (!settings.stabilize_output)
     {
         // StabilizationFilter.cpp:77-95: only up-keep the delay
+        LVKB_TRY(flush_remap());
         if (ready())
         {
             QueuedFrame& oldest = ring[ring_start];
@@ -832,6 +871,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     bool has_motion = false;
     host_tick(HP_UPLOAD);
     LVKB_TRY(track(q, motion, &has_motion));
+    LVKB_TRY(flush_remap());  // (frames on which no tracking chain ran)
     host_tick(HP_POST);
     const size_t elems = static_cast<size_t>(settings.motion_resolution_width) * settings.motion_resolution_height * 2;
     if (!has_motion) motion.assign(elems, 0.0f);  // m_NullMotion
@@ -961,6 +1001,7 @@ void lvkb200_stream::release()
         e = nullptr;
     }
     remaps_launched = 0;
+    pending.active = false;
     if (chain_point) cudaEventDestroy(chain_point);
     chain_point = nullptr;
     if (cs_in) cudaStreamDestroy(cs_in);

@@ -98,6 +98,23 @@ struct lvkb200_stream
     uint64_t remaps_launched = 0;
     cudaEvent_t chain_point = nullptr;  // recorded on cs before a remap is queued: uploads on cs have been issued
     lvkb200::DeviceBuffer spare_buf;
+    // A remap whose pixels nobody waits for inside submit (device output, pipelined host output) is held back and
+    // launched behind the NEXT frame's LK + RANSAC graph, where the SMs are idle (see apply_mesh / flush_remap).
+    struct PendingRemap
+    {
+        bool active = false;
+        lvkb200::RemapParams p{};
+        bool homography = true;
+        float tf[9] = {};
+        const float* dmesh = nullptr;
+        bool async_host_out = false;
+        int slot = 0;
+        uint64_t ticket = 0;
+        void* out = nullptr;
+        size_t out_pitch = 0;
+        lvkb200_memspace out_space = LVKB200_MEM_DEVICE;
+    } pending;
+    lvkb200_status flush_remap();
     lvkb200_status wait_frame_buffers_free(cudaStream_t stream);
     lvkb200_status join_remap(cudaStream_t stream);  // makes `stream` wait for every remap queued so far
     lvkb200_status sync_all();                       // host waits for cs and cs_remap
