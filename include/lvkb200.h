@@ -207,9 +207,8 @@ lvkb200_status lvkb200_stream_debug_fetch(lvkb200_stream* s, lvkb200_debug_item 
                                           size_t capacity, size_t* size);
 
 /* Per-stage device time of the last submit, in microseconds (CUDA events): the per-stage analogue of
- * VideoFilter::timings() (Filters/VideoFilter.hpp:58).  Stage order: ingest, pyramid, fast, lk, estimate, remap,
- * transfer_in (points + parameters, host -> device), transfer_out (tracking results, device -> host). */
-#define LVKB200_STAGE_COUNT 8
+ * VideoFilter::timings() (Filters/VideoFilter.hpp:58).  Stage order: ingest, pyramid, fast, lk, estimate, remap. */
+#define LVKB200_STAGE_COUNT 6
 lvkb200_status lvkb200_stream_stage_times_us(lvkb200_stream* s, float times[LVKB200_STAGE_COUNT]);
 /* Running per-stage totals (microseconds of device time, CUDA events on the stream's own CUDA stream) and sample
  * counts since the last reset — the Stopwatch history (Timing/Stopwatch.cpp:142-166) per stage.  Harvested lazily,

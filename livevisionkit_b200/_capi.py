@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(_HERE, "liblvkb200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NO_MODEL, ERR_CAPACITY = range(6)
 BGR, BGRA, RGB, RGBA, YUV, GRAY, UNKNOWN = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1
-STAGE_COUNT = 8
-STAGE_NAMES = ("ingest", "pyramid", "fast", "lk", "estimate", "remap", "transfer_in", "transfer_out")
+STAGE_COUNT = 6
+STAGE_NAMES = ("ingest", "pyramid", "fast", "lk", "estimate", "remap")
 
 (DBG_DETECTION_IMAGE, DBG_DETECTED, DBG_LK_MATCHED, DBG_LK_STATUS, DBG_TRACKED, DBG_MATCHED, DBG_INLIERS,
  DBG_HOMOGRAPHY, DBG_MOTION, DBG_CORRECTION, DBG_WARP_TRANSFORM, DBG_PROPAGATED, DBG_FAST_COUNTS) = range(13)

@@ -454,12 +454,14 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
     if (st == LVKB200_OK) st = pp.build(s->cs, dprev.as<uint8_t>(), pitch);
     if (st == LVKB200_OK) st = pn.build(s->cs, dnext.as<uint8_t>(), pitch);
     auto cuda_ok = [&](cudaError_t e) { if (e != cudaSuccess && st == LVKB200_OK) { set_error("lk_track: %s", cudaGetErrorString(e)); st = LVKB200_ERR_CUDA; } };
+    const int padded = (count + 3) / 4 * 4;  // the kernel moves points in groups of four
     if (st == LVKB200_OK)
     {
-        cuda_ok(dp.ensure(sizeof(float2) * count));
-        cuda_ok(dq.ensure(sizeof(float2) * count));
-        cuda_ok(dst.ensure(count));
+        cuda_ok(dp.ensure(sizeof(float2) * padded));
+        cuda_ok(dq.ensure(sizeof(float2) * padded));
+        cuda_ok(dst.ensure(padded));
     }
+    if (st == LVKB200_OK) cuda_ok(cudaMemsetAsync(dp.ptr, 0, sizeof(float2) * padded, s->cs));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dp.ptr, points, sizeof(float2) * count, cudaMemcpyHostToDevice, s->cs));
     DeviceBuffer dprm;
     TrackParams hprm{};
@@ -467,8 +469,15 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
     hprm.lk_epsilon_sq = lk_epsilon_for_call(std::max(call_index, 0));
     if (st == LVKB200_OK) cuda_ok(dprm.ensure(sizeof(TrackParams)));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(dprm.ptr, &hprm, sizeof(hprm), cudaMemcpyHostToDevice, s->cs));
-    if (st == LVKB200_OK) st = lk_track(s->cs, pp, pn, dp.as<float2>(), count, dprm.as<TrackParams>(), dq.as<float2>(),
-                                         dst.as<uint8_t>());
+    if (st == LVKB200_OK)
+    {
+        LkIo io{};
+        io.pts_in = dp.as<float2>();
+        io.prm_in = dprm.as<TrackParams>();
+        io.next = dq.as<float2>();
+        io.status = dst.as<uint8_t>();
+        st = lk_track(s->cs, pp, pn, padded, io);
+    }
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(matched, dq.ptr, sizeof(float2) * count, cudaMemcpyDeviceToHost, s->cs));
     if (st == LVKB200_OK) cuda_ok(cudaMemcpyAsync(status, dst.ptr, count, cudaMemcpyDeviceToHost, s->cs));
     cuda_ok(cudaStreamSynchronize(s->cs));

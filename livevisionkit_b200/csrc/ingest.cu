@@ -144,6 +144,47 @@ __global__ void __launch_bounds__(THREADS)
     }
 }
 
+// Integer scale factors with packed 3-byte pixels and SX a multiple of 4 (1080p and 4K onto 480x270: SX = 4, 8): one
+// thread per destination pixel, no shared memory and no tables.  A destination pixel's slice of a source row is
+// 3*SX bytes = 3*SX/4 ALIGNED 32-bit words, consecutive lanes read consecutive slices, and all sy*3*SX/4 loads of a
+// thread are independent.  Same arithmetic as the tiled kernel's integer path (exact integer sum, one rounding).
+template <int SX>
+__global__ void __launch_bounds__(128)
+    k_ingest_gray_int(const uint8_t* __restrict__ src, size_t pitch, int c0, int c1, int c2, int dw, int dh, int sy,
+                      int mode, float scale, uint8_t* __restrict__ dst, size_t dst_pitch)
+{
+    constexpr int W = 3 * SX / 4;
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (dx >= dw || dy >= dh) return;
+    const uint8_t* row = src + (size_t)dy * sy * pitch + (size_t)dx * (3 * SX);
+    const bool first_channel = (c1 == 0 && c2 == 0);  // YUV: extractChannel(0)
+    int sum = 0;
+#pragma unroll 4
+    for (int r = 0; r < sy; r++, row += pitch)
+    {
+        uint32_t w[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = __ldg(reinterpret_cast<const uint32_t*>(row) + k);
+#pragma unroll
+        for (int g = 0; g < W; g += 3)
+        {
+            const uint32_t w0 = w[g], w1 = w[g + 1], w2 = w[g + 2];
+            if (first_channel)
+                sum += (int)(w0 & 255) + (int)(w0 >> 24) + (int)((w1 >> 16) & 255) + (int)((w2 >> 8) & 255);
+            else
+            {
+                sum += (c0 * (int)(w0 & 255) + c1 * (int)((w0 >> 8) & 255) + c2 * (int)((w0 >> 16) & 255) + (1 << 14)) >> 15;
+                sum += (c0 * (int)(w0 >> 24) + c1 * (int)(w1 & 255) + c2 * (int)((w1 >> 8) & 255) + (1 << 14)) >> 15;
+                sum += (c0 * (int)((w1 >> 16) & 255) + c1 * (int)(w1 >> 24) + c2 * (int)(w2 & 255) + (1 << 14)) >> 15;
+                sum += (c0 * (int)((w2 >> 8) & 255) + c1 * (int)((w2 >> 16) & 255) + c2 * (int)(w2 >> 24) + (1 << 14)) >> 15;
+            }
+        }
+    }
+    int out = (mode == 2) ? ((sum + 2) >> 2) : __float2int_rn(__fmul_rn((float)sum, scale));
+    out = max(0, min(255, out));
+    dst[(size_t)dy * dst_pitch + dx] = (uint8_t)out;
+}
+
 // OpenCV computeResizeAreaTab (upstream imgproc/resize.cpp), restated.
 void build_axis(int ssize, int dsize, std::vector<int2>& tab, std::vector<float>& w, int& max_count)
 {
@@ -187,7 +228,8 @@ lvkb200_status IngestPlan::prepare(int src_w, int src_h, int dst_w, int dst_h, c
     const double scale_x = (double)src_w / dst_w, scale_y = (double)src_h / dst_h;
     LVKB_REQUIRE(scale_x * DT_W + 2 <= MAX_SW && scale_y * DT_H + 2 <= MAX_SH);
 
-    const int isx = (int)std::lrint(scale_x), isy = (int)std::lrint(scale_y);
+    isx = (int)std::lrint(scale_x);
+    isy = (int)std::lrint(scale_y);
     fast = 0;
     fast_scale = 0.f;
     if (std::fabs(scale_x - isx) < 2.220446049250313e-16 && std::fabs(scale_y - isy) < 2.220446049250313e-16)
@@ -230,6 +272,18 @@ lvkb200_status IngestPlan::launch(cudaStream_t cs, const uint8_t* src, size_t pi
         case LVKB200_YUV: c0 = 1; break;                                        // cv::extractChannel(0)
         case LVKB200_GRAY: stride = 1; c0 = 1; break;
         default: LVKB_REQUIRE(format != LVKB200_UNKNOWN);  // StabilizationFilter.cpp:71
+    }
+    const bool aligned = stride == 3 && (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    if (fast != 0 && aligned && (isx == 4 || isx == 8) && format != LVKB200_GRAY)
+    {
+        const dim3 g(div_up(dw, 32), div_up(dh, 4));
+        if (isx == 4)
+            k_ingest_gray_int<4><<<g, 128, 0, cs>>>(src, pitch, c0, c1, c2, dw, dh, isy, fast, fast_scale, dst, dst_pitch);
+        else
+            k_ingest_gray_int<8><<<g, 128, 0, cs>>>(src, pitch, c0, c1, c2, dw, dh, isy, fast, fast_scale, dst, dst_pitch);
+        count_launches(1);
+        LVKB_CUDA(cudaGetLastError());
+        return LVKB200_OK;
     }
     const dim3 grid(div_up(dw, DT_W), div_up(dh, DT_H));
     k_ingest_gray_area<<<grid, THREADS, 0, cs>>>(src, pitch, stride, c0, c1, c2, dw, dh, d_xtab.as<int2>(),

@@ -13,6 +13,7 @@ struct IngestPlan
     int xcount = 0, ycount = 0;  // table entries per destination column / row
     int fast = 0;                // 0 = weighted tables, 1 = integer block mean, 2 = OpenCV's 2x2 special case
     float fast_scale = 0.f;
+    int isx = 0, isy = 0;        // the integer scale factors when fast != 0
     DeviceBuffer d_xtab, d_ytab, d_xw, d_yw;
 
     // (Re)builds the tables when the geometry changed.

@@ -193,15 +193,50 @@ struct LkArg
 
 __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 
+// One warp per point, four points per CTA.  The frame's parameters and points normally travel AS KERNEL ARGUMENTS
+// (`pack`, up to LK_INLINE_POINTS points = 20.8 KB of the 32 KB parameter space): they ride the launch itself, so the
+// chain needs neither a copy-engine transfer (which would queue behind the neighbouring frames' multi-megabyte
+// uploads) nor SM reads of host memory over PCIe (measured: ~1 us per dependent read, serialised).  With
+// pack.inline_points == 0 they are read from io.pts_in / io.prm_in (device memory) instead.  Device copies of the
+// inputs are left for the kernels that follow; io.next_host / io.status_host (optional, mapped pinned host memory)
+// receive a second copy of the results as posted PCIe writes.
+static_assert(sizeof(TrackParams) == 24, "TrackParams is moved as six 32-bit words");
+static_assert(sizeof(LkPack) <= 32764 - 512, "kernel parameter space");
+
 __global__ void __launch_bounds__(128)
-    k_lk_track(LkArg a, const float2* __restrict__ prev_pts, const TrackParams* __restrict__ prm,
-               float2* __restrict__ next_pts, uint8_t* __restrict__ status)
+    k_lk_track(LkArg a, LkIo io, const __grid_constant__ LkPack pack)
 {
-    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pt >= prm->n) return;
+    __shared__ uint32_t s_prm[6];
+    __shared__ float s_pts[8];
+    __shared__ float s_out[8];
+    __shared__ uint32_t s_status;
+    const int base = blockIdx.x * 4;
+    if (pack.inline_points)
+    {
+        if (threadIdx.x < 6) s_prm[threadIdx.x] = reinterpret_cast<const uint32_t*>(&pack.prm)[threadIdx.x];
+        else if (threadIdx.x >= 8 && threadIdx.x < 16 && base + 3 < LK_INLINE_POINTS)
+            s_pts[threadIdx.x - 8] = reinterpret_cast<const float*>(pack.pts)[2 * base + (threadIdx.x - 8)];
+    }
+    else
+    {
+        if (threadIdx.x < 6) s_prm[threadIdx.x] = __ldcv(reinterpret_cast<const uint32_t*>(io.prm_in) + threadIdx.x);
+        else if (threadIdx.x >= 8 && threadIdx.x < 16)
+            s_pts[threadIdx.x - 8] = __ldcv(reinterpret_cast<const float*>(io.pts_in) + 2 * base + (threadIdx.x - 8));
+    }
+    if (threadIdx.x == 0) s_status = 0;
+    __syncthreads();
+    const TrackParams* prm = reinterpret_cast<const TrackParams*>(s_prm);
+    const int n = prm->n;
+    if (base >= n) return;  // whole CTA
+    if (blockIdx.x == 0 && threadIdx.x < 6 && io.prm_copy) reinterpret_cast<uint32_t*>(io.prm_copy)[threadIdx.x] = s_prm[threadIdx.x];
+    if (threadIdx.x < 8 && io.pts_copy) reinterpret_cast<float*>(io.pts_copy)[2 * base + threadIdx.x] = s_pts[threadIdx.x];
+
+    const int wid = threadIdx.x >> 5;
+    const int pt = base + wid;
     const double epsilon_sq = prm->lk_epsilon_sq;
     const int lane = threadIdx.x & 31;
-    const float2 p0 = prev_pts[pt];
+    const float2 p0 = make_float2(s_pts[2 * wid], s_pts[2 * wid + 1]);
+    const int max_level = (pt < n) ? a.max_level : -1;  // warps past the last point only take part in the barriers
     const float half = 5.0f;       // (winSize - 1) * 0.5
     const float FLT_SCALE = 1.0f / (float)(1 << 20);
     float2 out = make_float2(0.f, 0.f);
@@ -217,7 +252,7 @@ __global__ void __launch_bounds__(128)
         wx[q] = idx - wy[q] * WIN;
     }
 
-    for (int level = a.max_level; level >= 0; level--)
+    for (int level = max_level; level >= 0; level--)
     {
         const int cols = a.w[level], rows = a.h[level];
         const float inv = (float)(1.0 / (double)(1 << level));
@@ -335,8 +370,21 @@ __global__ void __launch_bounds__(128)
     }
     if (lane == 0)
     {
-        next_pts[pt] = out;
-        status[pt] = ok ? 1 : 0;
+        s_out[2 * wid] = out.x;
+        s_out[2 * wid + 1] = out.y;
+        atomicOr(&s_status, (ok ? 1u : 0u) << (8 * wid));
+    }
+    __syncthreads();
+    // 4 points = one 32-byte row of coordinates and one 32-bit word of status bytes per CTA
+    if (threadIdx.x < 8)
+    {
+        reinterpret_cast<float*>(io.next)[2 * base + threadIdx.x] = s_out[threadIdx.x];
+        if (io.next_host) reinterpret_cast<float*>(io.next_host)[2 * base + threadIdx.x] = s_out[threadIdx.x];
+    }
+    else if (threadIdx.x == 8)
+    {
+        reinterpret_cast<uint32_t*>(io.status)[blockIdx.x] = s_status;
+        if (io.status_host) reinterpret_cast<uint32_t*>(io.status_host)[blockIdx.x] = s_status;
     }
 }
 
@@ -462,12 +510,15 @@ double lk_epsilon_for_call(int call_index)
     return eps;
 }
 
-lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, const float2* d_prev_pts,
-                        int max_points, const TrackParams* d_params, float2* d_next_pts, uint8_t* d_status)
+lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid& next, int max_points, const LkIo& io,
+                        const LkPack* pack)
 {
-    // The grid covers max_points; warps beyond the frame's actual count (d_params->n) exit at once.
+    // The grid covers max_points; CTAs beyond the frame's actual count exit at once.
     const int n = max_points;
     if (n <= 0) return LVKB200_OK;
+    LVKB_REQUIRE((n & 3) == 0 && io.next && io.status);
+    LVKB_REQUIRE(pack ? (pack->inline_points != 0 && n <= LK_INLINE_POINTS) : (io.pts_in && io.prm_in));
+    static const LkPack no_pack{};  // inline_points == 0
     LVKB_REQUIRE(prev.levels == next.levels && prev.levels > 0 && prev.w[0] == next.w[0] && prev.h[0] == next.h[0]);
     LkArg a{};
     for (int l = 0; l < prev.levels; l++)
@@ -481,7 +532,7 @@ lvkb200_status lk_track(cudaStream_t cs, const LkPyramid& prev, const LkPyramid&
         a.h[l] = prev.h[l];
     }
     a.max_level = prev.levels - 1;
-    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, d_prev_pts, d_params, d_next_pts, d_status);
+    k_lk_track<<<div_up(n, 4), 128, 0, cs>>>(a, io, pack ? *pack : no_pack);
     count_launches(1);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;

@@ -42,18 +42,10 @@ namespace
 constexpr int HYP = RANSAC_HYPOTHESES;
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Zero-copy transfers of the chain's tiny inputs/outputs (params, <= 2 601 points, status/mask/model): a kernel
-// reads/writes MAPPED pinned host memory directly.  A cudaMemcpyAsync would queue on the copy engines behind the
-// multi-megabyte frame upload/download of the neighbouring frames (pipelined operation) and stall the whole chain.
-
-__global__ void __launch_bounds__(256)
-    k_transfer2(const uint4* __restrict__ src0, uint4* __restrict__ dst0, int n0, const uint4* __restrict__ src1,
-                uint4* __restrict__ dst1, int n1)
-{
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int i = tid; i < n0; i += nth) dst0[i] = src0[i];
-    for (int i = tid; i < n1; i += nth) dst1[i] = src1[i];
-}
+// The chain's tiny inputs/outputs (params, <= 2 601 points, status/mask/model) live in MAPPED pinned host memory that
+// the kernels read/write directly (LK fetches its inputs, LK and the refine kernel deliver the results).  A
+// cudaMemcpyAsync would queue on the copy engines behind the multi-megabyte frame upload/download of the neighbouring
+// frames (pipelined operation) and stall the whole chain; separate transfer kernels cost ~9 us each.
 
 // ---------------------------------------------------------------------------------------------------------------------
 // fast_filter: for k = n-1 .. 0: if !keep[k]: data[k] = data.back(); data.pop_back()
@@ -266,11 +258,11 @@ __global__ void __launch_bounds__(256)
 constexpr int RT = 256;   // refine CTA size (44 double accumulators per thread: keep the register budget)
 constexpr int NACC = 44;  // 36 (upper triangle of A^T W A) + 8 (A^T W b)
 
-__global__ void __launch_bounds__(RT)
-    k_ransac_refine(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                    const float* __restrict__ models, const float* __restrict__ scores,
-                    const TrackParams* __restrict__ prm, int iterations, RansacResult* __restrict__ result,
-                    uint8_t* __restrict__ mask)
+__device__ __forceinline__ void
+    refine_body(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
+                const float* __restrict__ models, const float* __restrict__ scores,
+                const TrackParams* __restrict__ prm, int iterations, RansacResult* __restrict__ result,
+                uint8_t* __restrict__ mask)
 {
     const float thr2 = prm->threshold_sq;
     cg::thread_block block = cg::this_thread_block();
@@ -536,19 +528,37 @@ __global__ void __launch_bounds__(RT)
     }
 }
 
-}  // namespace
+static_assert(sizeof(RansacResult) % 4 == 0, "RansacResult is moved as 32-bit words");
 
-lvkb200_status zero_copy_transfer(cudaStream_t cs, const void* src0, void* dst0, size_t bytes0, const void* src1,
-                                  void* dst1, size_t bytes1)
+__device__ __forceinline__ void copy16(const uint8_t* src, uint8_t* dst, int bytes)
 {
-    // all pointers 16-byte aligned, sizes rounded up to 16 by the caller's allocations
-    const int n0 = static_cast<int>((bytes0 + 15) / 16), n1 = static_cast<int>((bytes1 + 15) / 16);
-    k_transfer2<<<8, 256, 0, cs>>>(static_cast<const uint4*>(src0), static_cast<uint4*>(dst0), n0,
-                                   static_cast<const uint4*>(src1), static_cast<uint4*>(dst1), n1);
-    count_launches(1);
-    LVKB_CUDA(cudaGetLastError());
-    return LVKB200_OK;
+    for (int i = threadIdx.x; i < (bytes + 15) / 16; i += RT)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
 }
+
+// The estimator's last kernel also delivers the chain's results: it copies the used part of the result block (LK
+// matches + status of the prm->n tracked points, inlier mask, model) into MAPPED PINNED HOST memory with 16-byte
+// posted PCIe writes, so no transfer step follows on the frame's critical path and no copy engine is involved.
+__global__ void __launch_bounds__(RT)
+    k_ransac_refine(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
+                    const float* __restrict__ models, const float* __restrict__ scores,
+                    const TrackParams* __restrict__ prm, int iterations, RansacResult* __restrict__ result,
+                    uint8_t* __restrict__ mask, TrackOutCopy out)
+{
+    constexpr int RESULT_WORDS = sizeof(RansacResult) / 4;
+    if (threadIdx.x < RESULT_WORDS) reinterpret_cast<uint32_t*>(result)[threadIdx.x] = 0u;
+    __syncthreads();
+    refine_body(src, dst, n_ptr, models, scores, prm, iterations, result, mask);
+    if (!out.host) return;
+    __syncthreads();  // the block's global writes (mask, result) are visible to all of its threads
+    const int tracked = prm->n, estimated = *n_ptr;
+    copy16(out.dev, out.host, tracked * (int)sizeof(float2));
+    copy16(out.dev + out.off_status, out.host + out.off_status, tracked);
+    copy16(out.dev + out.off_mask, out.host + out.off_mask, estimated);
+    copy16(out.dev + out.off_result, out.host + out.off_result, (int)sizeof(RansacResult));
+}
+
+}  // namespace
 
 lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,
                                   const TrackParams* d_params, float2* d_a_out, float2* d_b_out, int* d_perm,
@@ -562,13 +572,12 @@ lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const floa
 
 lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,
                                  const TrackParams* d_params, float* d_models, float* d_scores,
-                                 RansacResult* d_result, uint8_t* d_mask)
+                                 RansacResult* d_result, uint8_t* d_mask, const TrackOutCopy& out)
 {
-    LVKB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(RansacResult), cs));
     k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, d_params, 0x9E3779B9u, d_models);
     k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, d_params, d_scores);
     k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, d_params, RANSAC_REFINE_ITERS, d_result,
-                                      d_mask);
+                                      d_mask, out);
     count_launches(3);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;

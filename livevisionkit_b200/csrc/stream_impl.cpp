@@ -35,8 +35,8 @@ constexpr float QA_UPDATE_RATE = 0.1f;  // StabilizationFilter.cpp:29
 constexpr float QA_BLEND_STEP = 0.05f;  // StabilizationFilter.cpp:30
 constexpr float HOMOGRAPHY_DISTRIBUTION_THRESHOLD = 0.6f;  // FrameTracker.cpp:37
 
-enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_FAST, ST_LK, ST_ESTIMATE, ST_REMAP, ST_XFER_IN, ST_XFER_OUT };
-static_assert(ST_XFER_OUT + 1 == LVKB200_STAGE_COUNT, "stage table out of step with lvkb200.h");
+enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_FAST, ST_LK, ST_ESTIMATE, ST_REMAP };
+static_assert(ST_REMAP + 1 == LVKB200_STAGE_COUNT, "stage table out of step with lvkb200.h");
 
 lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
 {
@@ -283,37 +283,60 @@ void lvkb200_stream::destroy_graphs()
 }
 
 // The device work of the tracking chain, in stream order on `cs` (either captured into a graph or executed eagerly):
-// params + points H2D -> LK -> [swap-erase compaction -> RANSAC] -> ONE D2H of all results.
-lvkb200_status lvkb200_stream::record_tracking_chain(int parity, bool global, int max_points, bool with_events)
+// LK (fetches the parameters + points from mapped pinned host memory itself) -> [swap-erase compaction -> RANSAC];
+// LK and the estimator's last kernel also write their results into mapped pinned host memory, so the chain has no
+// transfer steps of its own and never touches a copy engine.
+lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool with_events)
+{
+    // LK is launched eagerly: the frame's parameters and points ride the launch as kernel arguments (lk_pack).
+    uint8_t* hout = h_track_out.device_view<uint8_t>();
+    LVKB_REQUIRE(hout != nullptr);
+    LkIo io{};
+    io.pts_copy = d_pts_prev.as<float2>();
+    io.prm_copy = d_params.as<TrackParams>();
+    io.next = d_pts_next();
+    io.status = d_status();
+    if (!global)
+    {
+        // no estimator kernel follows (local motions are solved on the host): LK delivers its own results
+        io.next_host = reinterpret_cast<float2*>(hout);
+        io.status_host = hout + off_status;
+    }
+    const bool inline_points = point_capacity <= LK_INLINE_POINTS;
+    if (!inline_points)
+    {
+        // more points than the parameter space holds: the kernel reads them from mapped pinned host memory (slow path)
+        std::memcpy(h_params.ptr, &lk_pack.prm, sizeof(TrackParams));
+        io.pts_in = h_pts_prev.device_view<float2>();
+        io.prm_in = h_params.device_view<TrackParams>();
+    }
+    if (with_events) stage_begin(ST_LK);
+    LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], (n + 3) / 4 * 4, io, inline_points ? &lk_pack : nullptr));
+    if (with_events) stage_end(ST_LK);
+    return LVKB200_OK;
+}
+
+// The estimator's device work in stream order on `cs` (captured into a graph or executed eagerly):
+// swap-erase compaction -> hypotheses -> scores -> refine, whose last kernel also copies the chain's results into
+// mapped pinned host memory: no transfer step of its own, no copy engine.
+lvkb200_status lvkb200_stream::record_estimator_chain(bool with_events)
 {
     const TrackParams* prm = d_params.as<TrackParams>();
-    // inputs come straight out of mapped pinned memory (a kernel, not the copy engine: see k_transfer2)
-    const void* hp = h_params.device_view<void>();
-    const void* hpts = h_pts_prev.device_view<void>();
-    void* hout = h_track_out.device_view<void>();
-    LVKB_REQUIRE(hp != nullptr && hpts != nullptr && hout != nullptr);
-    if (with_events) stage_begin(ST_XFER_IN);
-    LVKB_TRY(zero_copy_transfer(cs, hp, d_params.ptr, sizeof(TrackParams), hpts, d_pts_prev.ptr,
-                                sizeof(float2) * max_points));
-    if (with_events) stage_end(ST_XFER_IN);
-    if (with_events) stage_begin(ST_LK);
-    LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], d_pts_prev.as<float2>(), max_points, prm, d_pts_next(), d_status()));
-    if (with_events) stage_end(ST_LK);
-    if (global)
-    {
-        // fast_filter + motion estimation chained on the device; the host replays the same erase order afterwards.
-        // The model (homography / partial affine, FrameTracker.cpp:167-176) is selected by TrackParams::model.
-        if (with_events) stage_begin(ST_ESTIMATE);
-        LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next(), d_status(), prm, d_src.as<float2>(),
-                                    d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(), d_count.as<int>()));
-        LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), prm,
-                                   d_models.as<float>(), d_scores.as<float>(), d_result(), d_mask()));
-        if (with_events) stage_end(ST_ESTIMATE);
-    }
-    // results go straight into mapped pinned memory; visible to the host after the stream synchronisation
-    if (with_events) stage_begin(ST_XFER_OUT);
-    LVKB_TRY(zero_copy_transfer(cs, d_track_out.ptr, hout, track_out_bytes, nullptr, nullptr, 0));
-    if (with_events) stage_end(ST_XFER_OUT);
+    TrackOutCopy out{};
+    out.dev = d_track_out.as<uint8_t>();
+    out.host = h_track_out.device_view<uint8_t>();
+    out.off_status = static_cast<uint32_t>(off_status);
+    out.off_mask = static_cast<uint32_t>(off_mask);
+    out.off_result = static_cast<uint32_t>(off_result);
+    LVKB_REQUIRE(out.host != nullptr);
+    // fast_filter + motion estimation chained on the device; the host replays the same erase order afterwards.
+    // The model (homography / partial affine, FrameTracker.cpp:167-176) is selected by TrackParams::model.
+    if (with_events) stage_begin(ST_ESTIMATE);
+    LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next(), d_status(), prm, d_src.as<float2>(),
+                                d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(), d_count.as<int>()));
+    LVKB_TRY(ransac_homography(cs, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), prm,
+                               d_models.as<float>(), d_scores.as<float>(), d_result(), d_mask(), out));
+    if (with_events) stage_end(ST_ESTIMATE);
     return LVKB200_OK;
 }
 
@@ -322,24 +345,30 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
 {
     const int n = static_cast<int>(pts.size() / 2);
     LVKB_TRY(ensure_points(n));
-    TrackParams* hp = h_params.as<TrackParams>();
-    hp->n = n;
-    hp->model = model;
-    hp->lk_epsilon_sq = lk_epsilon_for_call(lk_calls);
-    hp->threshold_sq = threshold * threshold;
+    TrackParams& hp = lk_pack.prm;
+    hp.n = n;
+    hp.model = model;
+    hp.lk_epsilon_sq = lk_epsilon_for_call(lk_calls);
+    hp.threshold_sq = threshold * threshold;
     lk_calls = std::min(lk_calls + 1, 64);  // one m_OpticalTracker per FrameTracker: never reset (FrameTracker.cpp:41)
-    std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
+    lk_pack.inline_points = 1;
+    if (point_capacity <= LK_INLINE_POINTS)
+        std::memcpy(lk_pack.pts, pts.data(), sizeof(float) * pts.size());
+    else
+        std::memcpy(h_pts_prev.ptr, pts.data(), sizeof(float) * pts.size());
 
-    if (!use_graphs || profile_stages)
-        return record_tracking_chain(cur, global, point_capacity, profile_stages);
+    LVKB_TRY(launch_lk(cur, global, n, profile_stages));
+    if (!global) return LVKB200_OK;
+    if (!use_graphs || profile_stages) return record_estimator_chain(profile_stages);
 
-    cudaGraphExec_t& exec = track_graph[cur][global ? 1 : 0];
+    // compaction + RANSAC (4 kernels) replay as ONE CUDA graph: one launch instead of four, no inter-kernel API gaps
+    cudaGraphExec_t& exec = track_graph[0][1];
     if (!exec)
     {
         const uint64_t launches_before = launch_count();
         cudaGraph_t graph = nullptr;
         LVKB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        const lvkb200_status st = record_tracking_chain(cur, global, point_capacity, false);
+        const lvkb200_status st = record_estimator_chain(false);
         const cudaError_t e = cudaStreamEndCapture(cs, &graph);
         count_launches(-static_cast<int>(launch_count() - launches_before));  // counted per replay instead
         if (st != LVKB200_OK || e != cudaSuccess || !graph)
@@ -347,7 +376,7 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
             use_graphs = false;  // fall back to eager launches for the rest of this stream's life
-            return record_tracking_chain(cur, global, point_capacity, false);
+            return record_estimator_chain(false);
         }
         const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
@@ -356,11 +385,11 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
             exec = nullptr;
             cudaGetLastError();
             use_graphs = false;
-            return record_tracking_chain(cur, global, point_capacity, false);
+            return record_estimator_chain(false);
         }
     }
     LVKB_CUDA(cudaGraphLaunch(exec, cs));
-    count_launches(global ? 7 : 3);  // transfer-in, LK, [compact, hypotheses, score, refine], transfer-out
+    count_launches(4);  // compact, hypotheses, score, refine
     return LVKB200_OK;
 }
 

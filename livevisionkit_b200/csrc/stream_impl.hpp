@@ -55,7 +55,9 @@ struct lvkb200_stream
     bool profile_stages = false;  // per-stage CUDA events (eager path); off by default
     void destroy_graphs();
     lvkb200_status enqueue_tracking(const std::vector<float>& pts, bool global, float threshold, int model);
-    lvkb200_status record_tracking_chain(int parity, bool global, int max_points, bool with_events);
+    lvkb200::LkPack lk_pack{};  // this frame's parameters + points: passed to the LK kernel by value
+    lvkb200_status launch_lk(int parity, bool global, int n, bool with_events);
+    lvkb200_status record_estimator_chain(bool with_events);
 
     // ---- StabilizationFilter / FrameTracker / FeatureDetector / PathSmoother host state
     lvkb200::FeatureGrid grid;
