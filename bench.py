@@ -33,8 +33,19 @@ import numpy as np  # noqa: E402
 
 RES = "1080p"
 WIDTH, HEIGHT = 1920, 1080
+METRIC = "stabilized_frames_per_second_1080p"
 WORKLOAD = ("1080p60 synthetic hand-shake sequence, OBS Homography preset (480x270 detection, FAST grid -> pyramidal LK "
             "-> homography RANSAC -> path smoother -> FSR-EASU remap), 1 stream per GPU")
+
+
+def _select_workload(res):
+    """BASELINE.json configs[1] (1080p60, the default and the configuration the metric is quoted on) or configs[2]
+    (4K60, `--resolution 4k`)."""
+    global RES, WIDTH, HEIGHT, METRIC, WORKLOAD
+    if res == "4k":
+        RES, WIDTH, HEIGHT = "4k", 3840, 2160
+        METRIC = "stabilized_frames_per_second_4k"
+        WORKLOAD = WORKLOAD.replace("1080p60", "4K60")
 
 
 def _peaks():
@@ -110,7 +121,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     fps = args.steps / dt
     line = {
-        "impl": "reference", "metric": "stabilized_frames_per_second_1080p", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": "OBS Homography"},
@@ -138,7 +149,7 @@ def cpu_baseline_sample(frames, warm=12, count=60):
         flt.apply(frames[i], O.BGR, i)
     dt = time.perf_counter() - t0
     return {"value": count / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{count} frames of the same 1080p clip after {warm} warm-up frames, oracle port "
+            "sample": f"{count} frames of the same {RES} clip after {warm} warm-up frames, oracle port "
                       f"(cv2 {cv2.__version__} + scalar C EASU, {cores} threads)"}
 
 
@@ -149,8 +160,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resolution", default="1080p", choices=["1080p", "4k"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    _select_workload(args.resolution)
 
     if args.impl == "reference":
         run_reference(args)
@@ -282,11 +295,11 @@ def main():
         traffic = None
         try:  # per-launch DRAM bytes of the remap kernel from the committed ncu capture, if present
             prof = json.load(open(os.path.join(ROOT, "profiles", "remap_traffic.json")))
-            traffic = prof.get("dram_bytes_per_launch_1080p")
+            traffic = prof.get(f"dram_bytes_per_launch_{RES}")
         except Exception:
             pass
         line = {
-            "metric": "stabilized_frames_per_second_1080p", "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": "OBS Homography",

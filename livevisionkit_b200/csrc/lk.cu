@@ -16,6 +16,9 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.hpp"
 #include "lk.hpp"
 
@@ -39,6 +42,15 @@ __device__ __forceinline__ int reflect101(int p, int n)
         else p = 2 * (n - 1) - p;
     }
     return p;
+}
+
+// the same for any overshoot, without a loop (n >= 2)
+__device__ __forceinline__ int reflect101_closed(int p, int n)
+{
+    const int period = 2 * (n - 1);
+    int m = p % period;
+    if (m < 0) m += period;
+    return (m < n) ? m : period - m;
 }
 
 // Level 0: copy the detection image into the padded layout.
@@ -178,6 +190,148 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(PyrArg a)
             a.deriv[l][(size_t)py * a.deriv_pitch[l] + px] = out;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same pyramid WITHOUT grid-wide barriers: one CTA owns a 32x32 tile of level 0 and the matching 16x16 / 8x8 / 4x4
+// tiles of levels 1..3, and recomputes the halo it needs in shared memory (a 69x69 patch of level 0 feeds a 33x33
+// patch of level 1, a 15x15 patch of level 2 and a 6x6 patch of level 3).  The levels are tiny (130 K pixels at
+// 480x270), so the cooperative version above spends its time in four grid.sync()s and, needing all its CTAs
+// co-resident, cannot start while another stream's kernel (the previous output's remap) fills the machine.
+//
+// Patch entry (cx, cy) of level l holds the PADDED image value P_l(c) = L_l(reflect101(c)), evaluated at the reflected
+// coordinate exactly like k_pyr_down, so image-border pixels see the same neighbours as in the padded global layout.
+// Each interior pixel is written by the CTA that owns it, together with its mirror images in the 11-pixel border
+// (single reflection: every level is wider than the window); the derivative planes' zero border is written once, when
+// the planes are allocated.
+constexpr int PT_TILE = 32;
+constexpr int PT_S3 = 6, PT_S2 = 2 * PT_S3 + 3, PT_S1 = 2 * PT_S2 + 3, PT_S0 = 2 * PT_S1 + 3;  // 6, 15, 33, 69
+static_assert(LK_MAX_LEVELS == 4, "patch sizes are laid out for four levels");
+
+// writes value v of interior pixel (x, y) to the padded plane and to its mirror images inside the border
+__device__ __forceinline__ void store_mirrored(uint8_t* img, size_t pitch, int w, int h, int x, int y, uint8_t v)
+{
+    int xs[3], ys[3], nx = 1, ny = 1;
+    xs[0] = x; ys[0] = y;
+    if (x >= 1 && x <= P) xs[nx++] = -x;
+    if (x >= w - 1 - P && x <= w - 2) xs[nx++] = 2 * (w - 1) - x;
+    if (y >= 1 && y <= P) ys[ny++] = -y;
+    if (y >= h - 1 - P && y <= h - 2) ys[ny++] = 2 * (h - 1) - y;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) img[(size_t)(ys[j] + P) * pitch + (xs[i] + P)] = v;
+}
+
+// pyrDown of the finer patch `f` (size fs, origin fo) evaluated at coarse coordinate (rx, ry)
+__device__ __forceinline__ int pyr_down_at(const uint8_t* f, int fs, int fox, int foy, int rx, int ry)
+{
+    int bx = 2 * rx - 2 - fox, by = 2 * ry - 2 - foy;
+    bx = max(0, min(fs - 5, bx));  // only entries nobody reads can be clamped (see above)
+    by = max(0, min(fs - 5, by));
+    const uint8_t* base = f + by * fs + bx;
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+    {
+        const uint8_t* r = base + j * fs;
+        const int row = (int)r[0] + 4 * (int)r[1] + 6 * (int)r[2] + 4 * (int)r[3] + (int)r[4];
+        const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+        sum += kj * row;
+    }
+    return (sum + 128) >> 8;
+}
+
+// interior pixels of this CTA's tile of one level: padded image (+ mirrors) and Scharr derivative from the patch
+template <int TILE>
+__device__ __forceinline__ void emit_level(const PyrArg& a, int l, const uint8_t* patch, int ps, int ox, int oy, int tx0,
+                                           int ty0)
+{
+    const int w = a.w[l], h = a.h[l];
+    for (int i = threadIdx.x; i < TILE * TILE; i += blockDim.x)
+    {
+        const int ly = i / TILE, lx = i - ly * TILE;
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x >= w || y >= h) continue;
+        const uint8_t* c = patch + (y - oy) * ps + (x - ox);
+        store_mirrored(a.img[l], a.img_pitch[l], w, h, x, y, c[0]);
+        const int u0 = c[-ps - 1], u1 = c[-ps], u2 = c[-ps + 1];
+        const int m0 = c[-1], m2 = c[1];
+        const int d0 = c[ps - 1], d1 = c[ps], d2 = c[ps + 1];
+        const int t0l = (u0 + d0) * 3 + m0 * 10, t0r = (u2 + d2) * 3 + m2 * 10;
+        const int t1l = d0 - u0, t1c = d1 - u1, t1r = d2 - u2;
+        a.deriv[l][(size_t)(y + P) * a.deriv_pitch[l] + (x + P)] =
+            make_short2((short)(t0r - t0l), (short)((t1r + t1l) * 3 + t1c * 10));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pyramid_tiles(PyrArg a)
+{
+    __shared__ uint8_t p0[PT_S0 * PT_S0], p1[PT_S1 * PT_S1], p2[PT_S2 * PT_S2], p3[PT_S3 * PT_S3];
+    // patch origins (level coordinates): the level-3 patch is the 4x4 tile plus the Scharr halo, each finer patch the
+    // 5-tap footprint of the coarser one
+    const int o3x = (PT_TILE >> 3) * blockIdx.x - 1, o3y = (PT_TILE >> 3) * blockIdx.y - 1;
+    const int o2x = 2 * o3x - 2, o2y = 2 * o3y - 2;
+    const int o1x = 2 * o2x - 2, o1y = 2 * o2y - 2;
+    const int o0x = 2 * o1x - 2, o0y = 2 * o1y - 2;
+
+    // reflected coordinates of every patch column and row, once per CTA (an integer modulo per ELEMENT was a third of
+    // this kernel's instructions): rx[l][i] = reflect101(o_l.x + i), same for ry
+    __shared__ short rx0[PT_S0], ry0[PT_S0], rx1[PT_S1], ry1[PT_S1], rx2[PT_S2], ry2[PT_S2], rx3[PT_S3], ry3[PT_S3];
+    {
+        const int t = threadIdx.x;
+        if (t < PT_S0) { rx0[t] = (short)reflect101_closed(o0x + t, a.w[0]); ry0[t] = (short)reflect101_closed(o0y + t, a.h[0]); }
+        else if (t >= 96 && t < 96 + PT_S1 && a.levels > 1)
+        { rx1[t - 96] = (short)reflect101_closed(o1x + t - 96, a.w[1]); ry1[t - 96] = (short)reflect101_closed(o1y + t - 96, a.h[1]); }
+        else if (t >= 160 && t < 160 + PT_S2 && a.levels > 2)
+        { rx2[t - 160] = (short)reflect101_closed(o2x + t - 160, a.w[2]); ry2[t - 160] = (short)reflect101_closed(o2y + t - 160, a.h[2]); }
+        else if (t >= 192 && t < 192 + PT_S3 && a.levels > 3)
+        { rx3[t - 192] = (short)reflect101_closed(o3x + t - 192, a.w[3]); ry3[t - 192] = (short)reflect101_closed(o3y + t - 192, a.h[3]); }
+    }
+    __syncthreads();
+    {
+        // all of a thread's loads are issued before the first store (19 independent global loads in flight per thread:
+        // the patch load is the only part of this kernel that waits for L2)
+        constexpr int PER = (PT_S0 * PT_S0 + 255) / 256;
+        uint8_t v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+        {
+            const int i = min(threadIdx.x + 256 * k, PT_S0 * PT_S0 - 1);
+            const int py = i / PT_S0, px = i - py * PT_S0;
+            v[k] = __ldg(a.det + (size_t)ry0[py] * a.det_pitch + rx0[px]);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+        {
+            const int i = threadIdx.x + 256 * k;
+            if (i < PT_S0 * PT_S0) p0[i] = v[k];
+        }
+    }
+    __syncthreads();
+    emit_level<PT_TILE>(a, 0, p0, PT_S0, o0x, o0y, PT_TILE * blockIdx.x, PT_TILE * blockIdx.y);
+    if (a.levels < 2) return;
+    for (int i = threadIdx.x; i < PT_S1 * PT_S1; i += blockDim.x)
+    {
+        const int py = i / PT_S1, px = i - py * PT_S1;
+        p1[i] = (uint8_t)pyr_down_at(p0, PT_S0, o0x, o0y, rx1[px], ry1[py]);
+    }
+    __syncthreads();
+    emit_level<(PT_TILE >> 1)>(a, 1, p1, PT_S1, o1x, o1y, (PT_TILE >> 1) * blockIdx.x, (PT_TILE >> 1) * blockIdx.y);
+    if (a.levels < 3) return;
+    if (threadIdx.x < PT_S2 * PT_S2)
+    {
+        const int py = threadIdx.x / PT_S2, px = threadIdx.x - py * PT_S2;
+        p2[threadIdx.x] = (uint8_t)pyr_down_at(p1, PT_S1, o1x, o1y, rx2[px], ry2[py]);
+    }
+    __syncthreads();
+    emit_level<(PT_TILE >> 2)>(a, 2, p2, PT_S2, o2x, o2y, (PT_TILE >> 2) * blockIdx.x, (PT_TILE >> 2) * blockIdx.y);
+    if (a.levels < 4) return;
+    if (threadIdx.x < PT_S3 * PT_S3)
+    {
+        const int py = threadIdx.x / PT_S3, px = threadIdx.x - py * PT_S3;
+        p3[threadIdx.x] = (uint8_t)pyr_down_at(p2, PT_S2, o2x, o2y, rx3[px], ry3[py]);
+    }
+    __syncthreads();
+    emit_level<(PT_TILE >> 3)>(a, 3, p3, PT_S3, o3x, o3y, (PT_TILE >> 3) * blockIdx.x, (PT_TILE >> 3) * blockIdx.y);
 }
 
 struct LkArg
@@ -409,10 +563,16 @@ lvkb200_status LkPyramid::prepare(int width, int height)
         h[l] = lh;
         img_pitch[l] = (size_t)((lw + 2 * P + 15) / 16 * 16);
         deriv_pitch[l] = (size_t)((lw + 2 * P + 3) / 4 * 4);
-        LVKB_CUDA(img[l].ensure(img_pitch[l] * (lh + 2 * P + 1) + 16));
-        LVKB_CUDA(deriv[l].ensure(sizeof(short2) * (deriv_pitch[l] * (lh + 2 * P + 1) + 16)));
+        const size_t img_bytes = img_pitch[l] * (lh + 2 * P + 1) + 16;
+        const size_t deriv_bytes = sizeof(short2) * (deriv_pitch[l] * (lh + 2 * P + 1) + 16);
+        LVKB_CUDA(img[l].ensure(img_bytes));
+        LVKB_CUDA(deriv[l].ensure(deriv_bytes));
+        // the derivative planes' border is zero (BORDER_CONSTANT) and only the tile builder's interior is rewritten
+        LVKB_CUDA(cudaMemset(img[l].ptr, 0, img_bytes));
+        LVKB_CUDA(cudaMemset(deriv[l].ptr, 0, deriv_bytes));
         levels++;
     }
+    LVKB_CUDA(cudaDeviceSynchronize());  // the memsets ran on the legacy stream: order them before any stream's kernels
     valid = false;
     return LVKB200_OK;
 }
@@ -431,7 +591,32 @@ void LkPyramid::release()
 
 lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_pitch)
 {
-    // ---- fast path: one cooperative launch for the whole pyramid
+    // ---- default: one ordinary launch, one CTA per 32x32 tile across all levels (no grid-wide barriers)
+    const char* forced = std::getenv("LVKB200_PYRAMID");  // "coop" / "levels": the older builders, kept for A/B tests
+    if (!forced || !*forced || std::strcmp(forced, "tiles") == 0)
+    {
+        PyrArg pa{};
+        pa.det = det;
+        pa.det_pitch = det_pitch;
+        pa.levels = levels;
+        for (int l = 0; l < levels; l++)
+        {
+            pa.img[l] = img[l].as<uint8_t>();
+            pa.deriv[l] = deriv[l].as<short2>();
+            pa.img_pitch[l] = img_pitch[l];
+            pa.deriv_pitch[l] = deriv_pitch[l];
+            pa.w[l] = w[l];
+            pa.h[l] = h[l];
+        }
+        k_pyramid_tiles<<<dim3(div_up(w[0], PT_TILE), div_up(h[0], PT_TILE)), 256, 0, cs>>>(pa);
+        count_launches(1);
+        LVKB_CUDA(cudaGetLastError());
+        valid = true;
+        return LVKB200_OK;
+    }
+    const bool allow_coop = std::strcmp(forced, "levels") != 0;
+
+    // ---- one cooperative launch for the whole pyramid
     static int coop_blocks = -1;  // co-resident 256-thread CTAs of k_pyramid_fused on this device (0 = unsupported)
     if (coop_blocks < 0)
     {
@@ -443,7 +628,7 @@ lvkb200_status LkPyramid::build(cudaStream_t cs, const uint8_t* det, size_t det_
         coop_blocks = (coop && per_sm > 0) ? sms * std::min(per_sm, 2) : 0;
         cudaGetLastError();
     }
-    if (coop_blocks > 0)
+    if (coop_blocks > 0 && allow_coop)
     {
         PyrArg pa{};
         pa.det = det;

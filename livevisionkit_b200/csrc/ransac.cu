@@ -255,8 +255,21 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-constexpr int RT = 256;   // refine CTA size (44 double accumulators per thread: keep the register budget)
-constexpr int NACC = 44;  // 36 (upper triangle of A^T W A) + 8 (A^T W b)
+constexpr int RT = 256;  // refine CTA size
+
+// Entry (r, c) of the 8 x 9 augmented normal equations [A^T W A | A^T W b] of the weighted DLT (h33 = 1) from the 23
+// moments S[0..5] = S0, S[6..11] = Su, S[12..17] = Sv, S[18..22] = Sq, each packed xx xy x yy y 1 (see refine_body).
+__device__ __forceinline__ double gram_entry(const double* S, int r, int c)
+{
+    const int pack[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    const int rb = r / 3, ri = r - 3 * rb;
+    if (c == 8) return (rb == 0) ? S[6 + pack[ri][2]] : (rb == 1) ? S[12 + pack[ri][2]] : -S[18 + pack[ri][2]];
+    const int cb = c / 3, ci = c - 3 * cb;
+    if (rb == cb) return (rb < 2) ? S[pack[ri][ci]] : S[18 + pack[ri][ci]];
+    if (rb + cb == 1) return 0.0;
+    const int other = min(rb, cb), i = (rb < cb) ? ri : ci, j = (rb < cb) ? ci : ri;  // i: index in p, j: block-2 index
+    return -S[(other == 0 ? 6 : 12) + pack[i][j]];
+}
 
 __device__ __forceinline__ void
     refine_body(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
@@ -269,7 +282,9 @@ __device__ __forceinline__ void
     cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
     __shared__ float s_best[RT / 32];
     __shared__ int s_besti[RT / 32];
-    __shared__ double s_acc[RT / 32][NACC];
+    __shared__ double s_acc[RT / 32][8];
+    __shared__ double s_part[RT / 32][32];
+    __shared__ double s_mom[32];
     __shared__ double s_T[8];
     __shared__ float s_m[9];
     __shared__ int s_ok;
@@ -404,14 +419,20 @@ __device__ __forceinline__ void
     // ---- IRLS: weighted DLT with h33 = 1 in normalised coordinates.
     // weights: sigma-consensus style, smooth and compactly supported: w = (1 - e/c)^2 for e < c, c = 2.25 * thr^2
     // (support 1.5x the acceptance radius), so points just outside the threshold still pull a little, far ones not at all.
+    //
+    // The normal equations A^T W A h = A^T W b of the rows [p 0 -u p | u], [0 p -v p | v] (p = (x, y, 1)) have block
+    // structure: every entry is +-one of the 23 moments  S0 = sum w p p^T, Su = sum w u p p^T, Sv = sum w v p p^T,
+    // Sq = sum w (u^2+v^2) p p^T  (gram_entry), so a thread carries 23 accumulators instead of 36 + 8, and the warp
+    // total is taken with a recursive-halving reduce-scatter (31 shuffles for all 23 values; lane l ends up owning
+    // moment l) instead of 44 five-step butterflies: the shuffle unit was what this single-CTA kernel waited on.
     const float c_sup = 2.25f * thr2;
     for (int it = 0; it < iterations; it++)
     {
         float m[9];
         for (int j = 0; j < 9; j++) m[j] = s_m[j];
-        double acc[NACC];
-        for (int j = 0; j < NACC; j++) acc[j] = 0.0;
-        double wsum = 0.0;
+        double acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = 0.0;
         for (int i = tid; i < n; i += RT)
         {
             const float2 p = src[i], d = dst[i];
@@ -419,50 +440,50 @@ __device__ __forceinline__ void
             if (!(e == e) || e >= c_sup) continue;
             const float t = 1.0f - e / c_sup;
             const double w = (double)(t * t);
-            wsum += w;
             const double x = (p.x - cx) * s1, y = (p.y - cy) * s1, u = (d.x - cu) * s2, v = (d.y - cv) * s2;
-            const double r0[8] = {x, y, 1, 0, 0, 0, -u * x, -u * y};
-            const double r1[8] = {0, 0, 0, x, y, 1, -v * x, -v * y};
-            int k = 0;
+            const double wx = w * x, wy = w * y;
+            const double pp[6] = {wx * x, wx * y, wx, wy * y, wy, w};  // w * p p^T, packed xx xy x yy y 1
+            const double q = u * u + v * v;
 #pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int b = a; b < 8; b++) acc[k++] += w * (r0[a] * r0[b] + r1[a] * r1[b]);
-#pragma unroll
-            for (int a = 0; a < 8; a++) acc[36 + a] += w * (r0[a] * u + r1[a] * v);
+            for (int j = 0; j < 6; j++)
+            {
+                acc[j] += pp[j];
+                acc[6 + j] += u * pp[j];
+                acc[12 + j] += v * pp[j];
+                if (j < 5) acc[18 + j] += q * pp[j];
+            }
         }
-        for (int j = 0; j < NACC; j++) acc[j] = cg::reduce(warp, acc[j], cg::plus<double>());
-        wsum = cg::reduce(warp, wsum, cg::plus<double>());
-        block.sync();
-        if (lane == 0)
+        // reduce-scatter over the warp: after the step with `half`, slot i holds moment i + (lane & ~(half - 1)) % 32
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1)
         {
-            for (int j = 0; j < NACC; j++) s_acc[wid][j] = acc[j];
-            s_T[6] = 0.0;
+            const bool upper = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; i++)
+            {
+                const double keep = upper ? acc[i + half] : acc[i];
+                const double send = upper ? acc[i] : acc[i + half];
+                acc[i] = keep + warp.shfl_xor(send, half);
+            }
         }
+        s_part[wid][lane] = acc[0];  // this warp's total of moment `lane`
         block.sync();
-        if (lane == 0) atomicAdd(&s_T[6], wsum);
-        if (tid < NACC)
+        if (tid < 32)
         {
             double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
-            s_acc[0][tid] = s;
+            for (int w = 0; w < RT / 32; w++) s += s_part[w][tid];
+            s_mom[tid] = s;
         }
         block.sync();
-        if (s_T[6] < 4.0) break;  // support collapsed: keep the current model
+        if (s_mom[5] < 4.0) break;  // sum of weights: support collapsed, keep the current model
 
         // warp 0: Gauss-Jordan on the 8x9 augmented SPD system, lane r owns row r
         if (wid == 0)
         {
             double row[9];
             const int r = lane & 7;
-            {
-                int k = 0;
-                double full[8][8];
-                for (int a = 0; a < 8; a++)
-                    for (int b = a; b < 8; b++) { full[a][b] = s_acc[0][k]; full[b][a] = s_acc[0][k]; k++; }
-                for (int c = 0; c < 8; c++) row[c] = full[r][c];
-                row[8] = s_acc[0][36 + r];
-            }
+#pragma unroll
+            for (int c = 0; c < 9; c++) row[c] = gram_entry(s_mom, r, c);
             bool ok = true;
             for (int c = 0; c < 8; c++)
             {

@@ -131,6 +131,30 @@ def test_lk_parity(gpu_stream, oracle, det):
     assert err <= 0.01
 
 
+@pytest.mark.parametrize("size", [(480, 270), (256, 256), (333, 201), (97, 64), (50, 37)])
+def test_pyramid_builders_agree(gpu_stream, size, monkeypatch):
+    """The tile pyramid builder (default, no grid-wide barriers) against the per-level builder: a dense grid of
+    probes, borders included, must track bit-identically, i.e. every level and derivative plane the windows touch
+    (all of them, with an 11-px window every 3 px) is the same.  The per-level builder is the one pinned against
+    cv2 by test_lk_parity before the tile builder existed."""
+    w, h = size
+    rng = np.random.default_rng(w * 1000 + h)
+    base = cv2.GaussianBlur(rng.integers(0, 256, (h + 8, w + 8), dtype=np.uint8), (0, 0), 1.5)
+    a = np.ascontiguousarray(base[4:4 + h, 4:4 + w])
+    b = np.ascontiguousarray(base[3:3 + h, 2:2 + w])  # shifted by (2, 1)
+    xs, ys = np.meshgrid(np.arange(-4, w + 4, 3, dtype=np.float32), np.arange(-4, h + 4, 3, dtype=np.float32))
+    pts = np.stack([xs.ravel() + 0.37, ys.ravel() + 0.61], axis=1).astype(np.float32)
+    results = {}
+    for builder in ("tiles", "levels", "coop"):
+        monkeypatch.setenv("LVKB200_PYRAMID", builder)
+        results[builder] = gpu_stream.lk_track(a, b, pts)
+    monkeypatch.delenv("LVKB200_PYRAMID")
+    for other in ("levels", "coop"):
+        assert np.array_equal(results["tiles"][1], results[other][1]), other
+        assert np.array_equal(results["tiles"][0], results[other][0]), other
+    assert results["tiles"][1].sum() > 0.3 * len(pts)
+
+
 def test_lk_repeated_calls_square_epsilon(gpu_stream, oracle):
     """Upstream OpenCV squares TermCriteria::epsilon IN PLACE on every calc() of one SparsePyrLKOpticalFlow object;
     the reference reuses one m_OpticalTracker for all frames (FrameTracker.cpp:41-48), so its n-th frame iterates
