@@ -148,9 +148,11 @@ lvkb200_status lvkb200_stream_stable_region(const lvkb200_stream* s, int frame_w
  * The input frame is copied into the stream's device ring before the call returns (the caller keeps its
  * buffer; the reference moves it into m_FrameQueue).  `out` may alias `frame` (OBS calls
  * apply(std::move(frame), frame), VSFilter.cpp:358).  When res->has_output == 0 `out` is untouched.
- * With out_space == HOST the call returns after the output has landed in `out`; with DEVICE it returns
- * once all work is enqueued on the stream's CUDA stream (call lvkb200_stream_sync, the equivalent of
- * Stopwatch::sync_gpu / cv::ocl::finish, Timing/Stopwatch.cpp:127-131, before reading it). */
+ * With out_space == HOST the call returns after the output has landed in `out`; with DEVICE the output is
+ * produced by stream-ordered work that may still be pending (the library can hold the remap back until the next
+ * submit, to run it beside that frame's tracking kernels): keep `out` valid and untouched and call
+ * lvkb200_stream_sync (the equivalent of Stopwatch::sync_gpu / cv::ocl::finish, Timing/Stopwatch.cpp:127-131)
+ * before reading it.  lvkb200_stream_sync and _event_record cover every output requested so far. */
 lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
                                      lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
                                      void* out, size_t out_pitch, lvkb200_memspace out_space, lvkb200_result* res);
@@ -166,7 +168,9 @@ lvkb200_status lvkb200_stream_sync(lvkb200_stream* s);
  *                                         copy-out stream after the call returns; *ticket (0 when there is no
  *                                         output) identifies it.
  *   lvkb200_stream_wait_output(ticket)    returns once that output has landed in the caller's buffer.
- * Results are identical to lvkb200_stream_submit; only the copies overlap. */
+ * Results are identical to lvkb200_stream_submit; only the copies overlap.  For full overlap keep TWO outputs in
+ * flight (three output buffers): output t's remap is launched inside submit t+1 and its download overlaps frame
+ * t+2, so collect it after submit t+2 (waiting earlier is correct, it only gives up part of the overlap). */
 lvkb200_status lvkb200_stream_prefetch(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height);
 lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
                                            lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
