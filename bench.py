@@ -38,14 +38,31 @@ WORKLOAD = ("1080p60 synthetic hand-shake sequence, OBS Homography preset (480x2
             "-> homography RANSAC -> path smoother -> FSR-EASU remap), 1 stream per GPU")
 
 
-def _select_workload(res):
+PRESET, PRESET_NAME = "H", "OBS Homography"
+
+
+def _select_workload(res, preset="H"):
     """BASELINE.json configs[1] (1080p60, the default and the configuration the metric is quoted on) or configs[2]
-    (4K60, `--resolution 4k`)."""
-    global RES, WIDTH, HEIGHT, METRIC, WORKLOAD
+    (4K60, `--resolution 4k`); tracking preset H (OBS "Homography", default) or D (library defaults: 256x256
+    detection, local motions -> LSCG mesh), the two presets SURVEY 8(d) asks for."""
+    global RES, WIDTH, HEIGHT, METRIC, WORKLOAD, PRESET, PRESET_NAME
     if res == "4k":
         RES, WIDTH, HEIGHT = "4k", 3840, 2160
         METRIC = "stabilized_frames_per_second_4k"
         WORKLOAD = WORKLOAD.replace("1080p60", "4K60")
+    if preset == "D":
+        PRESET, PRESET_NAME = "D", "library defaults"
+        WORKLOAD = WORKLOAD.replace("OBS Homography preset (480x270 detection, FAST grid -> pyramidal LK -> homography RANSAC",
+                                    "library-default settings (256x256 detection, FAST grid -> pyramidal LK -> local-motion "
+                                    "LSCG mesh")
+
+
+def _gpu_settings(L):
+    return L.StabilizationFilterSettings.obs_homography_preset() if PRESET == "H" else L.StabilizationFilterSettings()
+
+
+def _oracle_settings(O):
+    return O.StabilizationSettings.obs_homography_preset() if PRESET == "H" else O.StabilizationSettings()
 
 
 def _peaks():
@@ -134,7 +151,7 @@ def run_reference(args):
     cv2.setNumThreads(cores)
     clip = Clip(RES, "shake", frames=args.warmup + args.steps, seed=42)
     frames = [clip[i] for i in range(len(clip))]
-    flt = O.StabilizationFilter(O.StabilizationSettings.obs_homography_preset(), remap_threads=cores)
+    flt = O.StabilizationFilter(_oracle_settings(O), remap_threads=cores)
     for i in range(args.warmup):
         flt.apply(frames[i], O.BGR, i)
     t0 = time.perf_counter()
@@ -146,7 +163,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": "OBS Homography"},
+        "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": PRESET_NAME},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} frames after {args.warmup} warm-up frames, single stream, "
                                    f"cv2 {cv2.__version__} (reference pins 4.8.0) + scalar C EASU on {cores} threads"},
@@ -162,7 +179,7 @@ def cpu_baseline_sample(frames, warm=12, count=60):
     O.build_native()
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
-    flt = O.StabilizationFilter(O.StabilizationSettings.obs_homography_preset(), remap_threads=cores)
+    flt = O.StabilizationFilter(_oracle_settings(O), remap_threads=cores)
     count = min(count, len(frames) - warm)
     for i in range(warm):
         flt.apply(frames[i], O.BGR, i)
@@ -183,9 +200,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolution", default="1080p", choices=["1080p", "4k"])
+    ap.add_argument("--preset", default="H", choices=["H", "D"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    _select_workload(args.resolution)
+    _select_workload(args.resolution, args.preset)
 
     if args.impl == "reference":
         run_reference(args)
@@ -214,7 +232,7 @@ def main():
     from tools.scaling import stream_seed
     clip = Clip(RES, "shake", frames=n_frames, seed=stream_seed(rank))
     host_frames = [clip[i] for i in range(n_frames)]
-    settings = L.StabilizationFilterSettings.obs_homography_preset()
+    settings = _gpu_settings(L)
 
     def barrier():
         if world > 1:
@@ -324,7 +342,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": "OBS Homography",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "preset": PRESET_NAME,
                        "streams_per_gpu": 1,
                        "l2": f"{n_frames} distinct frames ({n_frames * WIDTH * HEIGHT * 3 / 1e9:.2f} GB per GPU) "
                              f"streamed once each: inputs larger than L2, no flush needed",

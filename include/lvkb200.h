@@ -178,6 +178,35 @@ lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame,
                                            lvkb200_result* res, uint64_t* ticket);
 lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket);
 
+/* ---- lvk::DeblockingFilter --------------------------------------------------------------------- */
+
+/* lvk::DeblockingFilterSettings — Filters/DeblockingFilter.hpp:26-32 (same names and defaults). */
+typedef struct lvkb200_deblock_settings
+{
+    uint32_t detection_levels; /* 3   (> 0) */
+    uint32_t block_size;       /* 16  (> 0) */
+    uint32_t filter_size;      /* 5   (odd, >= 3) */
+    float filter_scaling;      /* 4.0 (> 1): the smooth frame is filtered at 1/filter_scaling resolution */
+} lvkb200_deblock_settings;
+void lvkb200_deblock_settings_default(lvkb200_deblock_settings* s);
+
+/* DeblockingFilter::filter — Filters/DeblockingFilter.cpp:48-118: adaptively blends the largest whole-macroblock
+ * region of the frame with a median-smoothed copy of itself; pixels outside that region pass through.  The
+ * reference works in place and moves the input to the output; here `out` may be `frame` (in place) or a separate
+ * buffer.  Settings are checked like DeblockingFilter::configure (:36-45); this build covers integer
+ * filter_scaling dividing block_size, block_size in {4, 8, 16, 32}, filter_size 3/5/7 (the reference's callers
+ * only ever change detection_levels: ADBFilter.cpp:96-97) and returns LVKB200_ERR_INVALID otherwise.
+ * Host buffers are staged through the stream's device scratch; the call returns when a host `out` is filled. */
+lvkb200_status lvkb200_deblock(lvkb200_stream* s, const lvkb200_deblock_settings* settings, const void* frame,
+                               size_t pitch, int width, int height, lvkb200_format format,
+                               lvkb200_memspace frame_space, void* out, size_t out_pitch, lvkb200_memspace out_space);
+
+/* CompositeFilter{DeblockingFilter, StabilizationFilter} (Filters/CompositeFilter.cpp:58-88, BASELINE config 5)
+ * without leaving the device: every frame submitted from now on is deblocked inside the stream's frame ring before
+ * it is tracked and queued.  NULL switches the stage off.  Identical to calling lvkb200_deblock on the frame and
+ * submitting the result. */
+lvkb200_status lvkb200_stream_set_deblocking(lvkb200_stream* s, const lvkb200_deblock_settings* settings);
+
 /* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
  * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for
  * the later one.  The per-stage analogue of Stopwatch (Timing/Stopwatch.cpp:42-64) for the bench harness. */

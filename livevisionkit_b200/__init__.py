@@ -19,8 +19,8 @@ import numpy as np
 from . import _capi
 from ._capi import (BGR, BGRA, GRAY, RGB, RGBA, UNKNOWN, YUV, LvkB200Error, STAGE_NAMES)  # noqa: F401
 
-__all__ = ["StabilizationFilterSettings", "StabilizationFilter", "VideoFrame", "Stream", "BGR", "RGB", "YUV",
-           "LvkB200Error", "device_count"]
+__all__ = ["StabilizationFilterSettings", "StabilizationFilter", "DeblockingFilterSettings", "DeblockingFilter",
+           "CompositeFilter", "VideoFrame", "Stream", "BGR", "RGB", "YUV", "LvkB200Error", "device_count"]
 
 
 def device_count() -> int:
@@ -386,6 +386,100 @@ class Stream:
                                                              offsets.ctypes.data_as(C.POINTER(C.c_float)),
                                                              mask.ctypes.data_as(C.POINTER(C.c_uint8))))
         return state, offsets, mask
+
+    # ---- lvk::DeblockingFilter
+    def deblock(self, frame, settings: "DeblockingFilterSettings | None" = None, fmt: int = BGR, out=None):
+        """DeblockingFilter::filter on one frame (host or device); `out` defaults to a new buffer, may be `frame`."""
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        if ch != 3:
+            raise ValueError("deblocking takes packed 8UC3 frames")
+        if out is None:
+            out = np.empty_like(frame) if isinstance(frame, np.ndarray) else frame.new_empty(frame.shape)
+        optr, opitch, oh, ow, och, ospace = _buffer_info(out)
+        if (oh, ow, och) != (h, w, ch):
+            raise ValueError("output buffer must match the input frame")
+        c = (settings or DeblockingFilterSettings()).to_c()
+        _capi.check(self._lib.lvkb200_deblock(self._h, C.byref(c), ptr, pitch, w, h, fmt, space, optr, opitch, ospace))
+        return out
+
+    def set_deblocking(self, settings: "DeblockingFilterSettings | None"):
+        """Chains a DeblockingFilter in front of the stabilizer, on the device (None switches it off)."""
+        if settings is None:
+            _capi.check(self._lib.lvkb200_stream_set_deblocking(self._h, None))
+        else:
+            c = settings.to_c()
+            _capi.check(self._lib.lvkb200_stream_set_deblocking(self._h, C.byref(c)))
+
+
+@dataclass
+class DeblockingFilterSettings:
+    """lvk::DeblockingFilterSettings (Filters/DeblockingFilter.hpp:26-32)."""
+    detection_levels: int = 3
+    block_size: int = 16
+    filter_size: int = 5
+    filter_scaling: float = 4.0
+
+    def to_c(self) -> _capi.DeblockSettings:
+        return _capi.DeblockSettings(int(self.detection_levels), int(self.block_size), int(self.filter_size),
+                                     float(self.filter_scaling))
+
+
+class DeblockingFilter:
+    """lvk::DeblockingFilter behind lvk::VideoFilter::apply (Filters/DeblockingFilter.hpp:34-59)."""
+
+    def __init__(self, settings: DeblockingFilterSettings | None = None, device: int = 0, stream: "Stream | None" = None):
+        self._settings = settings or DeblockingFilterSettings()
+        self.stream = stream or Stream(None, device)
+        self.alias = "Deblocking Filter"
+        self.configure(self._settings)
+
+    def settings(self) -> DeblockingFilterSettings:
+        return self._settings
+
+    def configure(self, settings: DeblockingFilterSettings):
+        # DeblockingFilter::configure preconditions (DeblockingFilter.cpp:38-42)
+        if not (settings.block_size > 0 and settings.filter_size >= 3 and settings.filter_size % 2 == 1
+                and settings.detection_levels > 0 and settings.filter_scaling > 1.0):
+            raise LvkB200Error(_capi.ERR_INVALID, "DeblockingFilter::configure precondition")
+        self._settings = settings
+
+    def filter_region(self, width: int, height: int):
+        """DeblockingFilter::filter_region (:136-139) for a frame of this size: (x, y, w, h)."""
+        bs = int(self._settings.block_size)
+        return 0, 0, (width // bs) * bs, (height // bs) * bs
+
+    def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
+        out = self.stream.deblock(frame.data, self._settings, frame.format, output)
+        return VideoFrame(out, frame.timestamp, frame.format)
+
+
+class CompositeFilter:
+    """lvk::CompositeFilter (Filters/CompositeFilter.cpp:58-88): applies its filters in order, each one's output
+    being the next one's input.  The chain BASELINE config 5 names — DeblockingFilter -> StabilizationFilter — runs
+    as ONE device pipeline: the deblocking stage is attached to the stabilizer's stream and works on the frame inside
+    its device ring (no extra transfer, no intermediate buffer).  Other chains run filter by filter."""
+
+    def __init__(self, filters):
+        self.filters = list(filters)
+        self.alias = "Composite Filter"
+        self._fused = (len(self.filters) == 2 and isinstance(self.filters[0], DeblockingFilter)
+                       and isinstance(self.filters[1], StabilizationFilter))
+        if self._fused:
+            self.filters[1].stream.set_deblocking(self.filters[0].settings())
+
+    def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
+        if self._fused:
+            return self.filters[1].apply(frame, output)
+        for i, f in enumerate(self.filters):
+            frame = f.apply(frame, output if i == len(self.filters) - 1 else None)
+            if frame.empty():
+                return frame
+        return frame
+
+    def stream_frames(self, frames, callback, outputs=None) -> int:
+        if not self._fused:
+            raise NotImplementedError("pipelined streaming is provided for the fused deblocking -> stabilization chain")
+        return self.filters[1].stream_frames(frames, callback, outputs)
 
 
 class StabilizationFilter:

@@ -46,6 +46,12 @@ class Result(C.Structure):
     ]
 
 
+class DeblockSettings(C.Structure):
+    """lvkb200_deblock_settings — lvk::DeblockingFilterSettings."""
+    _fields_ = [("detection_levels", C.c_uint32), ("block_size", C.c_uint32), ("filter_size", C.c_uint32),
+                ("filter_scaling", C.c_float)]
+
+
 class KeyPoint(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("response", C.c_float), ("class_id", C.c_int32)]
 
@@ -92,6 +98,9 @@ SYMBOLS = {
     "lvkb200_find_homography": (C.c_int, [_vp, _fp, _fp, _i, C.c_float, _dp, _u8p]),
     "lvkb200_estimate_affine_partial": (C.c_int, [_vp, _fp, _fp, _i, C.c_float, _dp, _u8p]),
     "lvkb200_estimate_local_motions": (C.c_int, [_vp, _fp, _fp, _i, _fp, _fp, _u8p]),
+    "lvkb200_deblock_settings_default": (None, [C.POINTER(DeblockSettings)]),
+    "lvkb200_deblock": (C.c_int, [_vp, C.POINTER(DeblockSettings), _vp, _sz, _i, _i, _i, _i, _vp, _sz, _i]),
+    "lvkb200_stream_set_deblocking": (C.c_int, [_vp, C.POINTER(DeblockSettings)]),
 }
 
 _lib = None

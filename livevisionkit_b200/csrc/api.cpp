@@ -546,4 +546,66 @@ lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream* s, const float* tr
     return LVKB200_OK;
 }
 
+// ---- lvk::DeblockingFilter ------------------------------------------------------------------------------------------
+
+void lvkb200_deblock_settings_default(lvkb200_deblock_settings* s)
+{
+    if (!s) return;
+    // DeblockingFilterSettings — Filters/DeblockingFilter.hpp:28-31
+    s->detection_levels = 3;
+    s->block_size = 16;
+    s->filter_size = 5;
+    s->filter_scaling = 4.0f;
+}
+
+lvkb200_status lvkb200_deblock(lvkb200_stream* s, const lvkb200_deblock_settings* settings, const void* frame,
+                               size_t pitch, int width, int height, lvkb200_format format,
+                               lvkb200_memspace frame_space, void* out, size_t out_pitch, lvkb200_memspace out_space)
+{
+    LVKB_REQUIRE(s != nullptr && settings != nullptr && frame != nullptr && out != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0);  // LVK_ASSERT(!input.empty()) — DeblockingFilter.cpp:50
+    LVKB_REQUIRE(format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    LVKB_TRY(deblock_validate(*settings));
+    const size_t row = static_cast<size_t>(width) * 3;
+    LVKB_REQUIRE(pitch >= row && out_pitch >= row);
+    const uint8_t* din = nullptr;
+    size_t din_pitch = 0;
+    LVKB_TRY(s->stage_frame_in(frame, pitch, width, height, 3, frame_space, &din, &din_pitch));
+    // the kernels work in place on 4-byte aligned rows: straight in the caller's device buffer when it qualifies,
+    // otherwise in the stream's staging buffer
+    const bool direct = out_space == LVKB200_MEM_DEVICE && (out_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    uint8_t* work = static_cast<uint8_t*>(out);
+    size_t work_pitch = out_pitch;
+    if (!direct)
+    {
+        work_pitch = (row + 15) / 16 * 16;
+        LVKB_CUDA(s->stage_out.ensure(work_pitch * height));
+        work = s->stage_out.as<uint8_t>();
+    }
+    if (work != din)
+        LVKB_CUDA(cudaMemcpy2DAsync(work, work_pitch, din, din_pitch, row, height, cudaMemcpyDeviceToDevice, s->cs));
+    LVKB_TRY(s->deblock_stage.prepare(width, height, *settings, s->cs));
+    LVKB_TRY(s->deblock_stage.launch(s->cs, work, work_pitch, format));
+    if (!direct)
+        LVKB_CUDA(cudaMemcpy2DAsync(out, out_pitch, work, work_pitch, row, height,
+                                    out_space == LVKB200_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->cs));
+    if (out_space == LVKB200_MEM_HOST || frame_space == LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_set_deblocking(lvkb200_stream* s, const lvkb200_deblock_settings* settings)
+{
+    LVKB_REQUIRE(s != nullptr);
+    if (!settings)
+    {
+        s->deblock_enabled = false;
+        return LVKB200_OK;
+    }
+    LVKB_TRY(deblock_validate(*settings));
+    s->deblock_settings = *settings;
+    s->deblock_enabled = true;
+    return LVKB200_OK;
+}
+
 }  // extern "C"

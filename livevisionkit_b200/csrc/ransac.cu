@@ -579,7 +579,25 @@ __global__ void __launch_bounds__(RT)
     copy16(out.dev + out.off_result, out.host + out.off_result, (int)sizeof(RansacResult));
 }
 
+// Local-motion mode has no estimator kernel: one small CTA delivers the LK results (same 16-byte posted writes).
+// Per-CTA result writes from the 200-600 LK CTAs themselves cost ~0.4 us EACH on the PCIe write path (LK: 21 -> 217 us).
+__global__ void __launch_bounds__(RT) k_track_out_copy(const TrackParams* __restrict__ prm, TrackOutCopy out)
+{
+    const int tracked = prm->n;
+    copy16(out.dev, out.host, tracked * (int)sizeof(float2));
+    copy16(out.dev + out.off_status, out.host + out.off_status, tracked);
+}
+
 }  // namespace
+
+lvkb200_status track_out_copy(cudaStream_t cs, const TrackParams* d_params, const TrackOutCopy& out)
+{
+    LVKB_REQUIRE(out.dev != nullptr && out.host != nullptr);
+    k_track_out_copy<<<1, RT, 0, cs>>>(d_params, out);
+    count_launches(1);
+    LVKB_CUDA(cudaGetLastError());
+    return LVKB200_OK;
+}
 
 lvkb200_status compact_swap_erase(cudaStream_t cs, const float2* d_a, const float2* d_b, const uint8_t* d_keep,
                                   const TrackParams* d_params, float2* d_a_out, float2* d_b_out, int* d_perm,

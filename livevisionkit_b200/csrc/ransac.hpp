@@ -34,6 +34,10 @@ struct TrackOutCopy
     uint32_t off_status = 0, off_mask = 0, off_result = 0;
 };
 
+// Copies the LK part of the result block (d_params->n matches + status) to the host mirror: local-motion mode, where
+// no estimator kernel follows LK.
+lvkb200_status track_out_copy(cudaStream_t cs, const TrackParams* d_params, const TrackOutCopy& out);
+
 // d_* are device memory (the count too).  d_models: HYP*9 floats, d_scores: HYP floats.  With out.host set, the last
 // kernel also copies the used part of the result block (d_params->n matches + status, mask, model) to the host mirror.
 lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,

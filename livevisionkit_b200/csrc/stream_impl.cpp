@@ -296,12 +296,6 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
     io.prm_copy = d_params.as<TrackParams>();
     io.next = d_pts_next();
     io.status = d_status();
-    if (!global)
-    {
-        // no estimator kernel follows (local motions are solved on the host): LK delivers its own results
-        io.next_host = reinterpret_cast<float2*>(hout);
-        io.status_host = hout + off_status;
-    }
     const bool inline_points = point_capacity <= LK_INLINE_POINTS;
     if (!inline_points)
     {
@@ -312,6 +306,15 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
     }
     if (with_events) stage_begin(ST_LK);
     LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], (n + 3) / 4 * 4, io, inline_points ? &lk_pack : nullptr));
+    if (!global)
+    {
+        // no estimator kernel follows (local motions are solved on the host): one small CTA delivers the LK results
+        TrackOutCopy out{};
+        out.dev = d_track_out.as<uint8_t>();
+        out.host = hout;
+        out.off_status = static_cast<uint32_t>(off_status);
+        LVKB_TRY(track_out_copy(cs, d_params.as<TrackParams>(), out));
+    }
     if (with_events) stage_end(ST_LK);
     return LVKB200_OK;
 }
@@ -839,6 +842,13 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
                                     frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
     }
     q.w = width; q.h = height; q.format = format; q.timestamp = timestamp;
+    if (deblock_enabled)
+    {
+        // CompositeFilter{Deblocking, Stabilization} (CompositeFilter.cpp:58-88): the first filter's output is the
+        // second one's input — here the frame never leaves its ring slot
+        LVKB_TRY(deblock.prepare(width, height, deblock_settings, cs));
+        LVKB_TRY(deblock.launch(cs, q.buf.as<uint8_t>(), q.pitch, format));
+    }
     // The caller keeps ownership of its buffer: host memory must have been consumed before we return.
     struct InputGuard
     {
@@ -997,6 +1007,7 @@ void lvkb200_stream::release()
     }
     stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
+    deblock.release(); deblock_stage.release();
     destroy_graphs();
     d_pts_prev.release(); d_src.release(); d_dst.release(); d_models.release(); d_scores.release();
     d_track_out.release(); h_track_out.release(); d_params.release(); h_params.release();

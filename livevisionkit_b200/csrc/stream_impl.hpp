@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.hpp"
+#include "deblock.hpp"
 #include "fast.hpp"
 #include "host_logic.hpp"
 #include "host_mesh.hpp"
@@ -25,6 +26,11 @@ struct lvkb200_stream
     lvkb200::DeviceBuffer stage_in, stage_out, mesh_dev;
     lvkb200::PinnedBuffer mesh_pinned;
     cudaEvent_t user_events[LVKB200_EVENT_SLOTS] = {};
+
+    // ---- DeblockingFilter chained in front of the stabilizer (lvkb200_stream_set_deblocking) / stand-alone
+    lvkb200::DeblockPlan deblock, deblock_stage;
+    bool deblock_enabled = false;
+    lvkb200_deblock_settings deblock_settings{};
 
     // ---- device-side stages
     lvkb200::IngestPlan ingest;
