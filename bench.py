@@ -57,6 +57,34 @@ def _select_workload(res, preset="H"):
                                     "LSCG mesh")
 
 
+DEBLOCK = False
+
+
+def _make_filter(L, settings, device):
+    """The timed filter: lvk::StabilizationFilter, or with --deblock CompositeFilter{DeblockingFilter,
+    StabilizationFilter} (BASELINE configs[4]) fused on the device."""
+    flt = L.StabilizationFilter(settings, device=device)
+    if DEBLOCK:
+        flt.stream.set_deblocking(L.DeblockingFilterSettings())
+    return flt
+
+
+class _OracleChain:
+    """The same chain on the CPU for the baseline legs."""
+
+    def __init__(self, O, remap_threads):
+        self.flt = O.StabilizationFilter(_oracle_settings(O), remap_threads=remap_threads)
+        self.deblock = None
+        if DEBLOCK:
+            from oracle import deblock_oracle as D
+            self.deblock = D.DeblockingFilter()
+
+    def apply(self, frame, fmt, ts):
+        if self.deblock is not None:
+            frame = self.deblock.apply(frame, fmt)
+        return self.flt.apply(frame, fmt, ts)
+
+
 def _gpu_settings(L):
     return L.StabilizationFilterSettings.obs_homography_preset() if PRESET == "H" else L.StabilizationFilterSettings()
 
@@ -151,7 +179,7 @@ def run_reference(args):
     cv2.setNumThreads(cores)
     clip = Clip(RES, "shake", frames=args.warmup + args.steps, seed=42)
     frames = [clip[i] for i in range(len(clip))]
-    flt = O.StabilizationFilter(_oracle_settings(O), remap_threads=cores)
+    flt = _OracleChain(O, cores)
     for i in range(args.warmup):
         flt.apply(frames[i], O.BGR, i)
     t0 = time.perf_counter()
@@ -179,7 +207,7 @@ def cpu_baseline_sample(frames, warm=12, count=60):
     O.build_native()
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
-    flt = O.StabilizationFilter(_oracle_settings(O), remap_threads=cores)
+    flt = _OracleChain(O, cores)
     count = min(count, len(frames) - warm)
     for i in range(warm):
         flt.apply(frames[i], O.BGR, i)
@@ -201,9 +229,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolution", default="1080p", choices=["1080p", "4k"])
     ap.add_argument("--preset", default="H", choices=["H", "D"])
+    ap.add_argument("--deblock", action="store_true",
+                    help="BASELINE configs[4]: DeblockingFilter -> StabilizationFilter chained (per stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     _select_workload(args.resolution, args.preset)
+    if args.deblock:
+        global DEBLOCK, WORKLOAD
+        DEBLOCK = True
+        WORKLOAD = "DeblockingFilter (defaults) -> " + WORKLOAD
 
     if args.impl == "reference":
         run_reference(args)
@@ -243,7 +277,7 @@ def main():
     dev_frames = [torch.from_numpy(f).to(dev) for f in host_frames]
     out_ring = [torch.empty_like(dev_frames[0]) for _ in range(16)]
     torch.cuda.synchronize()
-    flt = L.StabilizationFilter(settings, device=local)
+    flt = _make_filter(L, settings, local)
     s = flt.stream
     for i in range(args.warmup):
         s.submit(dev_frames[i], out_ring[i % 16], L.BGR, i)
@@ -269,7 +303,7 @@ def main():
     totals, counts = s.stage_totals_us(reset=True)  # default mode: only the remap kernel is event-timed
     last_dev_out = out_ring[(n_frames - 1) % 16].cpu().numpy().copy()
     # untimed extra pass with per-stage CUDA events (eager launches instead of the tracking graph) for stage_us
-    prof = L.StabilizationFilter(settings, device=local)
+    prof = _make_filter(L, settings, local)
     prof.stream.set_profiling(True)
     n_prof = min(n_frames, 90)
     for i in range(n_prof):
@@ -284,7 +318,7 @@ def main():
     # ======== pass 2: end to end through the public API with pinned host buffers ========
     pinned_in = [torch.from_numpy(f).pin_memory() for f in host_frames]
     pinned_out = [torch.empty_like(pinned_in[0]).pin_memory() for _ in range(4)]
-    flt2 = L.StabilizationFilter(settings, device=local)
+    flt2 = _make_filter(L, settings, local)
     for i in range(args.warmup):
         flt2.apply(L.VideoFrame(pinned_in[i], i, L.BGR), output=pinned_out[i % 4])
     barrier()
@@ -302,7 +336,7 @@ def main():
     # ======== pass 2b: end to end through the pipelined public API (VideoFilter::stream analogue) ========
     # upload of frame t+1 and download of output t-1 overlap the processing of frame t; still one H2D of the input and
     # one D2H of the result per step, all inside the timed region.
-    flt3 = L.StabilizationFilter(settings, device=local)
+    flt3 = _make_filter(L, settings, local)
     warm = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup)]
     timed = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup, n_frames)]
     sink = []

@@ -45,8 +45,8 @@ struct LkIo
 };
 
 // The frame's parameters and points as ONE kernel argument (see k_lk_track): 51 x 51 suppression-grid cells, the
-// largest feature capacity of the presets the reference ships, rounded up to a multiple of four.
-constexpr int LK_INLINE_POINTS = 2604;
+// largest feature capacity of the presets the reference ships, rounded up to the stream's allocation granule (64).
+constexpr int LK_INLINE_POINTS = 2624;
 struct LkPack
 {
     TrackParams prm;

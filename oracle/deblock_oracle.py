@@ -95,7 +95,10 @@ def area_integer(img: np.ndarray, sx: int, sy: int) -> np.ndarray:
     h, w = img.shape[:2]
     c = 1 if img.ndim == 2 else img.shape[2]
     v = img.reshape(h // sy, sy, w // sx, sx, c).astype(np.int64).sum(axis=(1, 3))
-    out = np.rint(v.astype(np.float32) * np.float32(1.0 / (sx * sy))).astype(np.uint8)
+    if sx == 2 and sy == 2:
+        out = ((v + 2) >> 2).astype(np.uint8)  # OpenCV's 2x2 special case rounds half up
+    else:
+        out = np.rint(v.astype(np.float32) * np.float32(1.0 / (sx * sy))).astype(np.uint8)
     return out[..., 0] if img.ndim == 2 else out
 
 
