@@ -25,8 +25,6 @@ namespace
 
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 8;
-constexpr int SRC_W = 48;  // staged source tile capacity (pixels)
-constexpr int SRC_H = 20;
 
 struct Transform
 {
@@ -165,12 +163,6 @@ __device__ __forceinline__ float4 load_texel(const uint8_t* __restrict__ p)
     return t;
 }
 
-struct SmemTap
-{
-    const float4* base;  // &tile[(sy - y0) * SRC_W + (sx - x0)]
-    __device__ __forceinline__ float4 operator()(int dx, int dy) const { return base[dy * SRC_W + dx]; }
-};
-
 template <bool YUV>
 struct GlobalTap
 {
@@ -182,77 +174,285 @@ struct GlobalTap
     }
 };
 
-// MODE 0: homography (FSR.cl:407-452).  MODE 1: mesh offsets, bilinear upsample fused (WarpMesh.cpp:190-191 + FSR.cl:362-403).
-template <int MODE, bool YUV>
-__global__ void __launch_bounds__(TILE_W* TILE_H)
-    k_easu_remap(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch, int W,
-                 int H, Transform T, const float2* __restrict__ mesh, int mesh_cols, int mesh_rows, double mesh_sx,
-                 double mesh_sy, uchar3 bg)
+template <bool YUV>
+__device__ __noinline__ uchar3 easu_global(const uint8_t* __restrict__ base, size_t pitch, float ppx, float ppy)
 {
-    __shared__ float4 tile[SRC_H * SRC_W];
-    __shared__ int bbox[4];  // minx, miny, maxx, maxy over the EASU pixels of this tile
+    GlobalTap<YUV> tap{base, pitch};
+    return easu(tap, ppx, ppy);
+}
+
+// ---- packed float32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE-RN float32 operations per issue slot) --------
+// Lane .x carries pixel A of the thread's pair, lane .y pixel B; each lane is exactly the scalar operation.
+using f2 = float2;
+__device__ __forceinline__ f2 pk(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 pk1(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+
+// FSR.cl:131-176, the part that depends only on the SOURCE pixel C and its cross A(up) B(left) D(right) E(down):
+// {dirX, dirY, sat(|dirX|*rcp(max(|D-C|,|C-B|)))^2, sat(|dirY|*rcp(max(|E-C|,|C-A|)))^2}.  Evaluated once per source
+// pixel of the staged tile instead of once per (destination pixel, corner): same operations, same results.
+__device__ __forceinline__ float4 easu_direction_terms(float lA, float lB, float lC, float lD, float lE)
+{
+    const f2 de = pk(lD, lE), cc = pk1(lC), ba = pk(lB, lA);
+    const f2 dc_ec = add2(de, neg2(cc));  // (D-C, E-C)
+    const f2 cb_ca = add2(cc, neg2(ba));  // (C-B, C-A)
+    const f2 dir = add2(de, neg2(ba));    // (D-B, E-A)
+    float lenX = aprx_lo_rcp(fmaxf(fabsf(dc_ec.x), fabsf(cb_ca.x)));
+    float lenY = aprx_lo_rcp(fmaxf(fabsf(dc_ec.y), fabsf(cb_ca.y)));
+    f2 len = pk(sat01(fabsf(dir.x) * lenX), sat01(fabsf(dir.y) * lenY));
+    len = mul2(len, len);
+    return make_float4(dir.x, dir.y, len.x, len.y);
+}
+
+// FSR.cl:98-126 for the two pixels of a pair at once.  t1 = offy*diry, t2 = offy*dirx (shared by the taps of one row).
+__device__ __forceinline__ void easu_tap2(float (&aA)[3], float (&aB)[3], f2& aW, f2 offx, f2 t1, f2 t2, f2 dirx,
+                                          f2 ndiry, f2 lenx, f2 leny, f2 lob, f2 clp, const float4& cA,
+                                          const float4& cB)
+{
+    f2 vx = fma2(offx, dirx, t1);
+    f2 vy = fma2(offx, ndiry, t2);
+    vx = mul2(vx, lenx);
+    vy = mul2(vy, leny);
+    f2 d2 = fma2(vx, vx, mul2(vy, vy));
+    d2.x = fminf(d2.x, clp.x);
+    d2.y = fminf(d2.y, clp.y);
+    f2 wA = fma2(lob, d2, pk1(-1.0f));
+    f2 wB = fma2(pk1(2.0f / 5.0f), d2, pk1(-1.0f));
+    wA = mul2(wA, wA);
+    wB = fma2(pk1(25.0f / 16.0f), mul2(wB, wB), pk1(-(25.0f / 16.0f - 1.0f)));
+    const f2 w = mul2(wB, wA);
+    aA[0] = __fmaf_rn(cA.x, w.x, aA[0]);
+    aA[1] = __fmaf_rn(cA.y, w.x, aA[1]);
+    aA[2] = __fmaf_rn(cA.z, w.x, aA[2]);
+    aB[0] = __fmaf_rn(cB.x, w.y, aB[0]);
+    aB[1] = __fmaf_rn(cB.y, w.y, aB[1]);
+    aB[2] = __fmaf_rn(cB.z, w.y, aB[2]);
+    aW = add2(aW, w);
+}
+
+__device__ __forceinline__ uchar3 easu_resolve(const float (&a)[3], float aW, const float4& f, const float4& g,
+                                               const float4& j, const float4& k)
+{
+    const float mi0 = fminf(f.x, fminf(g.x, fminf(j.x, k.x)));
+    const float mi1 = fminf(f.y, fminf(g.y, fminf(j.y, k.y)));
+    const float mi2 = fminf(f.z, fminf(g.z, fminf(j.z, k.z)));
+    const float ma0 = fmaxf(f.x, fmaxf(g.x, fmaxf(j.x, k.x)));
+    const float ma1 = fmaxf(f.y, fmaxf(g.y, fmaxf(j.y, k.y)));
+    const float ma2 = fmaxf(f.z, fmaxf(g.z, fmaxf(j.z, k.z)));
+    const float rcpW = 1.0f / aW;  // native_recip
+    const float v0 = fminf(ma0, fmaxf(mi0, a[0] * rcpW));
+    const float v1 = fminf(ma1, fmaxf(mi1, a[1] * rcpW));
+    const float v2 = fminf(ma2, fmaxf(mi2, a[2] * rcpW));
+    uchar3 out;  // convert_uchar3: truncation
+    out.x = (unsigned char)__float2int_rz(v0 * 255.0f);
+    out.y = (unsigned char)__float2int_rz(v1 * 255.0f);
+    out.z = (unsigned char)__float2int_rz(v2 * 255.0f);
+    return out;
+}
+
+// FSR.cl:181-318 for a pixel pair, taps and per-source-pixel direction terms read from the staged tile.
+// tA / tB = &tile[f], dA / dB = &terms[f] of pixel A / B; pp* = fractional source position.
+template <int STRIDE>
+__device__ __forceinline__ void easu_pair(const float4* __restrict__ tA, const float4* __restrict__ tB,
+                                          const float4* __restrict__ dA, const float4* __restrict__ dB, f2 ppx, f2 ppy,
+                                          uchar3& outA, uchar3& outB)
+{
+    // ---- direction / length: bilinear blend of the four corners' terms (order f, g, j, k as FSR.cl:254-257)
+    const f2 omx = add2(pk1(1.0f), neg2(ppx)), omy = add2(pk1(1.0f), neg2(ppy));
+    const f2 w0 = mul2(omx, omy), w1 = mul2(ppx, omy), w2 = mul2(omx, ppy), w3 = mul2(ppx, ppy);
+    f2 dirx, diry, len;
+    {
+        float lenA = 0.0f, dxA = 0.0f, dyA = 0.0f, lenB = 0.0f, dxB = 0.0f, dyB = 0.0f;
+#define LVKB_ACC(OFF, WA, WB)                                                                                         \
+    {                                                                                                                 \
+        const float4 qa = dA[OFF], qb = dB[OFF];                                                                      \
+        dxA = __fmaf_rn(qa.x, WA, dxA); lenA = __fmaf_rn(qa.z, WA, lenA);                                             \
+        dyA = __fmaf_rn(qa.y, WA, dyA); lenA = __fmaf_rn(qa.w, WA, lenA);                                             \
+        dxB = __fmaf_rn(qb.x, WB, dxB); lenB = __fmaf_rn(qb.z, WB, lenB);                                             \
+        dyB = __fmaf_rn(qb.y, WB, dyB); lenB = __fmaf_rn(qb.w, WB, lenB);                                             \
+    }
+        LVKB_ACC(0, w0.x, w0.y)
+        LVKB_ACC(1, w1.x, w1.y)
+        LVKB_ACC(STRIDE, w2.x, w2.y)
+        LVKB_ACC(STRIDE + 1, w3.x, w3.y)
+#undef LVKB_ACC
+        dirx = pk(dxA, dxB); diry = pk(dyA, dyB); len = pk(lenA, lenB);
+    }
+
+    f2 dirR = fma2(dirx, dirx, mul2(diry, diry));
+    const bool zA = dirR.x < (1.0f / 32768.0f), zB = dirR.y < (1.0f / 32768.0f);
+    dirR = pk(zA ? 1.0f : aprx_lo_rsq(dirR.x), zB ? 1.0f : aprx_lo_rsq(dirR.y));
+    dirx = pk(zA ? 1.0f : dirx.x, zB ? 1.0f : dirx.y);
+    dirx = mul2(dirx, dirR);
+    diry = mul2(diry, dirR);
+
+    len = mul2(len, pk1(0.5f));
+    len = mul2(len, len);
+
+    f2 stretch = fma2(dirx, dirx, mul2(diry, diry));
+    stretch = mul2(stretch, pk(aprx_lo_rcp(fmaxf(fabsf(dirx.x), fabsf(diry.x))),
+                               aprx_lo_rcp(fmaxf(fabsf(dirx.y), fabsf(diry.y)))));
+    const f2 len2x = fma2(add2(stretch, pk1(-1.0f)), len, pk1(1.0f));
+    const f2 len2y = fma2(pk1(-0.5f), len, pk1(1.0f));
+    const f2 lob = fma2(pk1((1.0f / 4.0f - 0.04f) - 0.5f), len, pk1(0.5f));
+    const f2 clp = pk(aprx_lo_rcp(lob.x), aprx_lo_rcp(lob.y));
+    const f2 ndiry = neg2(diry);
+
+    // ---- the 12 taps, in the accumulation order of FSR.cl:291-302 (b c i j f e k l h g n o)
+    const f2 nppx = neg2(ppx), nppy = neg2(ppy);
+    const f2 oxm = add2(pk1(-1.0f), nppx), ox0 = add2(pk1(0.0f), nppx), ox1 = add2(pk1(1.0f), nppx),
+             ox2 = add2(pk1(2.0f), nppx);
+    const f2 oym = add2(pk1(-1.0f), nppy), oy0 = add2(pk1(0.0f), nppy), oy1 = add2(pk1(1.0f), nppy),
+             oy2 = add2(pk1(2.0f), nppy);
+    const f2 t1m = mul2(oym, diry), t10 = mul2(oy0, diry), t11 = mul2(oy1, diry), t12 = mul2(oy2, diry);
+    const f2 t2m = mul2(oym, dirx), t20 = mul2(oy0, dirx), t21 = mul2(oy1, dirx), t22 = mul2(oy2, dirx);
+
+    float aA[3] = {0.0f, 0.0f, 0.0f}, aB[3] = {0.0f, 0.0f, 0.0f};
+    f2 aW = pk1(0.0f);
+#define LVKB_TAP(DX, DY, OX, T1, T2)                                                                                  \
+    easu_tap2(aA, aB, aW, OX, T1, T2, dirx, ndiry, len2x, len2y, lob, clp, tA[(DY) * STRIDE + (DX)],                  \
+              tB[(DY) * STRIDE + (DX)]);
+    LVKB_TAP(0, -1, ox0, t1m, t2m)   // b
+    LVKB_TAP(1, -1, ox1, t1m, t2m)   // c
+    LVKB_TAP(-1, 1, oxm, t11, t21)   // i
+    LVKB_TAP(0, 1, ox0, t11, t21)    // j
+    LVKB_TAP(0, 0, ox0, t10, t20)    // f
+    LVKB_TAP(-1, 0, oxm, t10, t20)   // e
+    LVKB_TAP(1, 1, ox1, t11, t21)    // k
+    LVKB_TAP(2, 1, ox2, t11, t21)    // l
+    LVKB_TAP(2, 0, ox2, t10, t20)    // h
+    LVKB_TAP(1, 0, ox1, t10, t20)    // g
+    LVKB_TAP(0, 2, ox0, t12, t22)    // n
+    LVKB_TAP(1, 2, ox1, t12, t22)    // o
+#undef LVKB_TAP
+
+    outA = easu_resolve(aA, aW.x, tA[0], tA[1], tA[STRIDE], tA[STRIDE + 1]);
+    outB = easu_resolve(aB, aW.y, tB[0], tB[1], tB[STRIDE], tB[STRIDE + 1]);
+}
+
+// Destination tile of one CTA: 32 x 16 pixels, 256 threads, thread (tx, ty) owns the pair (x, y) and (x, y + 8).
+constexpr int PAIR_DY = 8;
+constexpr int CTA_H = 2 * PAIR_DY;
+constexpr int STG_W = 44;  // staged source tile capacity (pixels): 32 + 3 taps + warp slack, <= 2 * TILE_W
+constexpr int STG_H = 28;  // 16 + 3 taps + warp slack, <= 4 * TILE_H
+
+// Source position of destination pixel (x, y).  MODE 0: homography (FSR.cl:407-452).  MODE 1: mesh offsets with the
+// bilinear upsample of WarpMesh::apply fused in (WarpMesh.cpp:190-191 + FSR.cl:362-403).
+struct MeshArgs
+{
+    const float2* mesh;
+    int cols, rows;
+    double sx, sy;
+};
+
+template <int MODE>
+__device__ __forceinline__ void source_position(int x, int y, int W, int H, const Transform& T, const MeshArgs& M,
+                                                float& subx, float& suby)
+{
+    const float fx = (float)x, fy = (float)y;
+    float offx, offy;
+    if (MODE == 0)
+    {
+        const float dz = 1.0f / (T.r3x * fx + T.r3y * fy + T.r3z);
+        offx = (T.r1x * fx + T.r1y * fy + T.r1z) * dz - fx;
+        offy = (T.r2x * fx + T.r2y * fy + T.r2z) * dz - fy;
+    }
+    else
+    {
+        // cv::resize(mesh -> WxH, INTER_LINEAR) on CV_32FC2, then cv::multiply by (W, H).
+        float mx = (float)(((double)x + 0.5) * M.sx - 0.5);
+        float my = (float)(((double)y + 0.5) * M.sy - 0.5);
+        int cx = (int)floorf(mx), cy = (int)floorf(my);
+        mx -= (float)cx;
+        my -= (float)cy;
+        if (cx < 0) { mx = 0.0f; cx = 0; }
+        if (cx >= M.cols - 1) { mx = 0.0f; cx = M.cols - 1; }
+        if (cy < 0) { my = 0.0f; cy = 0; }
+        if (cy >= M.rows - 1) { my = 0.0f; cy = M.rows - 1; }
+        const int cx1 = min(cx + 1, M.cols - 1), cy1 = min(cy + 1, M.rows - 1);
+        const float2 m00 = __ldg(&M.mesh[cy * M.cols + cx]), m01 = __ldg(&M.mesh[cy * M.cols + cx1]);
+        const float2 m10 = __ldg(&M.mesh[cy1 * M.cols + cx]), m11 = __ldg(&M.mesh[cy1 * M.cols + cx1]);
+        const float ax0 = 1.0f - mx, ax1 = mx, ay0 = 1.0f - my, ay1 = my;
+        const float h0x = m00.x * ax0 + m01.x * ax1, h0y = m00.y * ax0 + m01.y * ax1;
+        const float h1x = m10.x * ax0 + m11.x * ax1, h1y = m10.y * ax0 + m11.y * ax1;
+        offx = (h0x * ay0 + h1x * ay1) * (float)W;
+        offy = (h0y * ay0 + h1y * ay1) * (float)H;
+    }
+    subx = fx + offx;
+    suby = fy + offy;
+}
+
+struct PixelClass
+{
+    int sx, sy;        // convert_int2_rtz(sub)
+    float ppx, ppy;    // sub - floor(sub)
+    bool border, in_src, do_easu;
+};
+
+__device__ __forceinline__ PixelClass classify(float subx, float suby, int W, int H, bool inside)
+{
+    PixelClass c;
+    c.sx = __float2int_rz(subx);
+    c.sy = __float2int_rz(suby);
+    c.ppx = subx - floorf(subx);
+    c.ppy = suby - floorf(suby);
+    // FSR.cl:387-399
+    c.border = (c.sx < 1) || (c.sy < 1) || (c.sx >= W - 4) || (c.sy >= H - 4);
+    c.in_src = (c.sx >= 0) && (c.sx < W) && (c.sy >= 0) && (c.sy < H);
+    c.do_easu = inside && !c.border;
+    return c;
+}
+
+template <int MODE, bool YUV>
+__global__ void __launch_bounds__(TILE_W* TILE_H, 2)
+    k_easu_remap(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch, int W,
+                 int H, Transform T, MeshArgs M, uchar3 bg)
+{
+    __shared__ float4 tile[STG_H * STG_W];   // {c0, c1, c2, luma} / 255 of the staged source pixels
+    __shared__ float4 terms[STG_H * STG_W];  // easu_direction_terms of the same pixels (interior only)
+    __shared__ int bbox[4];                  // minx, miny, maxx, maxy of f over the EASU pixels of this tile
 
     const int tx = threadIdx.x & (TILE_W - 1);
     const int ty = threadIdx.x / TILE_W;
     const int x = blockIdx.x * TILE_W + tx;
-    const int y = blockIdx.y * TILE_H + ty;
-    const bool inside = (x < W) && (y < H);
+    const int yA = blockIdx.y * CTA_H + ty, yB = yA + PAIR_DY;
+    const bool insideA = (x < W) && (yA < H), insideB = (x < W) && (yB < H);
 
     if (threadIdx.x == 0)
     {
         bbox[0] = INT_MAX; bbox[1] = INT_MAX; bbox[2] = INT_MIN; bbox[3] = INT_MIN;
     }
 
-    // ---- source coordinate of this destination pixel
-    float subx, suby;
+    float sxA, syA, sxB, syB;
+    if (MODE == 0)
     {
-        const float fx = (float)x, fy = (float)y;
-        float offx, offy;
-        if (MODE == 0)
-        {
-            const float dz = 1.0f / (T.r3x * fx + T.r3y * fy + T.r3z);
-            offx = (T.r1x * fx + T.r1y * fy + T.r1z) * dz - fx;
-            offy = (T.r2x * fx + T.r2y * fy + T.r2z) * dz - fy;
-        }
-        else
-        {
-            // cv::resize(mesh -> WxH, INTER_LINEAR) on CV_32FC2, then cv::multiply by (W, H).
-            float mx = (float)(((double)x + 0.5) * mesh_sx - 0.5);
-            float my = (float)(((double)y + 0.5) * mesh_sy - 0.5);
-            int cx = (int)floorf(mx), cy = (int)floorf(my);
-            mx -= (float)cx;
-            my -= (float)cy;
-            if (cx < 0) { mx = 0.0f; cx = 0; }
-            if (cx >= mesh_cols - 1) { mx = 0.0f; cx = mesh_cols - 1; }
-            if (cy < 0) { my = 0.0f; cy = 0; }
-            if (cy >= mesh_rows - 1) { my = 0.0f; cy = mesh_rows - 1; }
-            const int cx1 = min(cx + 1, mesh_cols - 1), cy1 = min(cy + 1, mesh_rows - 1);
-            const float2 m00 = __ldg(&mesh[cy * mesh_cols + cx]), m01 = __ldg(&mesh[cy * mesh_cols + cx1]);
-            const float2 m10 = __ldg(&mesh[cy1 * mesh_cols + cx]), m11 = __ldg(&mesh[cy1 * mesh_cols + cx1]);
-            const float ax0 = 1.0f - mx, ax1 = mx, ay0 = 1.0f - my, ay1 = my;
-            const float h0x = m00.x * ax0 + m01.x * ax1, h0y = m00.y * ax0 + m01.y * ax1;
-            const float h1x = m10.x * ax0 + m11.x * ax1, h1y = m10.y * ax0 + m11.y * ax1;
-            offx = (h0x * ay0 + h1x * ay1) * (float)W;
-            offy = (h0y * ay0 + h1y * ay1) * (float)H;
-        }
-        subx = fx + offx;
-        suby = fy + offy;
+        // the scalar expressions of source_position<0>, evaluated for both pixels of the pair per instruction
+        const f2 fx = pk1((float)x), fy = pk((float)yA, (float)yB);
+        const f2 den = add2(add2(mul2(pk1(T.r3x), fx), mul2(pk1(T.r3y), fy)), pk1(T.r3z));
+        const f2 dz = pk(1.0f / den.x, 1.0f / den.y);
+        const f2 nx = add2(add2(mul2(pk1(T.r1x), fx), mul2(pk1(T.r1y), fy)), pk1(T.r1z));
+        const f2 ny = add2(add2(mul2(pk1(T.r2x), fx), mul2(pk1(T.r2y), fy)), pk1(T.r2z));
+        const f2 sx2 = add2(fx, add2(mul2(nx, dz), neg2(fx)));
+        const f2 sy2 = add2(fy, add2(mul2(ny, dz), neg2(fy)));
+        sxA = sx2.x; sxB = sx2.y; syA = sy2.x; syB = sy2.y;
     }
-    const int sx = __float2int_rz(subx);  // convert_int2_rtz
-    const int sy = __float2int_rz(suby);
-    const float ppx = subx - floorf(subx);
-    const float ppy = suby - floorf(suby);
-
-    // ---- classify (FSR.cl:387-399)
-    const bool border = (sx < 1) || (sy < 1) || (sx >= W - 4) || (sy >= H - 4);
-    const bool in_src = (sx >= 0) && (sx < W) && (sy >= 0) && (sy < H);
-    const bool do_easu = inside && !border;
+    else
+    {
+        source_position<MODE>(x, yA, W, H, T, M, sxA, syA);
+        source_position<MODE>(x, yB, W, H, T, M, sxB, syB);
+    }
+    const PixelClass A = classify(sxA, syA, W, H, insideA), B = classify(sxB, syB, W, H, insideB);
 
     __syncthreads();
     {
         // warp-level reduce, one shared atomic per warp
-        const int lminx = do_easu ? sx : INT_MAX, lminy = do_easu ? sy : INT_MAX;
-        const int lmaxx = do_easu ? sx : INT_MIN, lmaxy = do_easu ? sy : INT_MIN;
+        const int lminx = min(A.do_easu ? A.sx : INT_MAX, B.do_easu ? B.sx : INT_MAX);
+        const int lminy = min(A.do_easu ? A.sy : INT_MAX, B.do_easu ? B.sy : INT_MAX);
+        const int lmaxx = max(A.do_easu ? A.sx : INT_MIN, B.do_easu ? B.sx : INT_MIN);
+        const int lmaxy = max(A.do_easu ? A.sy : INT_MIN, B.do_easu ? B.sy : INT_MIN);
         const int wminx = __reduce_min_sync(0xffffffffu, lminx), wminy = __reduce_min_sync(0xffffffffu, lminy);
         const int wmaxx = __reduce_max_sync(0xffffffffu, lmaxx), wmaxy = __reduce_max_sync(0xffffffffu, lmaxy);
         if ((threadIdx.x & 31) == 0 && wminx != INT_MAX)
@@ -266,74 +466,108 @@ __global__ void __launch_bounds__(TILE_W* TILE_H)
     const bool any_easu = bbox[0] != INT_MAX;
     const int x0 = bbox[0] - 1, y0 = bbox[1] - 1;                    // taps reach f-1 .. f+2
     const int bw = bbox[2] + 2 - x0 + 1, bh = bbox[3] + 2 - y0 + 1;  // all inside the image (border band excluded)
-    const bool staged = any_easu && bw <= SRC_W && bh <= SRC_H;
+    const bool staged = any_easu && bw <= STG_W && bh <= STG_H;
 
     if (staged)
     {
-        // thread (tx, ty) stages columns tx and tx+32 of rows ty, ty+8, ty+16 (SRC_W <= 64, SRC_H <= 24): no integer
-        // division, lanes read consecutive pixels of one row
-        static_assert(SRC_W <= 2 * TILE_W && SRC_H <= 3 * TILE_H, "staging pattern covers the tile");
+        // thread (tx, ty) stages columns tx and tx+32 of rows ty, ty+8, ty+16, ty+24: no integer division, lanes read
+        // consecutive pixels of one row
+        static_assert(STG_W <= 2 * TILE_W && STG_H <= 4 * TILE_H, "staging pattern covers the tile");
         const uint8_t* p0 = src + (size_t)(y0 + ty) * src_pitch + 3 * (x0 + tx);
 #pragma unroll
-        for (int rr = 0; rr < 3; rr++)
+        for (int rr = 0; rr < 4; rr++)
         {
             const int r = ty + TILE_H * rr;
             if (r < bh)
             {
                 const uint8_t* p = p0 + (size_t)(TILE_H * rr) * src_pitch;
-                if (tx < bw) tile[r * SRC_W + tx] = load_texel<YUV>(p);
-                if (tx + TILE_W < bw) tile[r * SRC_W + tx + TILE_W] = load_texel<YUV>(p + 3 * TILE_W);
+                if (tx < bw) tile[r * STG_W + tx] = load_texel<YUV>(p);
+                if (tx + TILE_W < bw) tile[r * STG_W + tx + TILE_W] = load_texel<YUV>(p + 3 * TILE_W);
+            }
+        }
+        __syncthreads();
+        // direction terms of the pixels that can be a corner f/g/j/k: columns 1 .. bw-2, rows 1 .. bh-2
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++)
+        {
+            const int r = 1 + ty + TILE_H * rr;
+            if (r < bh - 1)
+            {
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++)
+                {
+                    const int c = 1 + tx + TILE_W * cc;
+                    if (c < bw - 1)
+                    {
+                        const float4* t = &tile[r * STG_W + c];
+                        terms[r * STG_W + c] = easu_direction_terms(t[-STG_W].w, t[-1].w, t[0].w, t[1].w, t[STG_W].w);
+                    }
+                }
             }
         }
     }
     __syncthreads();
 
-    if (!inside) return;
-
-    uchar3 out = bg;
-    if (border)
+    uchar3 outA = bg, outB = bg;
+    if (staged && (A.do_easu || B.do_easu))
     {
-        if (in_src)
-        {
-            const uint8_t* p = src + (size_t)sy * src_pitch + 3 * sx;
-            out.x = __ldg(p); out.y = __ldg(p + 1); out.z = __ldg(p + 2);
-        }
-    }
-    else if (staged)
-    {
-        SmemTap tap{&tile[(sy - y0) * SRC_W + (sx - x0)]};
-        out = easu(tap, ppx, ppy);
+        // a lane whose pixel is not an EASU pixel computes on its partner's taps and discards the result
+        const int iA = A.do_easu ? (A.sy - y0) * STG_W + (A.sx - x0) : (B.sy - y0) * STG_W + (B.sx - x0);
+        const int iB = B.do_easu ? (B.sy - y0) * STG_W + (B.sx - x0) : iA;
+        uchar3 eA, eB;
+        easu_pair<STG_W>(&tile[iA], &tile[iB], &terms[iA], &terms[iB], pk(A.ppx, B.ppx), pk(A.ppy, B.ppy), eA, eB);
+        if (A.do_easu) outA = eA;
+        if (B.do_easu) outB = eB;
     }
     else
     {
-        GlobalTap<YUV> tap{src + (size_t)sy * src_pitch + 3 * sx, src_pitch};
-        out = easu(tap, ppx, ppy);
+        // extreme warp: the footprint does not fit the staging tile -> direct global reads, one pixel at a time
+        if (A.do_easu) outA = easu_global<YUV>(src + (size_t)A.sy * src_pitch + 3 * A.sx, src_pitch, A.ppx, A.ppy);
+        if (B.do_easu) outB = easu_global<YUV>(src + (size_t)B.sy * src_pitch + 3 * B.sx, src_pitch, B.ppx, B.ppy);
+    }
+    if (A.border && A.in_src)
+    {
+        const uint8_t* p = src + (size_t)A.sy * src_pitch + 3 * A.sx;
+        outA.x = __ldg(p); outA.y = __ldg(p + 1); outA.z = __ldg(p + 2);
+    }
+    if (B.border && B.in_src)
+    {
+        const uint8_t* p = src + (size_t)B.sy * src_pitch + 3 * B.sx;
+        outB.x = __ldg(p); outB.y = __ldg(p + 1); outB.z = __ldg(p + 2);
     }
 
-    uint8_t* q = dst + (size_t)y * dst_pitch + 3 * x;
-    q[0] = out.x; q[1] = out.y; q[2] = out.z;
+    if (insideA)
+    {
+        uint8_t* q = dst + (size_t)yA * dst_pitch + 3 * x;
+        q[0] = outA.x; q[1] = outA.y; q[2] = outA.z;
+    }
+    if (insideB)
+    {
+        uint8_t* q = dst + (size_t)yB * dst_pitch + 3 * x;
+        q[0] = outB.x; q[1] = outB.y; q[2] = outB.z;
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9])
 {
-    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, TILE_H));
+    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
     const Transform T{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     if (p.yuv)
         k_easu_remap<0, true><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                               p.height, T, nullptr, 0, 0, 0.0, 0.0, bg);
+                                                               p.height, T, MeshArgs{}, bg);
     else
         k_easu_remap<0, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                p.height, T, nullptr, 0, 0, 0.0, 0.0, bg);
+                                                                p.height, T, MeshArgs{}, bg);
     count_launches(1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
 {
-    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, TILE_H));
+    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
     const Transform T{};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     // cv::resize: scale = 1 / (dsize / ssize), in double
@@ -341,10 +575,10 @@ cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float
     const float2* m = reinterpret_cast<const float2*>(mesh);
     if (p.yuv)
         k_easu_remap<1, true><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                               p.height, T, m, mesh_cols, mesh_rows, sx, sy, bg);
+                                                               p.height, T, MeshArgs{m, mesh_cols, mesh_rows, sx, sy}, bg);
     else
         k_easu_remap<1, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                p.height, T, m, mesh_cols, mesh_rows, sx, sy, bg);
+                                                                p.height, T, MeshArgs{m, mesh_cols, mesh_rows, sx, sy}, bg);
     count_launches(1);
     return cudaGetLastError();
 }
