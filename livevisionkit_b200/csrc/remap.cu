@@ -16,6 +16,8 @@
 // --fmad=false so that nothing ELSE is contracted -> results are bit-identical to the oracle (tests assert 0 LSB).
 // Roofline: 6 B/px algorithmic (3 read + 3 written); see DESIGN.md.
 
+#include <cstdlib>
+
 #include "common.hpp"
 
 namespace lvkb200
@@ -186,9 +188,40 @@ __device__ __noinline__ uchar3 easu_global(const uint8_t* __restrict__ base, siz
 using f2 = float2;
 __device__ __forceinline__ f2 pk(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ f2 pk1(float a) { return make_float2(a, a); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+// Inline PTX with explicit .rn.  NOTE: nvcc 12.9 contracts a packed multiply whose only use is a packed add into
+// FFMA2 -- for the __fmul2_rn/__fadd2_rn intrinsics AND for explicit mul.rn.f32x2/add.rn.f32x2, --fmad=false
+// notwithstanding (seen in SASS and as 1-ulp parity breaks).  So no expression below feeds a mul2 result straight
+// into an add2: those few sites use scalar __fadd_rn.
+__device__ __forceinline__ unsigned long long f2_bits(f2 a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ f2 bits_f2(unsigned long long r)
+{
+    f2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
 __device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
 
 // FSR.cl:131-176, the part that depends only on the SOURCE pixel C and its cross A(up) B(left) D(right) E(down):
@@ -295,7 +328,8 @@ __device__ __forceinline__ void easu_pair(const float4* __restrict__ tA, const f
     f2 stretch = fma2(dirx, dirx, mul2(diry, diry));
     stretch = mul2(stretch, pk(aprx_lo_rcp(fmaxf(fabsf(dirx.x), fabsf(diry.x))),
                                aprx_lo_rcp(fmaxf(fabsf(dirx.y), fabsf(diry.y)))));
-    const f2 len2x = fma2(add2(stretch, pk1(-1.0f)), len, pk1(1.0f));
+    // (stretch - 1) in scalar: a packed add fed by a packed mul would be contracted by ptxas (see source_position)
+    const f2 len2x = fma2(pk(__fadd_rn(stretch.x, -1.0f), __fadd_rn(stretch.y, -1.0f)), len, pk1(1.0f));
     const f2 len2y = fma2(pk1(-0.5f), len, pk1(1.0f));
     const f2 lob = fma2(pk1((1.0f / 4.0f - 0.04f) - 0.5f), len, pk1(0.5f));
     const f2 clp = pk(aprx_lo_rcp(lob.x), aprx_lo_rcp(lob.y));
@@ -406,8 +440,8 @@ __device__ __forceinline__ PixelClass classify(float subx, float suby, int W, in
     return c;
 }
 
-template <int MODE, bool YUV>
-__global__ void __launch_bounds__(TILE_W* TILE_H, 2)
+template <int MODE, bool YUV, int OCC>
+__global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
     k_easu_remap(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch, int W,
                  int H, Transform T, MeshArgs M, uchar3 bg)
 {
@@ -427,23 +461,10 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, 2)
     }
 
     float sxA, syA, sxB, syB;
-    if (MODE == 0)
-    {
-        // the scalar expressions of source_position<0>, evaluated for both pixels of the pair per instruction
-        const f2 fx = pk1((float)x), fy = pk((float)yA, (float)yB);
-        const f2 den = add2(add2(mul2(pk1(T.r3x), fx), mul2(pk1(T.r3y), fy)), pk1(T.r3z));
-        const f2 dz = pk(1.0f / den.x, 1.0f / den.y);
-        const f2 nx = add2(add2(mul2(pk1(T.r1x), fx), mul2(pk1(T.r1y), fy)), pk1(T.r1z));
-        const f2 ny = add2(add2(mul2(pk1(T.r2x), fx), mul2(pk1(T.r2y), fy)), pk1(T.r2z));
-        const f2 sx2 = add2(fx, add2(mul2(nx, dz), neg2(fx)));
-        const f2 sy2 = add2(fy, add2(mul2(ny, dz), neg2(fy)));
-        sxA = sx2.x; sxB = sx2.y; syA = sy2.x; syB = sy2.y;
-    }
-    else
-    {
-        source_position<MODE>(x, yA, W, H, T, M, sxA, syA);
-        source_position<MODE>(x, yB, W, H, T, M, sxB, syB);
-    }
+    // scalar on purpose: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with explicit .rn and --fmad=false),
+    // which would change the rounding of these mul-then-add expressions
+    source_position<MODE>(x, yA, W, H, T, M, sxA, syA);
+    source_position<MODE>(x, yB, W, H, T, M, sxB, syB);
     const PixelClass A = classify(sxA, syA, W, H, insideA), B = classify(sxB, syB, W, H, insideB);
 
     __syncthreads();
@@ -550,17 +571,45 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, 2)
 
 }  // namespace
 
+static int remap_occupancy()
+{
+    static const int occ = [] {
+        const char* e = getenv("LVKB200_REMAP_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
+        const int v = e ? atoi(e) : 4;
+        return (v == 2 || v == 3) ? v : 4;
+    }();
+    return occ;
+}
+
+template <int MODE, bool YUV>
+static void launch_easu(cudaStream_t cs, dim3 grid, const RemapParams& p, const Transform& T, const MeshArgs& M,
+                        uchar3 bg)
+{
+    switch (remap_occupancy())
+    {
+    case 2:
+        k_easu_remap<MODE, YUV, 2><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
+                                                                      p.height, T, M, bg);
+        break;
+    case 3:
+        k_easu_remap<MODE, YUV, 3><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
+                                                                      p.height, T, M, bg);
+        break;
+    default:
+        k_easu_remap<MODE, YUV, 4><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
+                                                                      p.height, T, M, bg);
+    }
+}
+
 cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9])
 {
     const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
     const Transform T{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     if (p.yuv)
-        k_easu_remap<0, true><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                               p.height, T, MeshArgs{}, bg);
+        launch_easu<0, true>(cs, grid, p, T, MeshArgs{}, bg);
     else
-        k_easu_remap<0, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                p.height, T, MeshArgs{}, bg);
+        launch_easu<0, false>(cs, grid, p, T, MeshArgs{}, bg);
     count_launches(1);
     return cudaGetLastError();
 }
@@ -568,17 +617,14 @@ cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const
 cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
 {
     const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
-    const Transform T{};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     // cv::resize: scale = 1 / (dsize / ssize), in double
     const double sx = 1.0 / ((double)p.width / (double)mesh_cols), sy = 1.0 / ((double)p.height / (double)mesh_rows);
-    const float2* m = reinterpret_cast<const float2*>(mesh);
+    const MeshArgs M{reinterpret_cast<const float2*>(mesh), mesh_cols, mesh_rows, sx, sy};
     if (p.yuv)
-        k_easu_remap<1, true><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                               p.height, T, MeshArgs{m, mesh_cols, mesh_rows, sx, sy}, bg);
+        launch_easu<1, true>(cs, grid, p, Transform{}, M, bg);
     else
-        k_easu_remap<1, false><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                p.height, T, MeshArgs{m, mesh_cols, mesh_rows, sx, sy}, bg);
+        launch_easu<1, false>(cs, grid, p, Transform{}, M, bg);
     count_launches(1);
     return cudaGetLastError();
 }
