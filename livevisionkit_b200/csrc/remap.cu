@@ -152,14 +152,17 @@ __device__ __forceinline__ uchar3 easu(const Tap& tap, float ppx, float ppy)
     return out;
 }
 
+// (float)byte, exactly, without the quarter-rate conversion pipe (I2F): 2^23 + v has v in its low mantissa bits.
+__device__ __forceinline__ float u8_to_float(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
 template <bool YUV>
 __device__ __forceinline__ float4 load_texel(const uint8_t* __restrict__ p)
 {
     const float norm = 0.00392156862f;
     float4 t;
-    t.x = (float)__ldg(p) * norm;
-    t.y = (float)__ldg(p + 1) * norm;
-    t.z = (float)__ldg(p + 2) * norm;
+    t.x = u8_to_float(__ldg(p)) * norm;
+    t.y = u8_to_float(__ldg(p + 1)) * norm;
+    t.z = u8_to_float(__ldg(p + 2)) * norm;
     // FSR.cl:229-241 (the #ifndef is inverted relative to its comments; reproduced as written)
     t.w = YUV ? __fmaf_rn(t.z, 0.5f, __fmaf_rn(t.x, 0.5f, t.y)) : t.x;
     return t;
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
 {
     __shared__ float4 tile[STG_H * STG_W];   // {c0, c1, c2, luma} / 255 of the staged source pixels
     __shared__ float4 terms[STG_H * STG_W];  // easu_direction_terms of the same pixels (interior only)
+    __shared__ float luma[STG_H * STG_W];    // tile[].w again, contiguous: the 5-point cross reads are conflict-free
     __shared__ int bbox[4];                  // minx, miny, maxx, maxy of f over the EASU pixels of this tile
 
     const int tx = threadIdx.x & (TILE_W - 1);
@@ -502,8 +506,18 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
             if (r < bh)
             {
                 const uint8_t* p = p0 + (size_t)(TILE_H * rr) * src_pitch;
-                if (tx < bw) tile[r * STG_W + tx] = load_texel<YUV>(p);
-                if (tx + TILE_W < bw) tile[r * STG_W + tx + TILE_W] = load_texel<YUV>(p + 3 * TILE_W);
+                if (tx < bw)
+                {
+                    const float4 v = load_texel<YUV>(p);
+                    tile[r * STG_W + tx] = v;
+                    luma[r * STG_W + tx] = v.w;
+                }
+                if (tx + TILE_W < bw)
+                {
+                    const float4 v = load_texel<YUV>(p + 3 * TILE_W);
+                    tile[r * STG_W + tx + TILE_W] = v;
+                    luma[r * STG_W + tx + TILE_W] = v.w;
+                }
             }
         }
         __syncthreads();
@@ -520,8 +534,8 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
                     const int c = 1 + tx + TILE_W * cc;
                     if (c < bw - 1)
                     {
-                        const float4* t = &tile[r * STG_W + c];
-                        terms[r * STG_W + c] = easu_direction_terms(t[-STG_W].w, t[-1].w, t[0].w, t[1].w, t[STG_W].w);
+                        const float* l = &luma[r * STG_W + c];
+                        terms[r * STG_W + c] = easu_direction_terms(l[-STG_W], l[-1], l[0], l[1], l[STG_W]);
                     }
                 }
             }
@@ -546,15 +560,19 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
         if (A.do_easu) outA = easu_global<YUV>(src + (size_t)A.sy * src_pitch + 3 * A.sx, src_pitch, A.ppx, A.ppy);
         if (B.do_easu) outB = easu_global<YUV>(src + (size_t)B.sy * src_pitch + 3 * B.sx, src_pitch, B.ppx, B.ppy);
     }
-    if (A.border && A.in_src)
+    // border band (FSR.cl:387-399): nearest neighbour.  Only tiles on the frame's edge have any -> one warp-wide test
+    if (__any_sync(0xffffffffu, (A.border && A.in_src) || (B.border && B.in_src)))
     {
-        const uint8_t* p = src + (size_t)A.sy * src_pitch + 3 * A.sx;
-        outA.x = __ldg(p); outA.y = __ldg(p + 1); outA.z = __ldg(p + 2);
-    }
-    if (B.border && B.in_src)
-    {
-        const uint8_t* p = src + (size_t)B.sy * src_pitch + 3 * B.sx;
-        outB.x = __ldg(p); outB.y = __ldg(p + 1); outB.z = __ldg(p + 2);
+        if (A.border && A.in_src)
+        {
+            const uint8_t* p = src + (size_t)A.sy * src_pitch + 3 * A.sx;
+            outA.x = __ldg(p); outA.y = __ldg(p + 1); outA.z = __ldg(p + 2);
+        }
+        if (B.border && B.in_src)
+        {
+            const uint8_t* p = src + (size_t)B.sy * src_pitch + 3 * B.sx;
+            outB.x = __ldg(p); outB.y = __ldg(p + 1); outB.z = __ldg(p + 2);
+        }
     }
 
     if (insideA)
@@ -566,6 +584,272 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
     {
         uint8_t* q = dst + (size_t)yB * dst_pitch + 3 * x;
         q[0] = outB.x; q[1] = outB.y; q[2] = outB.z;
+    }
+}
+
+// =====================================================================================================================
+// Persistent, software-pipelined variant (LVKB200_REMAP_KERNEL=3; measured slower than the default): one CTA per (SM x OCC) walks over destination tiles; while tile
+// n is converted / filtered, the raw source bytes of tile n+1 are already in flight as TMA bulk copies
+// (cp.async.bulk global -> shared, one per source row, completion counted by an mbarrier), so no warp ever waits on a
+// global load.  The source window of a tile is PLANNED from the tile's four corners (a projective map is monotone
+// along rows and columns, so the corners bound the footprint); it is only a prefetch hint: every pixel re-checks that
+// its 12 taps lie inside the staged window and otherwise takes the direct-global path, so the result never depends
+// on the plan.
+// =====================================================================================================================
+
+constexpr int RAW_PITCH = 160;               // bytes per staged raw row: 3 * STG_W = 132, + 15 alignment, rounded to 16
+constexpr int RAW_BYTES = STG_H * RAW_PITCH;  // one raw buffer
+constexpr int V3_SMEM = STG_H * STG_W * (2 * (int)sizeof(float4) + (int)sizeof(float)) + 2 * RAW_BYTES;
+
+struct TilePlan
+{
+    int x0, y0;   // top-left source pixel of the staged window
+    int bw, bh;   // window size in pixels (bw == 0: nothing staged)
+    int off;      // byte offset of pixel x0 inside a raw row (alignment of the bulk copy)
+    int row_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do
+    {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Executed by warp 0: plans the source window of destination tile `t` into plan[b] and, on the bulk path, starts its
+// row copies into raw buffer b.
+template <int MODE>
+__device__ __forceinline__ void plan_and_fetch(int t, int b, int tiles_x, int W, int H, const Transform& T,
+                                               const MeshArgs& M, const uint8_t* __restrict__ src, size_t src_pitch,
+                                               bool bulk, TilePlan* plan, uint8_t* raw, uint64_t* full)
+{
+    const int lane = threadIdx.x & 31;
+    const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+    const int X0 = txi * TILE_W, Y0 = tyi * CTA_H;
+    const int X1 = min(X0 + TILE_W - 1, W - 1), Y1 = min(Y0 + CTA_H - 1, H - 1);
+    float fxs, fys;
+    source_position<MODE>((lane & 1) ? X1 : X0, (lane & 2) ? Y1 : Y0, W, H, T, M, fxs, fys);
+    // clamp before the conversion so that NaN / huge coordinates of a degenerate transform stay harmless
+    const int cx = __float2int_rz(fminf(fmaxf(fxs, -8.0f), (float)W + 8.0f));
+    const int cy = __float2int_rz(fminf(fmaxf(fys, -8.0f), (float)H + 8.0f));
+    const bool corner = lane < 4;
+    int minx = __reduce_min_sync(0xffffffffu, corner ? cx : INT_MAX);
+    int miny = __reduce_min_sync(0xffffffffu, corner ? cy : INT_MAX);
+    int maxx = __reduce_max_sync(0xffffffffu, corner ? cx : INT_MIN);
+    int maxy = __reduce_max_sync(0xffffffffu, corner ? cy : INT_MIN);
+    // +-1 px of slack for float rounding (mesh mode: the bilinear offsets are not monotone, the slack is a heuristic);
+    // f of an EASU pixel lies in [1, W-5] x [1, H-5] (FSR.cl:387-399)
+    minx = max(minx - 1, 1); miny = max(miny - 1, 1);
+    maxx = min(maxx + 1, W - 5); maxy = min(maxy + 1, H - 5);
+    TilePlan pl;
+    pl.x0 = minx - 1; pl.y0 = miny - 1;  // taps reach f-1 .. f+2
+    pl.bw = (minx <= maxx && miny <= maxy) ? min(maxx + 2 - pl.x0 + 1, STG_W) : 0;
+    pl.bh = min(maxy + 2 - pl.y0 + 1, STG_H);
+    pl.off = bulk ? (int)((3u * (unsigned)pl.x0) & 15u) : 0;
+    pl.row_bytes = (pl.off + 3 * pl.bw + 15) & ~15;
+    if (lane == 0) plan[b] = pl;
+    if (bulk && pl.bw > 0)
+    {
+        if (lane == 0) mbar_arrive_expect_tx(&full[b], (uint32_t)(pl.row_bytes * pl.bh));
+        __syncwarp();
+        if (lane < pl.bh)
+            bulk_g2s(raw + b * RAW_BYTES + lane * RAW_PITCH,
+                     src + (size_t)(pl.y0 + lane) * src_pitch + 3 * pl.x0 - pl.off, (uint32_t)pl.row_bytes, &full[b]);
+    }
+}
+
+template <int MODE, bool YUV, int OCC>
+__global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
+    k_easu_remap_pipelined(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst,
+                           size_t dst_pitch, int W, int H, Transform T, MeshArgs M, uchar3 bg, int tiles_x, int n_tiles,
+                           int bulk)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* const tile = reinterpret_cast<float4*>(smem);   // {c0, c1, c2, luma} / 255 of the staged source pixels
+    float4* const terms = tile + STG_H * STG_W;             // easu_direction_terms of the same pixels (interior only)
+    float* const luma = reinterpret_cast<float*>(terms + STG_H * STG_W);  // tile[].w again, contiguous (conflict-free)
+    uint8_t* const raw = reinterpret_cast<uint8_t*>(luma + STG_H * STG_W);  // 2 raw (byte) windows, bulk-copy targets
+    __shared__ TilePlan plan[2];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tx = threadIdx.x & (TILE_W - 1);
+    const int ty = threadIdx.x / TILE_W;
+    const bool warp0 = threadIdx.x < 32;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    int t = blockIdx.x;
+    if (warp0 && t < n_tiles) plan_and_fetch<MODE>(t, 0, tiles_x, W, H, T, M, src, src_pitch, bulk != 0, plan, raw, full);
+    __syncthreads();
+
+    uint32_t phase0 = 0, phase1 = 0;  // mbarrier phase parity of full[0] / full[1]
+    for (int it = 0; t < n_tiles; t += gridDim.x, it++)
+    {
+        const int b = it & 1;
+        const int tn = t + (int)gridDim.x;
+        // raw[b^1] was last read by the conversion of iteration it-1, which every thread left through a barrier
+        if (warp0 && tn < n_tiles)
+            plan_and_fetch<MODE>(tn, b ^ 1, tiles_x, W, H, T, M, src, src_pitch, bulk != 0, plan, raw, full);
+
+        const TilePlan pl = plan[b];
+        const int x0 = pl.x0, y0 = pl.y0, bw = pl.bw, bh = pl.bh;
+        uint8_t* const rawb = raw + b * RAW_BYTES;
+
+        if (bw > 0)
+        {
+            if (bulk)
+            {
+                mbar_wait(&full[b], b ? phase1 : phase0);
+                if (b) phase1 ^= 1u; else phase0 ^= 1u;
+            }
+            else
+            {
+                // source rows are not 16-byte aligned: plain byte copy, one warp per row (no prefetch on this path)
+                for (int r = ty; r < bh; r += TILE_H)
+                {
+                    const uint8_t* g = src + (size_t)(y0 + r) * src_pitch + 3 * x0;
+                    for (int i = tx; i < 3 * bw; i += TILE_W) rawb[r * RAW_PITCH + i] = __ldg(g + i);
+                }
+                __syncthreads();
+            }
+            // ---- raw bytes -> float4 texels.  thread (tx, ty): columns tx, tx+32 of rows ty, ty+8, ty+16, ty+24
+            static_assert(STG_W <= 2 * TILE_W && STG_H <= 4 * TILE_H, "staging pattern covers the window");
+            const float norm = 0.00392156862f;
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++)
+            {
+                const int r = ty + TILE_H * rr;
+                if (r < bh)
+                {
+#pragma unroll
+                    for (int cc = 0; cc < 2; cc++)
+                    {
+                        const int c = tx + TILE_W * cc;
+                        if (c < bw)
+                        {
+                            const uint8_t* q = rawb + r * RAW_PITCH + pl.off + 3 * c;
+                            float4 v;
+                            v.x = u8_to_float(q[0]) * norm;
+                            v.y = u8_to_float(q[1]) * norm;
+                            v.z = u8_to_float(q[2]) * norm;
+                            // FSR.cl:229-241 (the #ifndef is inverted relative to its comments; reproduced as written)
+                            v.w = YUV ? __fmaf_rn(v.z, 0.5f, __fmaf_rn(v.x, 0.5f, v.y)) : v.x;
+                            tile[r * STG_W + c] = v;
+                            luma[r * STG_W + c] = v.w;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- direction terms of the pixels that can be a corner f/g/j/k: columns 1 .. bw-2, rows 1 .. bh-2
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++)
+            {
+                const int r = 1 + ty + TILE_H * rr;
+                if (r < bh - 1)
+                {
+#pragma unroll
+                    for (int cc = 0; cc < 2; cc++)
+                    {
+                        const int c = 1 + tx + TILE_W * cc;
+                        if (c < bw - 1)
+                        {
+                            const float* l = &luma[r * STG_W + c];
+                            terms[r * STG_W + c] = easu_direction_terms(l[-STG_W], l[-1], l[0], l[1], l[STG_W]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- the tile's pixels: thread (tx, ty) owns (x, yA) and (x, yA + 8)
+        const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+        const int x = txi * TILE_W + tx;
+        const int yA = tyi * CTA_H + ty, yB = yA + PAIR_DY;
+        const bool insideA = (x < W) && (yA < H), insideB = (x < W) && (yB < H);
+        float sxA, syA, sxB, syB;
+        source_position<MODE>(x, yA, W, H, T, M, sxA, syA);
+        source_position<MODE>(x, yB, W, H, T, M, sxB, syB);
+        const PixelClass A = classify(sxA, syA, W, H, insideA), B = classify(sxB, syB, W, H, insideB);
+        // all 12 taps (f-1 .. f+2) and the 4 corner terms inside the staged window?
+        const bool fitA = A.do_easu && bw > 0 && A.sx - 1 >= x0 && A.sx + 2 < x0 + bw && A.sy - 1 >= y0 && A.sy + 2 < y0 + bh;
+        const bool fitB = B.do_easu && bw > 0 && B.sx - 1 >= x0 && B.sx + 2 < x0 + bw && B.sy - 1 >= y0 && B.sy + 2 < y0 + bh;
+
+        uchar3 outA = bg, outB = bg;
+        if (fitA || fitB)
+        {
+            // a lane whose pixel is not a staged EASU pixel computes on its partner's taps and discards the result
+            const int iA = fitA ? (A.sy - y0) * STG_W + (A.sx - x0) : (B.sy - y0) * STG_W + (B.sx - x0);
+            const int iB = fitB ? (B.sy - y0) * STG_W + (B.sx - x0) : iA;
+            uchar3 eA, eB;
+            easu_pair<STG_W>(&tile[iA], &tile[iB], &terms[iA], &terms[iB], pk(A.ppx, B.ppx), pk(A.ppy, B.ppy), eA, eB);
+            if (fitA) outA = eA;
+            if (fitB) outB = eB;
+        }
+        // outside the planned window (extreme warps): direct global reads, one pixel at a time
+        // rare pixels, behind one warp-wide test: outside the planned window -> direct global reads; border band
+        // (FSR.cl:387-399) -> nearest neighbour
+        if (__any_sync(0xffffffffu, (A.do_easu && !fitA) || (B.do_easu && !fitB) || (A.border && A.in_src) ||
+                                        (B.border && B.in_src)))
+        {
+            if (A.do_easu && !fitA)
+                outA = easu_global<YUV>(src + (size_t)A.sy * src_pitch + 3 * A.sx, src_pitch, A.ppx, A.ppy);
+            if (B.do_easu && !fitB)
+                outB = easu_global<YUV>(src + (size_t)B.sy * src_pitch + 3 * B.sx, src_pitch, B.ppx, B.ppy);
+            if (A.border && A.in_src)
+            {
+                const uint8_t* p = src + (size_t)A.sy * src_pitch + 3 * A.sx;
+                outA.x = __ldg(p); outA.y = __ldg(p + 1); outA.z = __ldg(p + 2);
+            }
+            if (B.border && B.in_src)
+            {
+                const uint8_t* p = src + (size_t)B.sy * src_pitch + 3 * B.sx;
+                outB.x = __ldg(p); outB.y = __ldg(p + 1); outB.z = __ldg(p + 2);
+            }
+        }
+        if (insideA)
+        {
+            uint8_t* q = dst + (size_t)yA * dst_pitch + 3 * x;
+            q[0] = outA.x; q[1] = outA.y; q[2] = outA.z;
+        }
+        if (insideB)
+        {
+            uint8_t* q = dst + (size_t)yB * dst_pitch + 3 * x;
+            q[0] = outB.x; q[1] = outB.y; q[2] = outB.z;
+        }
+        __syncthreads();  // tile / terms / plan[b] are free for the next iteration
     }
 }
 
@@ -581,50 +865,75 @@ static int remap_occupancy()
     return occ;
 }
 
+static int remap_kernel_version()
+{
+    static const int v = [] {
+        // tuning knob: 2 = one CTA per tile (default: measured 49 us at 1080p), 3 = persistent CTAs with TMA bulk
+        // prefetch (53 us: the kernel is issue / shared-memory bound, not load-latency bound, so the prefetch buys
+        // nothing and the extra barrier per tile costs)
+        const char* e = getenv("LVKB200_REMAP_KERNEL");
+        return (e && atoi(e) == 3) ? 3 : 2;
+    }();
+    return v;
+}
+
+template <int MODE, bool YUV, int OCC>
+static void launch_easu_occ(cudaStream_t cs, const RemapParams& p, const Transform& T, const MeshArgs& M, uchar3 bg)
+{
+    const int tiles_x = div_up(p.width, TILE_W), tiles_y = div_up(p.height, CTA_H);
+    if (remap_kernel_version() == 2)
+    {
+        k_easu_remap<MODE, YUV, OCC><<<dim3(tiles_x, tiles_y), TILE_W * TILE_H, 0, cs>>>(
+            p.src, p.src_pitch, p.dst, p.dst_pitch, p.width, p.height, T, M, bg);
+        return;
+    }
+    static const int ctas = [] {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_easu_remap_pipelined<MODE, YUV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
+        return sms * OCC;
+    }();
+    const int n_tiles = tiles_x * tiles_y;
+    // TMA bulk copies need 16-byte aligned global addresses: the frame ring always is, arbitrary caller buffers may not
+    const int bulk = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15u) == 0) ? 1 : 0;
+    k_easu_remap_pipelined<MODE, YUV, OCC><<<min(ctas, n_tiles), TILE_W * TILE_H, V3_SMEM, cs>>>(
+        p.src, p.src_pitch, p.dst, p.dst_pitch, p.width, p.height, T, M, bg, tiles_x, n_tiles, bulk);
+}
+
 template <int MODE, bool YUV>
-static void launch_easu(cudaStream_t cs, dim3 grid, const RemapParams& p, const Transform& T, const MeshArgs& M,
-                        uchar3 bg)
+static void launch_easu(cudaStream_t cs, const RemapParams& p, const Transform& T, const MeshArgs& M, uchar3 bg)
 {
     switch (remap_occupancy())
     {
-    case 2:
-        k_easu_remap<MODE, YUV, 2><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                      p.height, T, M, bg);
-        break;
-    case 3:
-        k_easu_remap<MODE, YUV, 3><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                      p.height, T, M, bg);
-        break;
-    default:
-        k_easu_remap<MODE, YUV, 4><<<grid, TILE_W * TILE_H, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
-                                                                      p.height, T, M, bg);
+    case 2: launch_easu_occ<MODE, YUV, 2>(cs, p, T, M, bg); break;
+    case 3: launch_easu_occ<MODE, YUV, 3>(cs, p, T, M, bg); break;
+    default: launch_easu_occ<MODE, YUV, 4>(cs, p, T, M, bg);
     }
 }
 
 cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9])
 {
-    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
     const Transform T{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     if (p.yuv)
-        launch_easu<0, true>(cs, grid, p, T, MeshArgs{}, bg);
+        launch_easu<0, true>(cs, p, T, MeshArgs{}, bg);
     else
-        launch_easu<0, false>(cs, grid, p, T, MeshArgs{}, bg);
+        launch_easu<0, false>(cs, p, T, MeshArgs{}, bg);
     count_launches(1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
 {
-    const dim3 grid(div_up(p.width, TILE_W), div_up(p.height, CTA_H));
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     // cv::resize: scale = 1 / (dsize / ssize), in double
     const double sx = 1.0 / ((double)p.width / (double)mesh_cols), sy = 1.0 / ((double)p.height / (double)mesh_rows);
     const MeshArgs M{reinterpret_cast<const float2*>(mesh), mesh_cols, mesh_rows, sx, sy};
     if (p.yuv)
-        launch_easu<1, true>(cs, grid, p, Transform{}, M, bg);
+        launch_easu<1, true>(cs, p, Transform{}, M, bg);
     else
-        launch_easu<1, false>(cs, grid, p, Transform{}, M, bg);
+        launch_easu<1, false>(cs, p, Transform{}, M, bg);
     count_launches(1);
     return cudaGetLastError();
 }
