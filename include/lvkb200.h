@@ -207,6 +207,61 @@ lvkb200_status lvkb200_deblock(lvkb200_stream* s, const lvkb200_deblock_settings
  * submitting the result. */
 lvkb200_status lvkb200_stream_set_deblocking(lvkb200_stream* s, const lvkb200_deblock_settings* settings);
 
+/* ---- FrameIngest: OBS frame layouts <-> packed 8UC3 frames ---------------------------------------- */
+
+/* The video_format values FrameIngest::Select accepts (Modules/OBS-Plugin/Interop/FrameIngest.cpp:38-76); the
+ * numbering is this library's, the names are libobs'. */
+typedef enum lvkb200_video_format
+{
+    LVKB200_VIDEO_I420 = 0, LVKB200_VIDEO_I422 = 1, LVKB200_VIDEO_I444 = 2,  /* planar Y, U, V */
+    LVKB200_VIDEO_I40A = 3, LVKB200_VIDEO_I42A = 4, LVKB200_VIDEO_YUVA = 5,  /* the same + an alpha plane LVK ignores */
+    LVKB200_VIDEO_NV12 = 6,                                                   /* planar Y + interleaved UV at half size */
+    LVKB200_VIDEO_YVYU = 7, LVKB200_VIDEO_YUY2 = 8, LVKB200_VIDEO_UYVY = 9,   /* packed 4:2:2 */
+    LVKB200_VIDEO_AYUV = 10,                                                  /* packed 4:4:4 with alpha first */
+    LVKB200_VIDEO_Y800 = 11, LVKB200_VIDEO_BGR3 = 12,                         /* direct copies (GRAY / BGR) */
+    LVKB200_VIDEO_FORMAT_COUNT = 13
+} lvkb200_video_format;
+
+/* The fields of obs_source_frame the ingest reads (FrameIngest.cpp:134-141, :330-470).  linesize[i] is the row
+ * pitch of plane i in bytes; 0 means tightly packed (the only case the reference handles: it copies
+ * width*height*channels contiguous bytes per plane). */
+typedef struct lvkb200_obs_frame
+{
+    uint8_t* data[4];
+    uint32_t linesize[4];
+    uint32_t width, height;
+    int32_t format;     /* lvkb200_video_format */
+    uint64_t timestamp;
+} lvkb200_obs_frame;
+
+/* FrameIngest::ocl_format (FrameIngest.cpp:113-116): the lvk::VideoFrame format a video format is ingested as
+ * (YUV for every YUV layout, GRAY for Y800, BGR for BGR3); LVKB200_UNKNOWN for an unsupported value
+ * (FrameIngest::Select returning nullptr). */
+lvkb200_format lvkb200_video_format_ocl(int video_format);
+
+/* FrameIngest::upload_obs_frame -> to_ocl (FrameIngest.cpp:93-103, :479-522 I4XX, :566-584 NV12, :618-645 packed
+ * 4:2:2, :689-698 AYUV, :738-747 direct): converts the planes of `src` (host or device memory) into a packed 8UC3
+ * frame at `dst` (8UC1 for Y800).  Subsampled chroma is upsampled with cv::resize(INTER_LINEAR) arithmetic,
+ * bit-exact with OpenCV's CPU path.  4:2:x layouts need an even width, 4:2:0 an even height. */
+lvkb200_status lvkb200_frame_upload(lvkb200_stream* s, const lvkb200_obs_frame* src, lvkb200_memspace src_space,
+                                    void* dst, size_t dst_pitch, lvkb200_memspace dst_space);
+
+/* FrameIngest::download_ocl_frame -> to_obs (FrameIngest.cpp:106-110, :526-560, :588-604, :649-678, :702-716,
+ * :751-757): the reverse; chroma is subsampled with cv::resize(INTER_AREA) arithmetic.  `format` must be the
+ * layout's own ocl format (the reference would colour-convert first via VideoFrame::viewAsFormat; that conversion
+ * is outside this path and reported as LVKB200_ERR_INVALID).  An alpha plane of I40A/I42A/YUVA is left untouched,
+ * AYUV's alpha is set to 255, as in the reference. */
+lvkb200_status lvkb200_frame_download(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                                      lvkb200_format format, lvkb200_memspace src_space, lvkb200_obs_frame* dst,
+                                      lvkb200_memspace dst_space);
+
+/* VSFilter::filter for asynchronous OBS sources (VSFilter.cpp:352-364 + OBSFrame::from_obs_frame / to_obs_frame,
+ * OBSFrame.cpp:93-123): ingest `in`, run StabilizationFilter::filter, and write the delayed stabilized frame into
+ * `out` in the same video format (`out` may be `in`: OBS filters the frame in place).  res->has_output == 0 leaves
+ * `out` untouched.  Only 1.5 B/px (4:2:0) cross PCIe in each direction instead of 3. */
+lvkb200_status lvkb200_stream_submit_obs(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_memspace in_space,
+                                         lvkb200_obs_frame* out, lvkb200_memspace out_space, lvkb200_result* res);
+
 /* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
  * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for
  * the later one.  The per-stage analogue of Stopwatch (Timing/Stopwatch.cpp:42-64) for the bench harness. */

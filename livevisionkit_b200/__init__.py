@@ -387,6 +387,16 @@ class Stream:
                                                              mask.ctypes.data_as(C.POINTER(C.c_uint8))))
         return state, offsets, mask
 
+    # ---- VSFilter::filter for asynchronous OBS sources: ingest -> stabilize -> egress
+    def submit_obs(self, frame: "ObsFrame", out: "ObsFrame") -> _capi.Result:
+        cin, space = frame.to_c()
+        cout, ospace = out.to_c()
+        res = _capi.Result()
+        _capi.check(self._lib.lvkb200_stream_submit_obs(self._h, C.byref(cin), space, C.byref(cout), ospace, C.byref(res)))
+        if res.has_output:
+            out.timestamp = cout.timestamp
+        return res
+
     # ---- lvk::DeblockingFilter
     def deblock(self, frame, settings: "DeblockingFilterSettings | None" = None, fmt: int = BGR, out=None):
         """DeblockingFilter::filter on one frame (host or device); `out` defaults to a new buffer, may be `frame`."""
@@ -409,6 +419,90 @@ class Stream:
         else:
             c = settings.to_c()
             _capi.check(self._lib.lvkb200_stream_set_deblocking(self._h, C.byref(c)))
+
+
+def _plane_info(buf):
+    """-> (pointer, pitch_bytes, memspace) of one 2-D uint8 plane (numpy array or torch tensor)."""
+    if isinstance(buf, np.ndarray):
+        if buf.dtype != np.uint8 or buf.ndim != 2 or buf.strides[1] != 1:
+            raise ValueError("planes must be 2-D uint8 arrays with contiguous rows")
+        return buf.ctypes.data, buf.strides[0], _capi.MEM_HOST
+    if hasattr(buf, "data_ptr") and hasattr(buf, "is_cuda"):
+        if str(buf.dtype) != "torch.uint8" or buf.dim() != 2 or buf.stride(1) != 1:
+            raise ValueError("planes must be 2-D uint8 tensors with contiguous rows")
+        return buf.data_ptr(), buf.stride(0), _capi.MEM_DEVICE if buf.is_cuda else _capi.MEM_HOST
+    raise TypeError(f"unsupported plane buffer type {type(buf)}")
+
+
+@dataclass
+class ObsFrame:
+    """The part of obs_source_frame the ingest reads: a video format name ("NV12", "I420", ...), the frame size and one
+    2-D uint8 buffer (rows x row bytes) per plane — all in host memory or all in device memory."""
+    format: str
+    width: int
+    height: int
+    planes: list
+    timestamp: int = 0
+
+    def to_c(self):
+        c = _capi.ObsFrame()
+        c.format = _capi.VIDEO_FORMATS[self.format]
+        c.width, c.height, c.timestamp = int(self.width), int(self.height), int(self.timestamp)
+        spaces = set()
+        for i, p in enumerate(self.planes):
+            ptr, pitch, space = _plane_info(p)
+            c.data[i], c.linesize[i] = ptr, pitch
+            spaces.add(space)
+        if len(spaces) != 1:
+            raise ValueError("all planes of a frame must live in the same memory space")
+        return c, spaces.pop()
+
+
+class FrameIngest:
+    """lvk::FrameIngest (Modules/OBS-Plugin/Interop/FrameIngest.hpp:28-60): converts between OBS frame layouts and the
+    packed frames the filters take.  `FrameIngest.Select(name)` returns None for a format LVK does not support."""
+
+    def __init__(self, obs_format: str, stream: "Stream | None" = None, device: int = 0):
+        self._obs_format = obs_format
+        self._lib = _capi.load()
+        self._ocl_format = self._lib.lvkb200_video_format_ocl(_capi.VIDEO_FORMATS[obs_format])
+        self.stream = stream or Stream(None, device)
+
+    @staticmethod
+    def Select(obs_format: str, stream: "Stream | None" = None, device: int = 0):
+        if obs_format not in _capi.VIDEO_FORMATS:
+            return None
+        return FrameIngest(obs_format, stream, device)
+
+    def obs_format(self) -> str:
+        return self._obs_format
+
+    def ocl_format(self) -> int:
+        return self._ocl_format
+
+    def upload_obs_frame(self, src: ObsFrame, out=None) -> VideoFrame:
+        """FrameIngest::upload_obs_frame: planes -> packed frame (8UC3, or 8UC1 for Y800)."""
+        if src.format != self._obs_format:
+            raise LvkB200Error(_capi.ERR_INVALID, "src->format == m_OBSFormat")
+        c, space = src.to_c()
+        ch = 1 if self._ocl_format == GRAY else 3
+        if out is None:
+            shape = (src.height, src.width) if ch == 1 else (src.height, src.width, 3)
+            out = np.empty(shape, np.uint8) if space == _capi.MEM_HOST else src.planes[0].new_empty(shape)
+        optr, opitch, oh, ow, och, ospace = _buffer_info(out)
+        if (oh, ow, och) != (src.height, src.width, ch):
+            raise ValueError("output buffer does not match the frame")
+        _capi.check(self._lib.lvkb200_frame_upload(self.stream._h, C.byref(c), space, optr, opitch, ospace))
+        return VideoFrame(out, src.timestamp, self._ocl_format)
+
+    def download_ocl_frame(self, src: VideoFrame, dst: ObsFrame):
+        """FrameIngest::download_ocl_frame: packed frame -> the planes of `dst` (written in place)."""
+        if dst.format != self._obs_format:
+            raise LvkB200Error(_capi.ERR_INVALID, "dst->format == m_OBSFormat")
+        ptr, pitch, h, w, ch, space = _buffer_info(src.data)
+        c, dspace = dst.to_c()
+        _capi.check(self._lib.lvkb200_frame_download(self.stream._h, ptr, pitch, w, h, src.format, space, C.byref(c), dspace))
+        dst.timestamp = src.timestamp
 
 
 @dataclass

@@ -52,6 +52,17 @@ class DeblockSettings(C.Structure):
                 ("filter_scaling", C.c_float)]
 
 
+class ObsFrame(C.Structure):
+    """lvkb200_obs_frame — the fields of obs_source_frame the ingest reads."""
+    _fields_ = [("data", C.c_void_p * 4), ("linesize", C.c_uint32 * 4), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("format", C.c_int32), ("timestamp", C.c_uint64)]
+
+
+# lvkb200_video_format
+VIDEO_FORMATS = {"I420": 0, "I422": 1, "I444": 2, "I40A": 3, "I42A": 4, "YUVA": 5, "NV12": 6, "YVYU": 7, "YUY2": 8,
+                 "UYVY": 9, "AYUV": 10, "Y800": 11, "BGR3": 12}
+
+
 class KeyPoint(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("response", C.c_float), ("class_id", C.c_int32)]
 
@@ -101,6 +112,10 @@ SYMBOLS = {
     "lvkb200_deblock_settings_default": (None, [C.POINTER(DeblockSettings)]),
     "lvkb200_deblock": (C.c_int, [_vp, C.POINTER(DeblockSettings), _vp, _sz, _i, _i, _i, _i, _vp, _sz, _i]),
     "lvkb200_stream_set_deblocking": (C.c_int, [_vp, C.POINTER(DeblockSettings)]),
+    "lvkb200_video_format_ocl": (C.c_int, [_i]),
+    "lvkb200_frame_upload": (C.c_int, [_vp, C.POINTER(ObsFrame), _i, _vp, _sz, _i]),
+    "lvkb200_frame_download": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(ObsFrame), _i]),
+    "lvkb200_stream_submit_obs": (C.c_int, [_vp, C.POINTER(ObsFrame), _i, C.POINTER(ObsFrame), _i, C.POINTER(Result)]),
 }
 
 _lib = None

@@ -1005,6 +1005,8 @@ void lvkb200_stream::release()
         std::fprintf(stderr, " total=%.1f\n", sum / frames);
         host_frames = 0;
     }
+    planes_in.release(); planes_out.release(); obs_frame_in.release(); obs_frame_out.release();
+    format_plan.xtab.release(); format_plan.ytab.release();
     stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
     deblock.release(); deblock_stage.release();

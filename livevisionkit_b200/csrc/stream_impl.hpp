@@ -7,6 +7,7 @@
 #include "common.hpp"
 #include "deblock.hpp"
 #include "fast.hpp"
+#include "formats.hpp"
 #include "host_logic.hpp"
 #include "host_mesh.hpp"
 #include "ingest.hpp"
@@ -31,6 +32,10 @@ struct lvkb200_stream
     lvkb200::DeblockPlan deblock, deblock_stage;
     bool deblock_enabled = false;
     lvkb200_deblock_settings deblock_settings{};
+
+    // ---- FrameIngest (OBS plane layouts <-> packed frames): chroma tap tables + plane / frame scratch
+    lvkb200::FormatPlan format_plan;
+    lvkb200::DeviceBuffer planes_in, planes_out, obs_frame_in, obs_frame_out;
 
     // ---- device-side stages
     lvkb200::IngestPlan ingest;
