@@ -50,6 +50,11 @@ def _select_workload(res, preset="H"):
         RES, WIDTH, HEIGHT = "4k", 3840, 2160
         METRIC = "stabilized_frames_per_second_4k"
         WORKLOAD = WORKLOAD.replace("1080p60", "4K60")
+    if preset == "F":
+        PRESET, PRESET_NAME = "F", "OBS Vector Field"
+        WORKLOAD = WORKLOAD.replace("OBS Homography preset (480x270 detection, FAST grid -> pyramidal LK -> homography RANSAC",
+                                    "OBS Vector Field preset (480x270 detection, FAST grid -> pyramidal LK -> 16x16 "
+                                    "local-motion LSCG mesh")
     if preset == "D":
         PRESET, PRESET_NAME = "D", "library defaults"
         WORKLOAD = WORKLOAD.replace("OBS Homography preset (480x270 detection, FAST grid -> pyramidal LK -> homography RANSAC",
@@ -86,11 +91,13 @@ class _OracleChain:
 
 
 def _gpu_settings(L):
-    return L.StabilizationFilterSettings.obs_homography_preset() if PRESET == "H" else L.StabilizationFilterSettings()
+    S = L.StabilizationFilterSettings
+    return {"H": S.obs_homography_preset, "F": S.obs_field_preset, "D": S}[PRESET]()
 
 
 def _oracle_settings(O):
-    return O.StabilizationSettings.obs_homography_preset() if PRESET == "H" else O.StabilizationSettings()
+    S = O.StabilizationSettings
+    return {"H": S.obs_homography_preset, "F": S.obs_field_preset, "D": S}[PRESET]()
 
 
 def _peaks():
@@ -228,7 +235,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolution", default="1080p", choices=["1080p", "4k"])
-    ap.add_argument("--preset", default="H", choices=["H", "D"])
+    ap.add_argument("--preset", default="H", choices=["H", "D", "F"])
     ap.add_argument("--deblock", action="store_true",
                     help="BASELINE configs[4]: DeblockingFilter -> StabilizationFilter chained (per stream)")
     args = ap.parse_args()

@@ -125,6 +125,8 @@ void lvkb200_set_assert_handler(lvkb200_assert_handler handler);
  * Stabilisation/VSFilter.cpp:269-280) that north_star names (FAST grid -> LK -> homography RANSAC). */
 void lvkb200_settings_default(lvkb200_settings* s);
 void lvkb200_settings_obs_homography(lvkb200_settings* s);
+/* The OBS "Vector Field" subsystem preset (VSFilter.cpp:257-268): 16x16 motion mesh, local motions on. */
+void lvkb200_settings_obs_field(lvkb200_settings* s);
 
 /* ---- lvk::StabilizationFilter ------------------------------------------------------------------------------- */
 

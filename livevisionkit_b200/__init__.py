@@ -62,6 +62,14 @@ class StabilizationFilterSettings:
                                            max_feature_density=0.12, min_feature_density=0.04, accumulation_rate=3.0,
                                            track_local_motions=False, acceptance_threshold=3.0)
 
+    @staticmethod
+    def obs_field_preset() -> "StabilizationFilterSettings":
+        """OBS 'Vector Field' preset — Modules/OBS-Plugin/Sources/Stabilisation/VSFilter.cpp:257-268."""
+        return StabilizationFilterSettings(detection_resolution=(480, 270), detection_regions=(2, 2),
+                                           max_feature_density=0.12, min_feature_density=0.06, accumulation_rate=3.0,
+                                           track_local_motions=True, acceptance_threshold=10.0,
+                                           motion_resolution=(16, 16))
+
     def to_c(self) -> _capi.Settings:
         s = _capi.Settings()
         s.detection_resolution_width, s.detection_resolution_height = self.detection_resolution

@@ -77,6 +77,7 @@ SYMBOLS = {
     "lvkb200_set_assert_handler": (None, [_vp]),
     "lvkb200_settings_default": (None, [C.POINTER(Settings)]),
     "lvkb200_settings_obs_homography": (None, [C.POINTER(Settings)]),
+    "lvkb200_settings_obs_field": (None, [C.POINTER(Settings)]),
     "lvkb200_stream_create": (C.c_int, [_i, C.POINTER(Settings), C.POINTER(_vp)]),
     "lvkb200_stream_destroy": (None, [_vp]),
     "lvkb200_stream_configure": (C.c_int, [_vp, C.POINTER(Settings)]),

@@ -125,6 +125,21 @@ void lvkb200_settings_obs_homography(lvkb200_settings* s)
     s->motion_resolution_width = 2; s->motion_resolution_height = 2;
 }
 
+void lvkb200_settings_obs_field(lvkb200_settings* s)
+{
+    if (!s) return;
+    lvkb200_settings_default(s);
+    // Modules/OBS-Plugin/Sources/Stabilisation/VSFilter.cpp:257-268 ("Vector Field" subsystem)
+    s->detection_resolution_width = 480; s->detection_resolution_height = 270;
+    s->acceptance_threshold = 10.0f;
+    s->track_local_motions = 1;
+    s->motion_resolution_width = 16; s->motion_resolution_height = 16;
+    s->detection_regions_width = 2; s->detection_regions_height = 2;
+    s->max_feature_density = 0.12f;
+    s->min_feature_density = 0.06f;
+    s->accumulation_rate = 3.0f;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 
 lvkb200_status lvkb200_stream_create(int device, const lvkb200_settings* settings, lvkb200_stream** out)

@@ -207,6 +207,13 @@ class StabilizationSettings:
                                      max_feature_density=0.12, min_feature_density=0.04, accumulation_rate=3.0,
                                      track_local_motions=False, acceptance_threshold=3.0, motion_resolution=(2, 2))
 
+    @staticmethod
+    def obs_field_preset() -> "StabilizationSettings":
+        """OBS 'Vector Field' subsystem preset — Modules/OBS-Plugin/Sources/Stabilisation/VSFilter.cpp:257-268."""
+        return StabilizationSettings(detection_resolution=(480, 270), detection_regions=(2, 2),
+                                     max_feature_density=0.12, min_feature_density=0.06, accumulation_rate=3.0,
+                                     track_local_motions=True, acceptance_threshold=10.0, motion_resolution=(16, 16))
+
 
 def _cv_round(x: float) -> int:
     """cv::saturate_cast<int>(float) == cvRound: round half to even."""

@@ -26,15 +26,18 @@ def _kp_array(tr):
     return np.array(tr, dtype=np.float64).reshape(-1, 4)
 
 
-@pytest.mark.parametrize("preset,res,frames", [("H", "1080p", 36), ("D", "720p", 30)])
+@pytest.mark.parametrize("preset,res,frames", [("H", "1080p", 36), ("D", "720p", 30), ("F", "1080p", 30)])
 def test_free_running_vs_oracle(oracle, preset, res, frames):
     import livevisionkit_b200 as L
     from livevisionkit_b200 import _capi as K
     from tools.synth import Clip
 
-    clip = Clip(res, "shake" if preset == "H" else "pan", frames=frames, fps=60 if preset == "H" else 30)
-    so = oracle.StabilizationSettings.obs_homography_preset() if preset == "H" else oracle.StabilizationSettings()
-    sg = L.StabilizationFilterSettings.obs_homography_preset() if preset == "H" else L.StabilizationFilterSettings()
+    clip = Clip(res, "pan" if preset == "D" else "shake", frames=frames, fps=30 if preset == "D" else 60)
+    # H = OBS "Homography" preset, D = library defaults (2x2 mesh, LSCG), F = OBS "Vector Field" preset (16x16 mesh)
+    so = {"H": oracle.StabilizationSettings.obs_homography_preset, "D": oracle.StabilizationSettings,
+          "F": oracle.StabilizationSettings.obs_field_preset}[preset]()
+    sg = {"H": L.StabilizationFilterSettings.obs_homography_preset, "D": L.StabilizationFilterSettings,
+          "F": L.StabilizationFilterSettings.obs_field_preset}[preset]()
     ref = oracle.StabilizationFilter(so)
     flt = L.StabilizationFilter(sg, device=0)
     ref.restart()  # scene quality 1.0 -> the trust factor ramps up immediately, corrections become non-trivial
@@ -109,6 +112,8 @@ def test_free_running_vs_oracle(oracle, preset, res, frames):
     assert stats["max_H_disp"] <= 0.25
     assert min(stats["pix_exact_given_T"] or [1.0]) == 1.0
     assert flt.frame_delay() == ref.frame_delay() == 10
+    if preset == "F":  # mesh path end to end: the per-pixel offsets come from a 512-unknown LSCG solve on both sides
+        assert all(frac >= 0.97 for _, frac in stats["pix_vs_oracle"]), stats["pix_vs_oracle"]
 
 
 def test_host_and_device_frames_agree(oracle):
