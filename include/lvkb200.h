@@ -287,7 +287,8 @@ typedef enum lvkb200_debug_item
     LVKB200_DBG_CORRECTION = 9,      /* float[rows*cols*2]: PathSmoother::next result (+ scene crop if enabled) */
     LVKB200_DBG_WARP_TRANSFORM = 10, /* double[9]: dst->src transform handed to the remap (WarpMesh.cpp:214) */
     LVKB200_DBG_PROPAGATED = 11,     /* lvkb200_keypoint[]: m_TrackedFeatures after propagate (:183-193) */
-    LVKB200_DBG_FAST_COUNTS = 12     /* int32[regions]: raw FAST keypoints per region this frame, -1 = region skipped */
+    LVKB200_DBG_FAST_COUNTS = 12,    /* int32[regions]: raw FAST keypoints per region this frame, -1 = region skipped */
+    LVKB200_DBG_MESH_ITERATIONS = 13 /* int32[1]: conjugate-gradient iterations of the last estimate_local_motions solve */
 } lvkb200_debug_item;
 /* Taps are only recorded while capture is enabled (it adds a device->host copy of the detection image and a
  * synchronisation per frame, so it is off by default — the equivalent of OBS "test mode", VSFilter.cpp:356-383). */

@@ -14,7 +14,7 @@ STAGE_COUNT = 6
 STAGE_NAMES = ("ingest", "pyramid", "fast", "lk", "estimate", "remap")
 
 (DBG_DETECTION_IMAGE, DBG_DETECTED, DBG_LK_MATCHED, DBG_LK_STATUS, DBG_TRACKED, DBG_MATCHED, DBG_INLIERS,
- DBG_HOMOGRAPHY, DBG_MOTION, DBG_CORRECTION, DBG_WARP_TRANSFORM, DBG_PROPAGATED, DBG_FAST_COUNTS) = range(13)
+ DBG_HOMOGRAPHY, DBG_MOTION, DBG_CORRECTION, DBG_WARP_TRANSFORM, DBG_PROPAGATED, DBG_FAST_COUNTS, DBG_MESH_ITERATIONS) = range(14)
 
 
 class Settings(C.Structure):

@@ -546,16 +546,14 @@ lvkb200_status lvkb200_estimate_local_motions(lvkb200_stream* s, const float* tr
 {
     LVKB_REQUIRE(s != nullptr && tracked != nullptr && matched != nullptr && mesh_state != nullptr &&
                  offsets_out != nullptr && mask != nullptr);
-    MeshSolver solver;
-    solver.configure(s->settings);
+    LVKB_CUDA(cudaSetDevice(s->device));
     const size_t elems = static_cast<size_t>(2) * s->settings.motion_resolution_width * s->settings.motion_resolution_height;
-    std::memcpy(solver.state().data(), mesh_state, sizeof(float) * elems);
     std::vector<float> a(tracked, tracked + 2 * static_cast<size_t>(count));
     std::vector<float> b(matched, matched + 2 * static_cast<size_t>(count));
     Mesh offsets;
     std::vector<uint8_t> m;
-    solver.estimate(a, b, offsets, m);
-    std::memcpy(mesh_state, solver.state().data(), sizeof(float) * elems);
+    // >= 64 unknowns: k_mesh_cgls on the device; the default 2x2 mesh: host solver (host_mesh.hpp)
+    LVKB_TRY(s->run_local_motions(a, b, mesh_state, offsets, m));
     std::memcpy(offsets_out, offsets.data(), sizeof(float) * elems);
     std::memcpy(mask, m.data(), count);
     return LVKB200_OK;

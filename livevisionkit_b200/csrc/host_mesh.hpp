@@ -3,7 +3,8 @@
 // The system is tiny for the library default (2x2 mesh: 8 unknowns, 8 + 2N rows with <= 4 non-zeros each), so the
 // preconditioned CG on the normal equations (Eigen::LeastSquaresConjugateGradient semantics: diagonal
 // preconditioner, tolerance FLT_EPSILON, max 2*cols iterations, warm start) runs on the host in float32.
-// TODO(round 2): single-CTA device CGLS (k_mesh_cgls) for the 16x16 "Vector Field" preset.
+// Larger meshes (the 16x16 "Vector Field" preset) are solved on the device by k_mesh_cgls (mesh.cu), which takes its
+// static rows and scalars from this class (export_static / device_params) and hands the solution back (adopt_state).
 #pragma once
 
 #include <cfloat>
@@ -110,7 +111,13 @@ public:
             const float err = std::fabs(x - b[rxi]) + std::fabs(y - b[ryi]);
             inliers[i] = err < acceptance ? 1 : 0;
         }
-        offsets.resize(static_cast<size_t>(ncols));
+        offsets_from_state(offsets);
+    }
+
+    // The motion mesh as normalised offsets (FrameTracker.cpp:303-318) from the current solution.
+    void offsets_from_state(Mesh& offsets) const
+    {
+        offsets.resize(static_cast<size_t>(2) * cols * rows);
         for (int r = 0; r < rows; r++)
             for (int c = 0; c < cols; c++)
             {
@@ -120,6 +127,29 @@ public:
                 offsets[k + 1] = (ay - mesh[k + 1]) / region_h;
             }
     }
+
+    // ---- hand-over to the device solver (mesh.cu)
+    int unknowns() const { return 2 * cols * rows; }
+    int mesh_cols() const { return cols; }
+    int mesh_rows() const { return rows; }
+    float temporal_weight() const { return ts; }
+    float acceptance_threshold() const { return acceptance; }
+    float key_w() const { return vg.kw; }
+    float key_h() const { return vg.kh; }
+    // Bumped whenever generate_constraints() ran: the device copy of the static rows is stale.
+    unsigned generation() const { return static_generation; }
+    // The similarity rows (everything static except the diagonal temporal rows), four non-zeros each.
+    void export_static(std::vector<int>& col4, std::vector<float>& val4) const
+    {
+        col4.clear(); val4.clear();
+        for (int r = 2 * cols * rows; r < static_count; r++)
+            for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; k++)
+            {
+                col4.push_back(A.col[k]);
+                val4.push_back(A.val[k]);
+            }
+    }
+    void adopt_state(const float* solution) { std::copy(solution, solution + mesh.size(), mesh.begin()); }
 
 private:
     void add_row4(int c0, float v0, int c1, float v1, int c2, float v2, int c3, float v3)
@@ -172,6 +202,7 @@ private:
                 A.add(i00 + 1, -weight); A.add(i10, w1); A.add(i10 + 1, weight); A.add(i11, -w1); A.end_row();
             }
         static_count = A.rows();
+        static_generation++;
     }
 
     void spmv(const std::vector<float>& x, std::vector<float>& y) const
@@ -250,6 +281,7 @@ private:
     }
 
     int cols = 0, rows = 0, static_count = 0;
+    unsigned static_generation = 0;
     float ts = 1.f, ls = 20.f, acceptance = 8.f, region_w = 0, region_h = 0, grid_w = -1, grid_h = -1;
     VGrid vg;
     SparseRows A;

@@ -1,0 +1,502 @@
+// K6c — FrameTracker::estimate_local_motions (LiveVisionKit/Vision/FrameTracker.cpp:200-321) on the device.
+//
+// The reference assembles a sparse system  A x = b  per frame and hands it to Eigen::LeastSquaresConjugateGradient
+// (diagonal preconditioner, tolerance FLT_EPSILON, at most 2*cols iterations, warm start from the previous mesh):
+//   rows 0 .. n-1          temporal:    ts * x[k]                         = ts * x_prev[k]      (FrameTracker.cpp:380-400)
+//   rows n .. n+S-1        similarity:  four non-zeros per row            = 0                   (FrameTracker.cpp:402-457)
+//   rows n+S+2i, n+S+2i+1  feature i:   bilinear weights of its mesh cell = matched point i     (FrameTracker.cpp:236-262)
+// For the OBS "Vector Field" preset (16x16 vertices, n = 512 unknowns, ~800 features) that is ~135 CG iterations of two
+// sparse products over ~3 000 rows: 2.7 ms in the host solver, i.e. 20x everything else on the frame's critical path.
+//
+// Here: ONE CTA keeps the whole system in shared memory and iterates with four barriers per CG step.
+//   * A p   : thread per row unit (a feature = one unit = its x and y row, which share their four weights);
+//   * A^T r : thread per unknown; the feature part is gathered CELL-wise (the features of the <= 4 cells around a
+//             vertex, found through a per-frame counting sort by cell), so no atomics and a fixed summation order;
+//   * dot products: warp shuffles + one shared round, every thread ends up with the total (no broadcast barrier).
+// The kernel follows k_compact_swap_erase on the tracking stream, so the host never touches the system: it reads
+// the mesh, the inlier mask and the LK results from mapped pinned memory after one stream synchronisation.
+// Arithmetic: float32 as in the reference; summation ORDER differs from Eigen's (and from the sequential CPU
+// restatement), so results agree to rounding (tests: <= 1e-3 px on the mesh, identical masks), not bit-wise.
+// Compiled with --fmad=false: the weights / the acceptance test are the reference's unfused expressions.
+
+#include <cfloat>
+#include <cstring>
+
+#include "mesh.hpp"
+
+namespace lvkb200
+{
+namespace
+{
+
+constexpr int T = MESH_CGLS_THREADS;
+constexpr int NW = T / 32;
+
+struct MeshSys
+{
+    int cols, rows;  // vertices
+    int n;           // unknowns = 2 * cols * rows
+    int S;           // similarity rows
+    int csc_nnz;     // non-zeros of the similarity rows (= 4 S), column-major copy
+    int cap;         // feature capacity the shared-memory carve-up was sized for
+    const uint16_t* sim_col;  // 4 per similarity row
+    const float* sim_val;
+    const int* csc_ptr;       // n + 1
+    const uint16_t* csc_row;  // row index (absolute, >= n)
+    const float* csc_val;
+};
+
+// Shared-memory carve-up (also evaluated on the host to size the launch).
+struct Carve
+{
+    size_t x, p, s, invd, r, q, fw, sim_val, csc_val, csc_ptr, cell_start, cell_cnt, sim_col, csc_row, fcell, forder,
+        red, total;
+    __host__ __device__ Carve(int n, int S, int nnz, int cells, int cap)
+    {
+        size_t o = 0;
+        auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
+        const size_t m = (size_t)n + S + 2 * (size_t)cap;
+        x = take(4 * (size_t)n); p = take(4 * (size_t)n); s = take(4 * (size_t)n); invd = take(4 * (size_t)n);
+        r = take(4 * m); q = take(4 * m);
+        fw = take(16 * (size_t)cap);
+        sim_val = take(16 * (size_t)S); csc_val = take(4 * (size_t)nnz);
+        csc_ptr = take(4 * ((size_t)n + 1)); cell_start = take(4 * ((size_t)cells + 1)); cell_cnt = take(4 * (size_t)cells);
+        sim_col = take(8 * (size_t)S); csc_row = take(2 * (size_t)nnz);
+        fcell = take(2 * (size_t)cap + 8); forder = take(2 * (size_t)cap);
+        red = take(2 * NW * sizeof(float2));
+        total = o;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum of (a, b) over the CTA, returned to EVERY thread.  `slot` (NW float2) must not be rewritten before all threads
+// have passed another barrier (the caller alternates two slots).
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* slot)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) slot[wid] = make_float2(a, b);
+    __syncthreads();
+    static_assert(NW <= 32, "one shuffle round covers the warp totals");
+    const float2 t = slot[lane < NW ? lane : 0];
+    return make_float2(warp_sum(lane < NW ? t.x : 0.0f), warp_sum(lane < NW ? t.y : 0.0f));
+}
+
+struct Ctx
+{
+    const MeshSys& sys;
+    float *x, *p, *s, *invd, *r, *q;
+    float4* fw;
+    const float *sim_val, *csc_val;
+    const int *csc_ptr, *cell_start;
+    const uint16_t *sim_col, *csc_row, *fcell, *forder;
+    int N, n, S, units;
+    float ts;
+};
+
+// out[rows] = A v for the row units this thread owns (unit u: temporal row u | similarity row | feature = two rows).
+// ASSIGN(row, value) stores one row's product.
+template <typename Assign>
+__device__ __forceinline__ void spmv_rows(const Ctx& c, const float* __restrict__ v, Assign assign)
+{
+    const int cols = c.sys.cols;
+    for (int u = threadIdx.x; u < c.units; u += T)
+    {
+        if (u < c.n)
+            assign(u, c.ts * v[u]);
+        else if (u < c.n + c.S)
+        {
+            const int k = u - c.n;
+            const ushort4 ci = reinterpret_cast<const ushort4*>(c.sim_col)[k];
+            const float4 cv = reinterpret_cast<const float4*>(c.sim_val)[k];
+            assign(u, cv.x * v[ci.x] + cv.y * v[ci.y] + cv.z * v[ci.z] + cv.w * v[ci.w]);
+        }
+        else
+        {
+            const int f = u - c.n - c.S;
+            const float4 w = c.fw[f];
+            const int cell = c.fcell[f];
+            const int cy = cell / (cols - 1), cx = cell - cy * (cols - 1);
+            const int i00 = 2 * (cy * cols + cx), i10 = i00 + 2, i01 = i00 + 2 * cols, i11 = i01 + 2;
+            const int row = c.n + c.S + 2 * f;
+            assign(row, w.x * v[i00] + w.y * v[i01] + w.z * v[i11] + w.w * v[i10]);
+            assign(row + 1, w.x * v[i00 + 1] + w.y * v[i01 + 1] + w.z * v[i11 + 1] + w.w * v[i10 + 1]);
+        }
+    }
+}
+
+// (A^T u)[col] for one unknown.  SQUARE: the column's squared norm instead (u ignored) -> the preconditioner.
+template <bool SQUARE>
+__device__ __forceinline__ float spmv_t_col(const Ctx& c, const float* __restrict__ u, int col)
+{
+    const int cols = c.sys.cols, rows = c.sys.rows, gw = cols - 1, gh = rows - 1;
+    float acc = SQUARE ? c.ts * c.ts : c.ts * u[col];
+    for (int k = c.csc_ptr[col]; k < c.csc_ptr[col + 1]; k++)
+    {
+        const float a = c.csc_val[k];
+        acc += SQUARE ? a * a : a * u[c.csc_row[k]];
+    }
+    const int vtx = col >> 1, comp = col & 1;
+    const int vy = vtx / cols, vx = vtx - vy * cols;
+    const float* fwf = reinterpret_cast<const float*>(c.fw);
+    const int base = c.n + c.S + comp;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+        // the vertex is corner i00 of cell (vx, vy) [w0], i10 of (vx-1, vy) [w3], i01 of (vx, vy-1) [w1],
+        // i11 of (vx-1, vy-1) [w2]
+        const int dx = (q & 1) ? -1 : 0, dy = (q & 2) ? -1 : 0;
+        const int wsel = (q == 0) ? 0 : (q == 1) ? 3 : (q == 2) ? 1 : 2;
+        const int cx = vx + dx, cy = vy + dy;
+        if (cx < 0 || cy < 0 || cx >= gw || cy >= gh) continue;
+        const int cell = cy * gw + cx;
+        for (int k = c.cell_start[cell]; k < c.cell_start[cell + 1]; k++)
+        {
+            const int f = c.forder[k];
+            const float a = fwf[4 * f + wsel];
+            acc += SQUARE ? a * a : a * u[base + 2 * f];
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void copy16(const uint8_t* src, uint8_t* dst, int bytes)
+{
+    for (int i = threadIdx.x; i < (bytes + 15) / 16; i += T)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+__global__ void __launch_bounds__(T, 1)
+    k_mesh_cgls(MeshSys sys, MeshSolveParams prm, const float2* __restrict__ src, const float2* __restrict__ dst,
+                const int* __restrict__ n_ptr, const TrackParams* __restrict__ tp, float* __restrict__ state,
+                uint8_t* __restrict__ mask, uint8_t* __restrict__ res_dev, uint8_t* __restrict__ res_host,
+                TrackOutCopy out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int cells = (sys.cols - 1) * (sys.rows - 1);
+    const Carve cv(sys.n, sys.S, sys.csc_nnz, cells, sys.cap);
+    float* const x = reinterpret_cast<float*>(smem + cv.x);
+    float* const p = reinterpret_cast<float*>(smem + cv.p);
+    float* const s = reinterpret_cast<float*>(smem + cv.s);
+    float* const invd = reinterpret_cast<float*>(smem + cv.invd);
+    float* const r = reinterpret_cast<float*>(smem + cv.r);
+    float* const q = reinterpret_cast<float*>(smem + cv.q);
+    float4* const fw = reinterpret_cast<float4*>(smem + cv.fw);
+    float* const sim_val = reinterpret_cast<float*>(smem + cv.sim_val);
+    float* const csc_val = reinterpret_cast<float*>(smem + cv.csc_val);
+    int* const csc_ptr = reinterpret_cast<int*>(smem + cv.csc_ptr);
+    int* const cell_start = reinterpret_cast<int*>(smem + cv.cell_start);
+    int* const cell_cnt = reinterpret_cast<int*>(smem + cv.cell_cnt);
+    uint16_t* const sim_col = reinterpret_cast<uint16_t*>(smem + cv.sim_col);
+    uint16_t* const csc_row = reinterpret_cast<uint16_t*>(smem + cv.csc_row);
+    uint16_t* const fcell = reinterpret_cast<uint16_t*>(smem + cv.fcell);
+    uint16_t* const forder = reinterpret_cast<uint16_t*>(smem + cv.forder);
+    float2* const red = reinterpret_cast<float2*>(smem + cv.red);
+
+    const int tid = threadIdx.x;
+    const int n = sys.n, S = sys.S, cols = sys.cols, rows = sys.rows, gw = cols - 1, gh = rows - 1;
+    const int N = min(*n_ptr, sys.cap);
+    MeshSolveResult* const hdr = reinterpret_cast<MeshSolveResult*>(res_dev);
+    float* const mesh_out = reinterpret_cast<float*>(res_dev + sizeof(MeshSolveResult));
+    int iterations = 0;
+    const bool solve = N >= prm.min_samples;  // FrameTracker.cpp:152-156: too few samples -> no estimate at all
+
+    if (solve)
+    {
+        // ---- stage the static system, the warm start and this frame's features
+        for (int i = tid; i < n; i += T) x[i] = state[i];
+        for (int i = tid; i <= n; i += T) csc_ptr[i] = sys.csc_ptr[i];
+        for (int i = tid; i < 4 * S; i += T) { sim_col[i] = sys.sim_col[i]; sim_val[i] = sys.sim_val[i]; }
+        for (int i = tid; i < sys.csc_nnz; i += T) { csc_row[i] = sys.csc_row[i]; csc_val[i] = sys.csc_val[i]; }
+        for (int i = tid; i < cells; i += T) cell_cnt[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += T)
+        {
+            // FrameTracker.cpp:236-262: mesh cell of the tracked point and its barycentric weights (Math.tpp:247-265)
+            const float2 t = src[i];
+            int kx = (int)max(min(__float2ll_rz(t.x / prm.key_w), (long long)INT_MAX), (long long)INT_MIN);
+            int ky = (int)max(min(__float2ll_rz(t.y / prm.key_h), (long long)INT_MAX), (long long)INT_MIN);
+            kx = min(max(kx, 0), gw - 1);
+            ky = min(max(ky, 0), gh - 1);
+            const float p0x = (float)kx * prm.key_w, p0y = (float)ky * prm.key_h;
+            const float p1x = (float)(kx + 1) * prm.key_w, p1y = (float)(ky + 1) * prm.key_h;
+            const float rx = fminf(p0x, p1x), ry = fminf(p0y, p1y);
+            const float rw = fmaxf(p0x, p1x) - rx, rh = fmaxf(p0y, p1y) - ry;
+            const float inv_area = 1.0f / (rw * rh);
+            const float x2 = rx + rw, y2 = ry + rh;
+            const float rx1 = x2 - t.x, ry1 = y2 - t.y, rx2 = t.x - rx, ry2 = t.y - ry;
+            fw[i] = make_float4(rx1 * ry1 * inv_area, rx1 * ry2 * inv_area, rx2 * ry2 * inv_area, rx2 * ry1 * inv_area);
+            const int cell = ky * gw + kx;
+            fcell[i] = (uint16_t)cell;
+            atomicAdd(&cell_cnt[cell], 1);
+        }
+        __syncthreads();
+        // exclusive scan of the cell populations (<= a few hundred cells: one warp, 32 cells per step)
+        if (tid < 32)
+        {
+            int carry = 0;
+            for (int c0 = 0; c0 < cells; c0 += 32)
+            {
+                const int c = c0 + tid;
+                const int v = c < cells ? cell_cnt[c] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t2;
+                }
+                if (c < cells) cell_start[c] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) cell_start[cells] = carry;
+        }
+        __syncthreads();
+        // stable placement: feature i goes behind the features j < i of its cell (fixed summation order, no atomics)
+        for (int i = tid; i < N; i += T)
+        {
+            const uint16_t me = fcell[i];
+            int rank = 0;
+            for (int j = 0; j < i; j++) rank += (fcell[j] == me);
+            forder[cell_start[me] + rank] = (uint16_t)i;
+        }
+        __syncthreads();
+
+        Ctx c{sys, x, p, s, invd, r, q, fw, sim_val, csc_val, csc_ptr, cell_start, sim_col, csc_row, fcell, forder,
+              N, n, S, n + S + N, prm.temporal_weight};
+        const float ts = prm.temporal_weight;
+
+        // ---- LeastSquareDiagonalPreconditioner, residual = b - A x, z = A^T b
+        // q <- b  (temporal rows: ts * x_prev, similarity rows: 0, feature rows: the matched point)
+        for (int u = tid; u < c.units; u += T)
+        {
+            if (u < n) q[u] = ts * x[u];
+            else if (u < n + S) q[u] = 0.0f;
+            else
+            {
+                const float2 m = dst[u - n - S];
+                q[n + S + 2 * (u - n - S)] = m.x;
+                q[n + S + 2 * (u - n - S) + 1] = m.y;
+            }
+        }
+        spmv_rows(c, x, [&](int row, float v) { r[row] = v; });  // A x (own rows, read back by the same thread below)
+        __syncthreads();
+        float zz = 0.0f;
+        for (int col = tid; col < n; col += T)
+        {
+            const float d = spmv_t_col<true>(c, nullptr, col);
+            invd[col] = d > 0.0f ? 1.0f / d : 1.0f;
+            const float z = spmv_t_col<false>(c, q, col);  // A^T b
+            zz += z * z;
+        }
+        const float rhs_norm2 = block_sum2(zz, 0.0f, red).x;
+        // residual = b - A x
+        for (int i = tid; i < n + S + 2 * N; i += T) r[i] = q[i] - r[i];
+        __syncthreads();
+
+        if (rhs_norm2 == 0.0f)
+        {
+            for (int i = tid; i < n; i += T) x[i] = 0.0f;
+        }
+        else
+        {
+            const float threshold = FLT_EPSILON * FLT_EPSILON * rhs_norm2;
+            float ss = 0.0f, sz = 0.0f;
+            for (int col = tid; col < n; col += T)
+            {
+                const float v = spmv_t_col<false>(c, r, col);
+                s[col] = v;
+                const float z = invd[col] * v;
+                p[col] = z;
+                ss += v * v;
+                sz += v * z;
+            }
+            const float2 t0 = block_sum2(ss, sz, red + NW);
+            float abs_new = t0.y;
+            if (!(t0.x < threshold))
+            {
+                __syncthreads();  // p complete
+                const int max_iters = 2 * n;
+                while (iterations < max_iters)
+                {
+                    // q = A p ; alpha = abs_new / |q|^2
+                    float qq = 0.0f;
+                    spmv_rows(c, p, [&](int row, float v) { q[row] = v; qq += v * v; });
+                    const float alpha = abs_new / block_sum2(qq, 0.0f, red).x;
+                    // x += alpha p ; residual -= alpha q  (q rows are this thread's own)
+                    for (int i = tid; i < n; i += T) x[i] += alpha * p[i];
+                    for (int u = tid; u < c.units; u += T)
+                    {
+                        if (u < n + S) r[u] -= alpha * q[u];
+                        else
+                        {
+                            const int row = n + S + 2 * (u - n - S);
+                            r[row] -= alpha * q[row];
+                            r[row + 1] -= alpha * q[row + 1];
+                        }
+                    }
+                    __syncthreads();
+                    // s = A^T residual ; z = M^-1 s
+                    ss = 0.0f; sz = 0.0f;
+                    for (int col = tid; col < n; col += T)
+                    {
+                        const float v = spmv_t_col<false>(c, r, col);
+                        s[col] = v;
+                        ss += v * v;
+                        sz += v * (invd[col] * v);
+                    }
+                    const float2 t1 = block_sum2(ss, sz, red + NW);
+                    if (t1.x < threshold) break;
+                    const float beta = t1.y / abs_new;
+                    abs_new = t1.y;
+                    for (int col = tid; col < n; col += T) p[col] = invd[col] * s[col] + beta * p[col];
+                    iterations++;
+                    __syncthreads();
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- results: new state, mesh copy for the host, inlier mask (FrameTracker.cpp:279-300)
+        for (int i = tid; i < n; i += T)
+        {
+            const float v = x[i];
+            state[i] = v;
+            mesh_out[i] = v;
+        }
+        for (int i = tid; i < N; i += T)
+        {
+            const float4 w = fw[i];
+            const int cell = fcell[i];
+            const int cy = cell / gw, cx = cell - cy * gw;
+            const int i00 = 2 * (cy * cols + cx), i10 = i00 + 2, i01 = i00 + 2 * cols, i11 = i01 + 2;
+            // row product in the reference's triplet order i00, i01, i11, i10
+            const float ex = ((w.x * x[i00] + w.y * x[i01]) + w.z * x[i11]) + w.w * x[i10];
+            const float ey = ((w.x * x[i00 + 1] + w.y * x[i01 + 1]) + w.z * x[i11 + 1]) + w.w * x[i10 + 1];
+            const float2 m = dst[i];
+            mask[i] = (fabsf(ex - m.x) + fabsf(ey - m.y)) < prm.acceptance ? 1 : 0;
+        }
+    }
+    if (tid == 0)
+    {
+        hdr->solved = solve ? 1 : 0;
+        hdr->iterations = iterations;
+        hdr->n = N;
+        hdr->pad = 0;
+    }
+    __syncthreads();  // the block's global writes (mask, header, mesh) are visible to all of its threads
+    if (res_host) copy16(res_dev, res_host, (int)sizeof(MeshSolveResult) + (solve ? 4 * n : 0));
+    if (out.host)
+    {
+        const int tracked = tp->n;
+        copy16(out.dev, out.host, tracked * (int)sizeof(float2));
+        copy16(out.dev + out.off_status, out.host + out.off_status, tracked);
+        if (solve) copy16(out.dev + out.off_mask, out.host + out.off_mask, N);
+    }
+}
+
+}  // namespace
+
+bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaStream_t cs, cudaError_t* err)
+{
+    *err = cudaSuccess;
+    const int n = 2 * sys.mesh_cols * sys.mesh_rows, S = sys.rows(), nnz = 4 * S;
+    const int cells = (sys.mesh_cols - 1) * (sys.mesh_rows - 1);
+    n_unknowns = 0;
+    if (sys.mesh_cols < 2 || sys.mesh_rows < 2 || n + S > 65535 || feature_capacity > 65535 || cells > 65535) return false;
+    const Carve cv(n, S, nnz, cells, feature_capacity);
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (cv.total > static_cast<size_t>(max_smem)) return false;
+    if ((*err = cudaFuncSetAttribute(k_mesh_cgls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total)) != cudaSuccess)
+        return false;
+
+    // column-major copy of the similarity rows (stable: ascending row inside every column)
+    std::vector<int> ptr(n + 1, 0);
+    for (int k = 0; k < nnz; k++) ptr[sys.col[k] + 1]++;
+    for (int c = 0; c < n; c++) ptr[c + 1] += ptr[c];
+    std::vector<uint16_t> crow(nnz), scol(nnz);
+    std::vector<float> cval(nnz);
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int r = 0; r < S; r++)
+        for (int k = 4 * r; k < 4 * r + 4; k++)
+        {
+            const int at = fill[sys.col[k]]++;
+            crow[at] = static_cast<uint16_t>(n + r);
+            cval[at] = sys.val[k];
+            scol[k] = static_cast<uint16_t>(sys.col[k]);
+        }
+
+    // one blob: [sim_val f32 x nnz | csc_val f32 x nnz | csc_ptr i32 x (n+1) | sim_col u16 x nnz | csc_row u16 x nnz]
+    const size_t o_simval = 0, o_cscval = o_simval + 4 * (size_t)nnz, o_ptr = o_cscval + 4 * (size_t)nnz,
+                 o_simcol = o_ptr + 4 * ((size_t)n + 1), o_cscrow = o_simcol + 2 * (size_t)nnz,
+                 bytes = o_cscrow + 2 * (size_t)nnz;
+    std::vector<uint8_t> blob(bytes);
+    std::memcpy(blob.data() + o_simval, sys.val.data(), 4 * (size_t)nnz);
+    std::memcpy(blob.data() + o_cscval, cval.data(), 4 * (size_t)nnz);
+    std::memcpy(blob.data() + o_ptr, ptr.data(), 4 * ((size_t)n + 1));
+    std::memcpy(blob.data() + o_simcol, scol.data(), 2 * (size_t)nnz);
+    std::memcpy(blob.data() + o_cscrow, crow.data(), 2 * (size_t)nnz);
+    if ((*err = d_static.ensure(bytes + 16)) != cudaSuccess) return false;
+    if ((*err = d_state.ensure(4 * (size_t)n)) != cudaSuccess) return false;
+    const size_t out_bytes = sizeof(MeshSolveResult) + 4 * (size_t)n + 16;
+    if ((*err = d_out.ensure(out_bytes)) != cudaSuccess) return false;
+    if ((*err = h_out.ensure(out_bytes)) != cudaSuccess) return false;
+    std::memset(h_out.ptr, 0, out_bytes);
+    // synchronous, pageable source: configure is not on the per-frame path
+    if ((*err = cudaStreamSynchronize(cs)) != cudaSuccess) return false;
+    if ((*err = cudaMemcpy(d_static.ptr, blob.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return false;
+    const bool resized = mesh_cols != sys.mesh_cols || mesh_rows != sys.mesh_rows;
+    mesh_cols = sys.mesh_cols; mesh_rows = sys.mesh_rows;
+    n_sim = S; csc_nnz = nnz; capacity = feature_capacity; smem_bytes = cv.total;
+    n_unknowns = n;
+    if (resized && (*err = cudaMemset(d_state.ptr, 0, 4 * (size_t)n)) != cudaSuccess) { n_unknowns = 0; return false; }
+    return true;
+}
+
+cudaError_t MeshCgls::reset_state(cudaStream_t cs)
+{
+    if (!ready()) return cudaSuccess;
+    return cudaMemsetAsync(d_state.ptr, 0, 4 * (size_t)n_unknowns, cs);
+}
+
+cudaError_t MeshCgls::set_state(cudaStream_t cs, const float* mesh)
+{
+    cudaError_t e = cudaStreamSynchronize(cs);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(d_state.ptr, mesh, 4 * (size_t)n_unknowns, cudaMemcpyHostToDevice);
+}
+
+cudaError_t MeshCgls::launch(cudaStream_t cs, const MeshSolveParams& prm, const float2* d_src, const float2* d_dst,
+                             const int* d_n, const TrackParams* d_params, uint8_t* d_mask, const TrackOutCopy& out)
+{
+    const uint8_t* b = d_static.as<uint8_t>();
+    const size_t nnz = static_cast<size_t>(csc_nnz), n = static_cast<size_t>(n_unknowns);
+    MeshSys sys{};
+    sys.cols = mesh_cols; sys.rows = mesh_rows; sys.n = n_unknowns; sys.S = n_sim; sys.csc_nnz = csc_nnz; sys.cap = capacity;
+    sys.sim_val = reinterpret_cast<const float*>(b);
+    sys.csc_val = reinterpret_cast<const float*>(b + 4 * nnz);
+    sys.csc_ptr = reinterpret_cast<const int*>(b + 8 * nnz);
+    sys.sim_col = reinterpret_cast<const uint16_t*>(b + 8 * nnz + 4 * (n + 1));
+    sys.csc_row = reinterpret_cast<const uint16_t*>(b + 8 * nnz + 4 * (n + 1) + 2 * nnz);
+    k_mesh_cgls<<<1, T, smem_bytes, cs>>>(sys, prm, d_src, d_dst, d_n, d_params, d_state.as<float>(), d_mask,
+                                          d_out.as<uint8_t>(), h_out.device_view<uint8_t>(), out);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+void MeshCgls::release()
+{
+    d_static.release(); d_state.release(); d_out.release(); h_out.release();
+    n_unknowns = 0; mesh_cols = mesh_rows = 0;
+}
+
+}  // namespace lvkb200

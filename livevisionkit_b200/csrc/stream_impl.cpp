@@ -69,7 +69,11 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     // StabilizationFilter.cpp:51-52: disabling the stabilization resets the context
     if (configured && settings.stabilize_output && !s.stabilize_output) LVKB_TRY(reset_context());
 
-    if (!configured) host_trace = std::getenv("LVKB200_HOST_TRACE") != nullptr;
+    if (!configured)
+    {
+        host_trace = std::getenv("LVKB200_HOST_TRACE") != nullptr;
+        if (const char* e = std::getenv("LVKB200_MESH_DEVICE_MIN")) mesh_device_min_unknowns = std::atoi(e);
+    }
     const bool det_changed = !configured || s.detection_resolution_width != settings.detection_resolution_width ||
                              s.detection_resolution_height != settings.detection_resolution_height;
     settings = s;
@@ -93,6 +97,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
 
     grid.configure(s);
     mesh_solver.configure(s);
+    mesh_device_unfit = false;  // re-evaluated by prepare_mesh_device for the new mesh
     det_w = s.detection_resolution_width;
     det_h = s.detection_resolution_height;
     if (det_changed)
@@ -128,6 +133,7 @@ lvkb200_status lvkb200_stream::reset_context()
     grid.reset();
     frame_initialized = false;
     mesh_solver.restart();
+    if (mesh_device.ready()) LVKB_CUDA(mesh_device.reset_state(cs));
     smoother.restart();
     return LVKB200_OK;
 }
@@ -306,9 +312,17 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
     }
     if (with_events) stage_begin(ST_LK);
     LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], (n + 3) / 4 * 4, io, inline_points ? &lk_pack : nullptr));
+    if (!global && mesh_on_device())
+    {
+        // swap-erase compaction -> k_mesh_cgls, which also delivers the LK results
+        if (with_events) { stage_end(ST_LK); stage_begin(ST_ESTIMATE); }
+        LVKB_TRY(launch_mesh_device());
+        if (with_events) stage_end(ST_ESTIMATE);
+        return LVKB200_OK;
+    }
     if (!global)
     {
-        // no estimator kernel follows (local motions are solved on the host): one small CTA delivers the LK results
+        // no estimator kernel follows (small meshes are solved on the host): one small CTA delivers the LK results
         TrackOutCopy out{};
         out.dev = d_track_out.as<uint8_t>();
         out.host = hout;
@@ -316,6 +330,54 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
         LVKB_TRY(track_out_copy(cs, d_params.as<TrackParams>(), out));
     }
     if (with_events) stage_end(ST_LK);
+    return LVKB200_OK;
+}
+
+// Local-motion estimator on the device (FrameTracker.cpp:200-321): fast_filter compaction, then the whole LSCG solve
+// in one CTA; its last step copies mesh, mask and LK results into mapped pinned host memory.
+lvkb200_status lvkb200_stream::prepare_mesh_device()
+{
+    if (mesh_device.ready() && mesh_device_generation == mesh_solver.generation() &&
+        mesh_device_capacity == point_capacity)
+        return LVKB200_OK;
+    MeshStaticRows sys;
+    sys.mesh_cols = mesh_solver.mesh_cols();
+    sys.mesh_rows = mesh_solver.mesh_rows();
+    mesh_solver.export_static(sys.col, sys.val);
+    cudaError_t err = cudaSuccess;
+    const bool had_state = mesh_device.ready() && mesh_device.unknowns() == mesh_solver.unknowns();
+    if (!mesh_device.configure(sys, point_capacity, cs, &err))
+    {
+        LVKB_CUDA(err);
+        mesh_device_unfit = true;  // too large for one CTA: the host solver takes over
+        return LVKB200_OK;
+    }
+    // a fresh device solver starts from the host's current solution (zeros after a restart / resize)
+    if (!had_state) LVKB_CUDA(mesh_device.set_state(cs, mesh_solver.state().data()));
+    mesh_device_generation = mesh_solver.generation();
+    mesh_device_capacity = point_capacity;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::launch_mesh_device()
+{
+    TrackOutCopy out{};
+    out.dev = d_track_out.as<uint8_t>();
+    out.host = h_track_out.device_view<uint8_t>();
+    out.off_status = static_cast<uint32_t>(off_status);
+    out.off_mask = static_cast<uint32_t>(off_mask);
+    out.off_result = static_cast<uint32_t>(off_result);
+    LVKB_REQUIRE(out.host != nullptr);
+    const TrackParams* prm = d_params.as<TrackParams>();
+    LVKB_TRY(compact_swap_erase(cs, d_pts_prev.as<float2>(), d_pts_next(), d_status(), prm, d_src.as<float2>(),
+                                d_dst.as<float2>(), d_perm.as<int>(), d_removed.as<int>(), d_count.as<int>()));
+    MeshSolveParams mp{};
+    mp.temporal_weight = mesh_solver.temporal_weight();
+    mp.acceptance = mesh_solver.acceptance_threshold();
+    mp.key_w = mesh_solver.key_w();
+    mp.key_h = mesh_solver.key_h();
+    mp.min_samples = static_cast<int>(settings.min_motion_samples);
+    LVKB_CUDA(mesh_device.launch(cs, mp, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(), prm, d_mask(), out));
     return LVKB200_OK;
 }
 
@@ -348,6 +410,7 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
 {
     const int n = static_cast<int>(pts.size() / 2);
     LVKB_TRY(ensure_points(n));
+    if (!global && mesh_on_device()) LVKB_TRY(prepare_mesh_device());
     TrackParams& hp = lk_pack.prm;
     hp.n = n;
     hp.model = model;
@@ -447,6 +510,67 @@ lvkb200_status lvkb200_stream::run_homography(const std::vector<float>& tracked,
     *found = r.found != 0;
     mask.assign(base + off_mask, base + off_mask + n);
     std::memcpy(h, r.h, sizeof(double) * 9);
+    return LVKB200_OK;
+}
+
+// Stage-level entry (parity tests): estimate_local_motions on caller-supplied correspondences and mesh state.
+lvkb200_status lvkb200_stream::run_local_motions(const std::vector<float>& tracked, const std::vector<float>& matched,
+                                                 float* mesh_state, Mesh& offsets, std::vector<uint8_t>& mask)
+{
+    const int n = static_cast<int>(tracked.size() / 2);
+    const size_t elems = static_cast<size_t>(mesh_solver.unknowns());
+    if (mesh_on_device())
+    {
+        LVKB_TRY(ensure_points(n));
+        LVKB_TRY(prepare_mesh_device());
+    }
+    if (!mesh_on_device())  // small mesh, or one that does not fit a CTA: host solver on a scratch copy of the settings
+    {
+        MeshSolver solver;
+        solver.configure(settings);
+        std::memcpy(solver.state().data(), mesh_state, sizeof(float) * elems);
+        solver.estimate(tracked, matched, offsets, mask, &last_mesh_iterations);
+        std::memcpy(mesh_state, solver.state().data(), sizeof(float) * elems);
+        return LVKB200_OK;
+    }
+    std::memcpy(h_src.ptr, tracked.data(), sizeof(float) * tracked.size());
+    std::memcpy(h_dst.ptr, matched.data(), sizeof(float) * matched.size());
+    *h_count.as<int>() = n;
+    TrackParams* hp = h_params.as<TrackParams>();
+    *hp = TrackParams{};
+    hp->n = 0;  // no LK results to deliver
+    LVKB_CUDA(mesh_device.set_state(cs, mesh_state));
+    LVKB_CUDA(cudaMemcpyAsync(d_params.ptr, h_params.ptr, sizeof(TrackParams), cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_src.ptr, h_src.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_dst.ptr, h_dst.ptr, sizeof(float2) * n, cudaMemcpyHostToDevice, cs));
+    LVKB_CUDA(cudaMemcpyAsync(d_count.ptr, h_count.ptr, sizeof(int), cudaMemcpyHostToDevice, cs));
+    TrackOutCopy out{};
+    out.dev = d_track_out.as<uint8_t>();
+    out.host = h_track_out.device_view<uint8_t>();
+    out.off_status = static_cast<uint32_t>(off_status);
+    out.off_mask = static_cast<uint32_t>(off_mask);
+    out.off_result = static_cast<uint32_t>(off_result);
+    MeshSolveParams mp{};
+    mp.temporal_weight = mesh_solver.temporal_weight();
+    mp.acceptance = mesh_solver.acceptance_threshold();
+    mp.key_w = mesh_solver.key_w();
+    mp.key_h = mesh_solver.key_h();
+    mp.min_samples = 0;
+    LVKB_CUDA(mesh_device.launch(cs, mp, d_src.as<float2>(), d_dst.as<float2>(), d_count.as<int>(),
+                                 d_params.as<TrackParams>(), d_mask(), out));
+    LVKB_CUDA(cudaStreamSynchronize(cs));
+    const MeshSolveResult& r = mesh_device.result();
+    LVKB_REQUIRE(r.solved == 1 && r.n == n);
+    last_mesh_iterations = r.iterations;
+    std::memcpy(mesh_state, mesh_device.mesh(), sizeof(float) * elems);
+    const uint8_t* m = h_track_out.as<uint8_t>() + off_mask;
+    mask.assign(m, m + n);
+    // offsets from the solution, without disturbing the stream's own tracker state
+    std::vector<float> keep = mesh_solver.state();
+    mesh_solver.adopt_state(mesh_state);
+    mesh_solver.offsets_from_state(offsets);
+    mesh_solver.adopt_state(keep.data());
+    LVKB_CUDA(mesh_device.set_state(cs, keep.data()));
     return LVKB200_OK;
 }
 
@@ -574,10 +698,23 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
 
     // ---- motion estimation (FrameTracker.cpp:157-176)
-    if (settings.track_local_motions)
+    if (settings.track_local_motions && mesh_on_device())
+    {
+        // solved by k_mesh_cgls behind LK: the mesh and the mask are already in pinned host memory
+        const MeshSolveResult& r = mesh_device.result();
+        const size_t n_est = matched.size() / 2;
+        // the device compaction must have produced exactly the host's survivor list
+        LVKB_REQUIRE(r.solved == 1 && r.n == static_cast<int>(n_est));
+        const uint8_t* m = h_track_out.as<uint8_t>() + off_mask;
+        inliers.assign(m, m + n_est);
+        mesh_solver.adopt_state(mesh_device.mesh());
+        mesh_solver.offsets_from_state(motion);
+        last_mesh_iterations = r.iterations;
+    }
+    else if (settings.track_local_motions)
     {
         stage_begin(ST_ESTIMATE);
-        mesh_solver.estimate(tracked, matched, motion, inliers);
+        mesh_solver.estimate(tracked, matched, motion, inliers, &last_mesh_iterations);
         stage_end(ST_ESTIMATE);
     }
     else
@@ -984,6 +1121,11 @@ lvkb200_status lvkb200_stream::debug_fetch(lvkb200_debug_item which, void* buffe
         case LVKB200_DBG_WARP_TRANSFORM: return dbg_has_t ? copy_out(dbg_t, 9, buffer, capacity, size) : LVKB200_OK;
         case LVKB200_DBG_PROPAGATED: return copy_out(dbg_propagated.data(), dbg_propagated.size(), buffer, capacity, size);
         case LVKB200_DBG_FAST_COUNTS: return copy_out(dbg_fast_counts.data(), dbg_fast_counts.size(), buffer, capacity, size);
+        case LVKB200_DBG_MESH_ITERATIONS:
+        {
+            const int32_t it = last_mesh_iterations;
+            return copy_out(&it, 1, buffer, capacity, size);
+        }
     }
     return LVKB200_ERR_INVALID;
 }
@@ -1007,7 +1149,7 @@ void lvkb200_stream::release()
     }
     planes_in.release(); planes_out.release(); obs_frame_in.release(); obs_frame_out.release();
     format_plan.xtab.release(); format_plan.ytab.release();
-    stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release();
+    stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release(); mesh_device.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
     deblock.release(); deblock_stage.release();
     destroy_graphs();

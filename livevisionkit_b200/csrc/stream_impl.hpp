@@ -12,6 +12,7 @@
 #include "host_mesh.hpp"
 #include "ingest.hpp"
 #include "lk.hpp"
+#include "mesh.hpp"
 #include "ransac.hpp"
 #include "stream.hpp"
 
@@ -74,6 +75,17 @@ struct lvkb200_stream
     lvkb200::FeatureGrid grid;
     lvkb200::PathSmoother smoother;
     lvkb200::MeshSolver mesh_solver;
+    // K6c: meshes with >= MESH_DEVICE_MIN_UNKNOWNS unknowns are solved by one CTA on the tracking stream (mesh.cu)
+    lvkb200::MeshCgls mesh_device;
+    unsigned mesh_device_generation = ~0u;  // mesh_solver.generation() the device copy of the static rows was made from
+    int mesh_device_capacity = 0;
+    bool mesh_device_unfit = false;  // the system does not fit one CTA's shared memory: host solver
+    int mesh_device_min_unknowns = lvkb200::MESH_DEVICE_MIN_UNKNOWNS;  // LVKB200_MESH_DEVICE_MIN overrides (tuning knob)
+    bool mesh_on_device() const { return settings.track_local_motions && !mesh_device_unfit &&
+                                         mesh_solver.unknowns() >= mesh_device_min_unknowns; }
+    lvkb200_status prepare_mesh_device();  // (re)uploads the static rows when the settings or the capacity changed
+    lvkb200_status launch_mesh_device();   // compaction + solve behind LK on cs
+    int last_mesh_iterations = 0;
     std::vector<lvkb200::Feature> features;  // m_TrackedFeatures
     bool frame_initialized = false;
     int lk_calls = 0;  // calc() calls made on this tracker's cv::SparsePyrLKOpticalFlow equivalent
@@ -186,6 +198,8 @@ struct lvkb200_stream
     lvkb200_status ensure_points(int n);
     lvkb200_status fetch_tracking(int n, bool with_model, std::vector<float>& matched, std::vector<uint8_t>& status,
                                   lvkb200::RansacResult* model, std::vector<uint8_t>& mask);
+    lvkb200_status run_local_motions(const std::vector<float>& tracked, const std::vector<float>& matched,
+                                     float* mesh_state, lvkb200::Mesh& offsets, std::vector<uint8_t>& mask);
     lvkb200_status run_homography(const std::vector<float>& tracked, const std::vector<float>& matched, float threshold, int model,
                                   double h[9], std::vector<uint8_t>& mask, bool* found);
     lvkb200_status apply_mesh(QueuedFrame& src, const lvkb200::Mesh& offsets, void* out, size_t out_pitch,

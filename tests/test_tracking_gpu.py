@@ -351,3 +351,38 @@ def test_local_motions_vs_oracle(gpu_stream, oracle):
         assert np.abs(offsets.reshape(2, 2, 2) - motion_ref).max() * 256 <= 1e-3  # corner displacement in px
         assert np.abs(state - trk.optimized_mesh).max() <= 1e-3
     s.close()
+
+
+@pytest.mark.parametrize("mesh", ["field16x16", "default2x2_on_device"])
+def test_local_motions_device_solver_vs_oracle(gpu_stream, oracle, mesh, monkeypatch):
+    """K6c k_mesh_cgls (one CTA, whole LSCG solve in shared memory) against the sequential CPU restatement of Eigen's
+    LeastSquaresConjugateGradient (oracle/lscg_ref.c): same iteration, different float32 summation order."""
+    import livevisionkit_b200 as L
+    if mesh == "field16x16":
+        sg, so = L.StabilizationFilterSettings.obs_field_preset(), oracle.StabilizationSettings.obs_field_preset()
+    else:
+        monkeypatch.setenv("LVKB200_MESH_DEVICE_MIN", "1")
+        sg, so = L.StabilizationFilterSettings(), oracle.StabilizationSettings()
+    w, h = so.detection_resolution
+    mc, mr = so.motion_resolution
+    s = L.Stream(sg, 0)
+    rng = np.random.default_rng(11)
+    n = 1100
+    p = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], axis=1).astype(np.float32)
+    # a smooth non-rigid field (what the mesh is for) + noise + gross outliers
+    flow = np.stack([1.5 + 2.0 * np.sin(p[:, 1] / h * 3.0), -0.8 + 1.5 * np.cos(p[:, 0] / w * 2.0)], axis=1)
+    q = (p * np.float32(1.002) + flow + rng.normal(0, 0.05, (n, 2))).astype(np.float32)
+    q[:50] += 30.0
+    trk = oracle.FrameTracker(so)
+    state = np.zeros(2 * mc * mr, dtype=np.float32)
+    worst_state = worst_off = 0.0
+    for it in range(4):  # warm-started over consecutive "frames"
+        motion_ref, inl_ref = trk.estimate_local_motions(p.tolist(), q.tolist())
+        state, offsets, mask = s.estimate_local_motions(p, q, state)
+        assert (mask != inl_ref).sum() <= 1, f"frame {it}: {(mask != inl_ref).sum()} inlier flags differ"
+        worst_off = max(worst_off, float(np.abs(offsets.reshape(mr, mc, 2) - motion_ref).max() * max(w, h)))
+        worst_state = max(worst_state, float(np.abs(state - np.asarray(trk.optimized_mesh).ravel()).max()))
+        q = (q + rng.normal(0, 0.02, (n, 2))).astype(np.float32)
+    print(f"[mesh {mesh}] max |vertex - oracle| {worst_state:.2e} px, max offset deviation {worst_off:.2e} px")
+    assert worst_state <= 5e-3 and worst_off <= 5e-3
+    s.close()
