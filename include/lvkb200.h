@@ -209,6 +209,39 @@ lvkb200_status lvkb200_deblock(lvkb200_stream* s, const lvkb200_deblock_settings
  * submitting the result. */
 lvkb200_status lvkb200_stream_set_deblocking(lvkb200_stream* s, const lvkb200_deblock_settings* settings);
 
+/* ---- lvk::ScalingFilter: FSR upscale + sharpen -------------------------------------------------- */
+
+/* lvk::ScalingFilterSettings — Filters/ScalingFilter.hpp:27-32 (same names and defaults). */
+typedef struct lvkb200_scaling_settings
+{
+    int32_t output_width;  /* 1920 (> 0) */
+    int32_t output_height; /* 1080 (> 0) */
+    float sharpness;       /* 0.8, in [0, 1] */
+    int32_t yuv_input;     /* 1: the EASU luma is computed for a YUV frame (Image.cpp:168-179) */
+} lvkb200_scaling_settings;
+void lvkb200_scaling_settings_default(lvkb200_scaling_settings* s);
+
+/* lvk::upscale(src, dst, size, yuv) — Functions/Image.cpp:155-201, kernel easu_scale (FSR.cl:326-358): FSR-EASU
+ * upsampling of a packed 8UC3 frame to dst_width x dst_height (both >= the source's, Image.cpp:157; equal sizes
+ * are a plain copy, :162-166).  `dst` must not overlap `src`. */
+lvkb200_status lvkb200_upscale(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                               lvkb200_memspace src_space, void* dst, size_t dst_pitch, int dst_width, int dst_height,
+                               lvkb200_memspace dst_space, int yuv_input);
+
+/* lvk::sharpen(src, dst, sharpness) — Functions/Image.cpp:205-233, kernel rcas (FSR.cl:460-535): FSR-RCAS on a packed
+ * 8UC3 frame, sharpness in [0, 1] (LVK_ASSERT_01, :209).  Every tap reads the unsharpened input: `dst` may equal
+ * `src` (the frame is then sharpened through the stream's scratch buffer), which is what the reference's in-place
+ * call (ScalingFilter.cpp:57) means but, racing between work-groups, does not guarantee. */
+lvkb200_status lvkb200_sharpen(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                               lvkb200_memspace src_space, void* dst, size_t dst_pitch, lvkb200_memspace dst_space,
+                               float sharpness);
+
+/* ScalingFilter::filter — Filters/ScalingFilter.cpp:52-59: upscale to settings->output_{width,height}, then sharpen;
+ * the intermediate frame never leaves the device.  Settings are checked like ScalingFilter::configure (:41-48). */
+lvkb200_status lvkb200_scaling_filter(lvkb200_stream* s, const lvkb200_scaling_settings* settings, const void* frame,
+                                      size_t pitch, int width, int height, lvkb200_memspace frame_space, void* out,
+                                      size_t out_pitch, lvkb200_memspace out_space);
+
 /* ---- FrameIngest: OBS frame layouts <-> packed 8UC3 frames ---------------------------------------- */
 
 /* The video_format values FrameIngest::Select accepts (Modules/OBS-Plugin/Interop/FrameIngest.cpp:38-76); the

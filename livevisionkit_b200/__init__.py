@@ -20,6 +20,7 @@ from . import _capi
 from ._capi import (BGR, BGRA, GRAY, RGB, RGBA, UNKNOWN, YUV, LvkB200Error, STAGE_NAMES)  # noqa: F401
 
 __all__ = ["StabilizationFilterSettings", "StabilizationFilter", "DeblockingFilterSettings", "DeblockingFilter",
+           "ScalingFilterSettings", "ScalingFilter",
            "CompositeFilter", "VideoFrame", "Stream", "BGR", "RGB", "YUV", "LvkB200Error", "device_count"]
 
 
@@ -428,6 +429,54 @@ class Stream:
             c = settings.to_c()
             _capi.check(self._lib.lvkb200_stream_set_deblocking(self._h, C.byref(c)))
 
+    # ---- lvk::ScalingFilter: lvk::upscale / lvk::sharpen (Functions/Image.cpp:155-233)
+    @staticmethod
+    def _new_like(frame, h, w):
+        return np.empty((h, w, 3), dtype=np.uint8) if isinstance(frame, np.ndarray) else frame.new_empty((h, w, 3))
+
+    def upscale(self, frame, size, yuv: bool = False, out=None):
+        """lvk::upscale(src, dst, size, yuv): FSR-EASU to size = (width, height) >= the frame's."""
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        if ch != 3:
+            raise ValueError("upscale takes packed 8UC3 frames")
+        ow, oh = int(size[0]), int(size[1])
+        if out is None:
+            out = self._new_like(frame, oh, ow)
+        optr, opitch, bh, bw, och, ospace = _buffer_info(out)
+        if (bh, bw, och) != (oh, ow, 3):
+            raise ValueError("output buffer must have the requested size")
+        _capi.check(self._lib.lvkb200_upscale(self._h, ptr, pitch, w, h, space, optr, opitch, ow, oh, ospace, int(yuv)))
+        return out
+
+    def sharpen(self, frame, sharpness: float, out=None):
+        """lvk::sharpen(src, dst, sharpness): FSR-RCAS; `out` may be `frame`."""
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        if ch != 3:
+            raise ValueError("sharpen takes packed 8UC3 frames")
+        if out is None:
+            out = self._new_like(frame, h, w)
+        optr, opitch, bh, bw, och, ospace = _buffer_info(out)
+        if (bh, bw, och) != (h, w, 3):
+            raise ValueError("output buffer must match the input frame")
+        _capi.check(self._lib.lvkb200_sharpen(self._h, ptr, pitch, w, h, space, optr, opitch, ospace, float(sharpness)))
+        return out
+
+    def scaling_filter(self, frame, settings: "ScalingFilterSettings | None" = None, out=None):
+        """ScalingFilter::filter: upscale then sharpen, the intermediate frame stays on the device."""
+        st = settings or ScalingFilterSettings()
+        ptr, pitch, h, w, ch, space = _buffer_info(frame)
+        if ch != 3:
+            raise ValueError("the scaling filter takes packed 8UC3 frames")
+        ow, oh = int(st.output_size[0]), int(st.output_size[1])
+        if out is None:
+            out = self._new_like(frame, oh, ow)
+        optr, opitch, bh, bw, och, ospace = _buffer_info(out)
+        if (bh, bw, och) != (oh, ow, 3):
+            raise ValueError("output buffer must have the configured output size")
+        c = st.to_c()
+        _capi.check(self._lib.lvkb200_scaling_filter(self._h, C.byref(c), ptr, pitch, w, h, space, optr, opitch, ospace))
+        return out
+
 
 def _plane_info(buf):
     """-> (pointer, pitch_bytes, memspace) of one 2-D uint8 plane (numpy array or torch tensor)."""
@@ -553,6 +602,40 @@ class DeblockingFilter:
     def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
         out = self.stream.deblock(frame.data, self._settings, frame.format, output)
         return VideoFrame(out, frame.timestamp, frame.format)
+
+
+@dataclass
+class ScalingFilterSettings:
+    """lvk::ScalingFilterSettings (Filters/ScalingFilter.hpp:27-32)."""
+    output_size: tuple = (1920, 1080)
+    sharpness: float = 0.8
+    yuv_input: bool = True
+
+    def to_c(self) -> _capi.ScalingSettings:
+        return _capi.ScalingSettings(int(self.output_size[0]), int(self.output_size[1]), float(self.sharpness),
+                                     int(bool(self.yuv_input)))
+
+
+class ScalingFilter:
+    """lvk::ScalingFilter behind lvk::VideoFilter::apply (Filters/ScalingFilter.hpp:34-52, .cpp:28-59)."""
+
+    def __init__(self, settings: "ScalingFilterSettings | None" = None, device: int = 0, stream: "Stream | None" = None):
+        self.stream = stream or Stream(None, device)
+        self.alias = "Scaling Filter"
+        self.configure(settings or ScalingFilterSettings())
+
+    def settings(self) -> ScalingFilterSettings:
+        return self._settings
+
+    def configure(self, settings: ScalingFilterSettings):
+        # ScalingFilter::configure preconditions (ScalingFilter.cpp:43-45)
+        if not (0.0 <= settings.sharpness <= 1.0 and settings.output_size[0] > 0 and settings.output_size[1] > 0):
+            raise LvkB200Error(_capi.ERR_INVALID, "ScalingFilter::configure precondition")
+        self._settings = settings
+
+    def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
+        out = self.stream.scaling_filter(frame.data, self._settings, output)
+        return VideoFrame(out, frame.timestamp, frame.format)  # output.timestamp = input.timestamp (:58)
 
 
 class CompositeFilter:

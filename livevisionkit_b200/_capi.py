@@ -52,6 +52,12 @@ class DeblockSettings(C.Structure):
                 ("filter_scaling", C.c_float)]
 
 
+class ScalingSettings(C.Structure):
+    """lvkb200_scaling_settings — lvk::ScalingFilterSettings."""
+    _fields_ = [("output_width", C.c_int32), ("output_height", C.c_int32), ("sharpness", C.c_float),
+                ("yuv_input", C.c_int32)]
+
+
 class ObsFrame(C.Structure):
     """lvkb200_obs_frame — the fields of obs_source_frame the ingest reads."""
     _fields_ = [("data", C.c_void_p * 4), ("linesize", C.c_uint32 * 4), ("width", C.c_uint32), ("height", C.c_uint32),
@@ -113,6 +119,10 @@ SYMBOLS = {
     "lvkb200_deblock_settings_default": (None, [C.POINTER(DeblockSettings)]),
     "lvkb200_deblock": (C.c_int, [_vp, C.POINTER(DeblockSettings), _vp, _sz, _i, _i, _i, _i, _vp, _sz, _i]),
     "lvkb200_stream_set_deblocking": (C.c_int, [_vp, C.POINTER(DeblockSettings)]),
+    "lvkb200_scaling_settings_default": (None, [C.POINTER(ScalingSettings)]),
+    "lvkb200_upscale": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _i, _i, _i]),
+    "lvkb200_sharpen": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, C.c_float]),
+    "lvkb200_scaling_filter": (C.c_int, [_vp, C.POINTER(ScalingSettings), _vp, _sz, _i, _i, _i, _vp, _sz, _i]),
     "lvkb200_video_format_ocl": (C.c_int, [_i]),
     "lvkb200_frame_upload": (C.c_int, [_vp, C.POINTER(ObsFrame), _i, _vp, _sz, _i]),
     "lvkb200_frame_download": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(ObsFrame), _i]),

@@ -2,6 +2,9 @@
 // (include/lvkb200.h).  Same names, argument meaning and error behaviour as
 //   LiveVisionKit/Filters/VideoFilter.hpp:32-61          lvk::VideoFilter (apply / alias / timings / filter)
 //   LiveVisionKit/Filters/StabilizationFilter.hpp:28-77  lvk::StabilizationFilterSettings, lvk::StabilizationFilter
+//   LiveVisionKit/Filters/DeblockingFilter.hpp:26-59     lvk::DeblockingFilterSettings, lvk::DeblockingFilter
+//   LiveVisionKit/Filters/ScalingFilter.hpp:27-52        lvk::ScalingFilterSettings, lvk::ScalingFilter
+//   LiveVisionKit/Filters/CompositeFilter.hpp:27-75      lvk::CompositeFilterSettings, lvk::CompositeFilter
 //   LiveVisionKit/Vision/FrameTracker.hpp:31-44, FeatureDetector.hpp:28-37, PathSmoother.hpp:29-39  settings bases
 //   LiveVisionKit/Utility/Configurable.hpp:27-44         lvk::Configurable<T>
 //   LiveVisionKit/Data/VideoFrame.hpp:25-79              lvk::VideoFrame (format, timestamp, width/height)
@@ -18,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <initializer_list>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -356,6 +361,201 @@ private:
     VideoFrame m_Scratch;
     int m_Device = 0;
     int m_LastWidth = 0, m_LastHeight = 0;
+};
+
+// ---- shared plumbing of the stateless per-frame filters (own lvkb200_stream = device scratch + CUDA stream) -----------
+namespace detail
+{
+class DeviceFilterBase
+{
+protected:
+    explicit DeviceFilterBase(int cuda_device)
+    {
+        lvkb200_set_assert_handler(nullptr);
+        check(lvkb200_stream_create(cuda_device, nullptr, &m_Stream), "lvkb200_stream_create");
+    }
+    ~DeviceFilterBase() { if (m_Stream) lvkb200_stream_destroy(m_Stream); }
+    DeviceFilterBase(const DeviceFilterBase&) = delete;
+    DeviceFilterBase& operator=(const DeviceFilterBase&) = delete;
+    static bool check(lvkb200_status st, const char* where)
+    {
+        if (st == LVKB200_OK) return true;
+        context::assert_handler("lvkb200", where, lvkb200_last_error());
+        return false;
+    }
+    static lvkb200_memspace space_of(const VideoFrame& f) { return f.on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST; }
+    lvkb200_stream* m_Stream = nullptr;
+};
+}  // namespace detail
+
+// ---- Filters/DeblockingFilter.hpp:26-59 --------------------------------------------------------------------------------------
+struct DeblockingFilterSettings
+{
+    uint32_t detection_levels = 3;  // Must be greater than 0
+    uint32_t block_size = 16;       // Must be greater than 0
+    uint32_t filter_size = 5;       // Must be odd
+    float filter_scaling = 4;       // Smaller is stronger (1/x)
+};
+
+class DeblockingFilter final : public VideoFilter, public Configurable<DeblockingFilterSettings>, private detail::DeviceFilterBase
+{
+public:
+    explicit DeblockingFilter(DeblockingFilterSettings settings = {}, int cuda_device = 0)
+        : VideoFilter("Deblocking Filter"), detail::DeviceFilterBase(cuda_device)
+    {
+        configure(settings);
+    }
+    void configure(const DeblockingFilterSettings& settings) override  // DeblockingFilter.cpp:36-45
+    {
+        LVK_ASSERT(settings.block_size > 0);
+        LVK_ASSERT(settings.filter_size >= 3);
+        LVK_ASSERT(settings.filter_size % 2 == 1);
+        LVK_ASSERT(settings.detection_levels > 0);
+        LVK_ASSERT(settings.filter_scaling > 1.0f);
+        m_Settings = settings;
+    }
+    void draw_influence(VideoFrame&) const {}  // debug overlay (DeblockingFilter.cpp:122-132): not on the hot path
+    cvlite::Rect filter_region() const { return m_FilterRegion; }  // :136-139
+    lvkb200_stream* native_handle() const { return m_Stream; }
+
+private:
+    void filter(VideoFrame&& input, VideoFrame& output) override  // DeblockingFilter.cpp:48-118: in place, then moved out
+    {
+        LVK_ASSERT(!input.empty());
+        const lvkb200_deblock_settings pod{m_Settings.detection_levels, m_Settings.block_size, m_Settings.filter_size,
+                                           m_Settings.filter_scaling};
+        const int bs = static_cast<int>(m_Settings.block_size);
+        m_FilterRegion.x = m_FilterRegion.y = 0;
+        m_FilterRegion.width = input.cols / bs * bs; m_FilterRegion.height = input.rows / bs * bs;
+        check(lvkb200_deblock(m_Stream, &pod, input.data, input.step, input.cols, input.rows,
+                              static_cast<lvkb200_format>(input.format), space_of(input), input.data, input.step,
+                              space_of(input)), "DeblockingFilter::filter");
+        if (&input != &output) output = std::move(input);
+    }
+    void sync_device() override { lvkb200_stream_sync(m_Stream); }
+    cvlite::Rect m_FilterRegion;
+};
+
+// ---- Filters/ScalingFilter.hpp:27-52 -------------------------------------------------------------------------------------------
+struct ScalingFilterSettings
+{
+    cvlite::Size output_size = {1920, 1080};
+    float sharpness = 0.8f;
+    bool yuv_input = true;
+};
+
+class ScalingFilter final : public VideoFilter, public Configurable<ScalingFilterSettings>, private detail::DeviceFilterBase
+{
+public:
+    explicit ScalingFilter(const ScalingFilterSettings& settings = {}, int cuda_device = 0)
+        : VideoFilter("Scaling Filter"), detail::DeviceFilterBase(cuda_device)
+    {
+        configure(settings);
+    }
+    explicit ScalingFilter(const cvlite::Size& output_size, const float sharpness = 0.8f)
+        : ScalingFilter(make_settings(output_size, sharpness)) {}
+    void configure(const ScalingFilterSettings& settings) override  // ScalingFilter.cpp:41-48
+    {
+        LVK_ASSERT(settings.sharpness >= 0.0f && settings.sharpness <= 1.0f);
+        LVK_ASSERT(settings.output_size.width > 0);
+        LVK_ASSERT(settings.output_size.height > 0);
+        m_Settings = settings;
+    }
+    lvkb200_stream* native_handle() const { return m_Stream; }
+
+private:
+    static ScalingFilterSettings make_settings(const cvlite::Size& size, float sharpness)
+    {
+        ScalingFilterSettings s;
+        s.output_size = size; s.sharpness = sharpness;
+        return s;
+    }
+    void filter(VideoFrame&& input, VideoFrame& output) override  // ScalingFilter.cpp:52-59
+    {
+        LVK_ASSERT(!input.empty());
+        const lvkb200_scaling_settings pod{m_Settings.output_size.width, m_Settings.output_size.height, m_Settings.sharpness,
+                                           m_Settings.yuv_input ? 1 : 0};
+        // a host output is (re)created at the output size (dst.create, Image.cpp:182); a device output must already have it
+        VideoFrame result;
+        VideoFrame* dst = &result;
+        if (&input != &output && output.on_device && output.cols == pod.output_width && output.rows == pod.output_height)
+            dst = &output;
+        else
+            result.create(pod.output_height, pod.output_width);
+        const bool ok = check(lvkb200_scaling_filter(m_Stream, &pod, input.data, input.step, input.cols, input.rows,
+                                                     space_of(input), dst->data, dst->step, space_of(*dst)),
+                              "ScalingFilter::filter");
+        const uint64_t ts = input.timestamp;
+        const VideoFrame::Format fmt = input.format;
+        if (!ok) { output.release(); return; }
+        if (dst != &output) output = std::move(result);
+        output.timestamp = ts;  // ScalingFilter.cpp:58
+        output.format = fmt;
+    }
+    void sync_device() override { lvkb200_stream_sync(m_Stream); }
+};
+
+// ---- Filters/CompositeFilter.hpp:27-75 -----------------------------------------------------------------------------------------
+struct CompositeFilterSettings
+{
+    std::vector<std::shared_ptr<lvk::VideoFilter>> filter_chain;
+    bool save_outputs = false;
+};
+
+class CompositeFilter final : public VideoFilter, public Configurable<CompositeFilterSettings>
+{
+public:
+    explicit CompositeFilter(const CompositeFilterSettings& settings = {}) : VideoFilter("Composite Filter") { configure(settings); }
+    CompositeFilter(const std::initializer_list<std::shared_ptr<lvk::VideoFilter>>& filter_chain,
+                    const CompositeFilterSettings& settings = {})
+        : VideoFilter("Composite Filter")
+    {
+        CompositeFilterSettings s;
+        s.filter_chain = filter_chain; s.save_outputs = settings.save_outputs;
+        configure(s);
+    }
+    void configure(const CompositeFilterSettings& settings) override  // CompositeFilter.cpp:46-55
+    {
+        m_Settings = settings;
+        m_FilterOutputs.resize(settings.filter_chain.size());
+        m_FilterRunState.resize(settings.filter_chain.size(), true);
+        enable_all_filters();
+    }
+    const std::vector<std::shared_ptr<lvk::VideoFilter>>& filters() const { return m_Settings.filter_chain; }
+    std::shared_ptr<lvk::VideoFilter> filters(const size_t index)
+    {
+        LVK_ASSERT(index < m_Settings.filter_chain.size());
+        return m_Settings.filter_chain[index];
+    }
+    const std::vector<Frame>& outputs() const { return m_FilterOutputs; }
+    const VideoFrame& outputs(const size_t index) { LVK_ASSERT(index < m_FilterOutputs.size()); return m_FilterOutputs[index]; }
+    bool is_filter_enabled(const size_t index) { LVK_ASSERT(index < m_FilterRunState.size()); return m_FilterRunState[index]; }
+    void disable_filter(const size_t index) { LVK_ASSERT(index < m_FilterRunState.size()); m_FilterRunState[index] = false; }
+    void enable_filter(const size_t index) { LVK_ASSERT(index < m_FilterRunState.size()); m_FilterRunState[index] = true; }
+    void enable_all_filters() { for (size_t i = 0; i < m_FilterRunState.size(); i++) m_FilterRunState[i] = true; }
+    size_t filter_count() const { return m_Settings.filter_chain.size(); }
+
+private:
+    void filter(VideoFrame&& input, VideoFrame& output) override  // CompositeFilter.cpp:58-88
+    {
+        LVK_ASSERT(!input.empty());
+        VideoFrame& prev_filter_output = input;
+        for (size_t i = 0; i < m_Settings.filter_chain.size(); i++)
+        {
+            if (!is_filter_enabled(i)) continue;
+            VideoFrame& filter_input = prev_filter_output;
+            VideoFrame& filter_output = m_FilterOutputs[i];
+            if (filter_input.empty()) break;  // exit the chain if a filter input is empty
+            m_Settings.filter_chain[i]->apply(std::move(filter_input), filter_output);
+            if (m_Settings.save_outputs)
+                prev_filter_output = filter_output;  // clone
+            else
+                prev_filter_output = std::move(filter_output);
+        }
+        output = std::move(prev_filter_output);
+    }
+    std::vector<bool> m_FilterRunState;
+    std::vector<Frame> m_FilterOutputs;
 };
 
 }  // namespace lvk

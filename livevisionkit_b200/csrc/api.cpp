@@ -1,5 +1,6 @@
 // C-ABI implementation (include/lvkb200.h).  Host C++ only: orchestration + calls into the kernel launchers.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -618,6 +619,117 @@ lvkb200_status lvkb200_stream_set_deblocking(lvkb200_stream* s, const lvkb200_de
     LVKB_TRY(deblock_validate(*settings));
     s->deblock_settings = *settings;
     s->deblock_enabled = true;
+    return LVKB200_OK;
+}
+
+// ---- lvk::ScalingFilter ---------------------------------------------------------------------------------------------
+
+void lvkb200_scaling_settings_default(lvkb200_scaling_settings* s)
+{
+    if (!s) return;
+    // ScalingFilterSettings — Filters/ScalingFilter.hpp:29-31
+    s->output_width = 1920;
+    s->output_height = 1080;
+    s->sharpness = 0.8f;
+    s->yuv_input = 1;
+}
+
+// Image.cpp:227: the kernel argument, computed in float
+static float rcas_kernel_sharpness(float sharpness) { return std::exp2(-2.0f * (1.0f - sharpness)); }
+
+// upscale of a device frame into a device frame on s->cs (Image.cpp:155-201)
+static lvkb200_status upscale_device(lvkb200_stream* s, const uint8_t* src, size_t src_pitch, int width, int height,
+                                     uint8_t* dst, size_t dst_pitch, int dst_width, int dst_height, bool yuv)
+{
+    if (dst_width == width && dst_height == height)  // src.copyTo(dst) — Image.cpp:162-166
+    {
+        LVKB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, static_cast<size_t>(width) * 3, height,
+                                    cudaMemcpyDeviceToDevice, s->cs));
+        return LVKB200_OK;
+    }
+    RemapParams p{};
+    p.src = src; p.src_pitch = src_pitch; p.dst = dst; p.dst_pitch = dst_pitch;
+    p.width = width; p.height = height; p.dst_width = dst_width; p.dst_height = dst_height; p.yuv = yuv;
+    LVKB_CUDA(launch_upscale(s->cs, p));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_upscale(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                               lvkb200_memspace src_space, void* dst, size_t dst_pitch, int dst_width, int dst_height,
+                               lvkb200_memspace dst_space, int yuv_input)
+{
+    LVKB_REQUIRE(s != nullptr && src != nullptr && dst != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0);                          // Image.cpp:158
+    LVKB_REQUIRE(dst_width >= width && dst_height >= height);      // Image.cpp:157
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const uint8_t* din = nullptr;
+    size_t din_pitch = 0;
+    uint8_t* dout = nullptr;
+    size_t dout_pitch = 0;
+    LVKB_TRY(s->stage_frame_in(src, src_pitch, width, height, 3, src_space, &din, &din_pitch));
+    LVKB_TRY(s->stage_frame_out(dst, dst_pitch, dst_width, dst_height, 3, dst_space, &dout, &dout_pitch));
+    LVKB_TRY(upscale_device(s, din, din_pitch, width, height, dout, dout_pitch, dst_width, dst_height, yuv_input != 0));
+    LVKB_TRY(s->finish_frame_out(dst, dst_pitch, dst_width, dst_height, 3, dst_space));
+    if (src_space == LVKB200_MEM_HOST && dst_space != LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_sharpen(lvkb200_stream* s, const void* src, size_t src_pitch, int width, int height,
+                               lvkb200_memspace src_space, void* dst, size_t dst_pitch, lvkb200_memspace dst_space,
+                               float sharpness)
+{
+    LVKB_REQUIRE(s != nullptr && src != nullptr && dst != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0);                // Image.cpp:207
+    LVKB_REQUIRE(sharpness >= 0.0f && sharpness <= 1.0f);  // LVK_ASSERT_01 — Image.cpp:209
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const uint8_t* din = nullptr;
+    size_t din_pitch = 0;
+    uint8_t* dout = nullptr;
+    size_t dout_pitch = 0;
+    LVKB_TRY(s->stage_frame_in(src, src_pitch, width, height, 3, src_space, &din, &din_pitch));
+    LVKB_TRY(s->stage_frame_out(dst, dst_pitch, width, height, 3, dst_space, &dout, &dout_pitch));
+    if (din == dout)
+    {
+        // in place on a device frame: the taps must see the unsharpened input -> sharpen a scratch copy of it
+        const size_t row = static_cast<size_t>(width) * 3, sp = (row + 15) / 16 * 16;
+        LVKB_CUDA(s->scaling_scratch.ensure(sp * height));
+        LVKB_CUDA(cudaMemcpy2DAsync(s->scaling_scratch.ptr, sp, din, din_pitch, row, height, cudaMemcpyDeviceToDevice, s->cs));
+        din = s->scaling_scratch.as<uint8_t>();
+        din_pitch = sp;
+    }
+    LVKB_CUDA(launch_rcas(s->cs, din, din_pitch, dout, dout_pitch, width, height, rcas_kernel_sharpness(sharpness)));
+    LVKB_TRY(s->finish_frame_out(dst, dst_pitch, width, height, 3, dst_space));
+    if (src_space == LVKB200_MEM_HOST && dst_space != LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(s->cs));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_scaling_filter(lvkb200_stream* s, const lvkb200_scaling_settings* settings, const void* frame,
+                                      size_t pitch, int width, int height, lvkb200_memspace frame_space, void* out,
+                                      size_t out_pitch, lvkb200_memspace out_space)
+{
+    LVKB_REQUIRE(s != nullptr && settings != nullptr && frame != nullptr && out != nullptr);
+    LVKB_REQUIRE(width > 0 && height > 0);  // LVK_ASSERT(!input.empty()) — ScalingFilter.cpp:54
+    // ScalingFilter::configure — ScalingFilter.cpp:43-45
+    LVKB_REQUIRE(settings->sharpness >= 0.0f && settings->sharpness <= 1.0f);
+    LVKB_REQUIRE(settings->output_width > 0);
+    LVKB_REQUIRE(settings->output_height > 0);
+    const int ow = settings->output_width, oh = settings->output_height;
+    LVKB_REQUIRE(ow >= width && oh >= height);  // lvk::upscale — Image.cpp:157
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const uint8_t* din = nullptr;
+    size_t din_pitch = 0;
+    uint8_t* dout = nullptr;
+    size_t dout_pitch = 0;
+    LVKB_TRY(s->stage_frame_in(frame, pitch, width, height, 3, frame_space, &din, &din_pitch));
+    LVKB_TRY(s->stage_frame_out(out, out_pitch, ow, oh, 3, out_space, &dout, &dout_pitch));
+    // the upscaled frame stays in the stream's device scratch (16-byte aligned rows for the RCAS tile loads)
+    const size_t sp = (static_cast<size_t>(ow) * 3 + 15) / 16 * 16;
+    LVKB_CUDA(s->scaling_scratch.ensure(sp * oh));
+    uint8_t* mid = s->scaling_scratch.as<uint8_t>();
+    LVKB_TRY(upscale_device(s, din, din_pitch, width, height, mid, sp, ow, oh, settings->yuv_input != 0));
+    LVKB_CUDA(launch_rcas(s->cs, mid, sp, dout, dout_pitch, ow, oh, rcas_kernel_sharpness(settings->sharpness)));
+    LVKB_TRY(s->finish_frame_out(out, out_pitch, ow, oh, 3, out_space));
+    if (frame_space == LVKB200_MEM_HOST && out_space != LVKB200_MEM_HOST) LVKB_CUDA(cudaStreamSynchronize(s->cs));
     return LVKB200_OK;
 }
 

@@ -75,9 +75,10 @@ struct RemapParams
     size_t src_pitch;
     uint8_t* dst;  // device, packed 8UC3
     size_t dst_pitch;
-    int width, height;
+    int width, height;  // source size (== destination size for the remaps)
     uint8_t bg[3];
     bool yuv;
+    int dst_width = 0, dst_height = 0;  // launch_upscale only
 };
 
 // easu_remap_homography (FSR.cl:407-452). t = dst->src transform narrowed to float (Image.cpp:133-135).
@@ -85,5 +86,11 @@ cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const
 // easu_remap (FSR.cl:362-403) with the WarpMesh::apply upsample (WarpMesh.cpp:190-191) fused in:
 // mesh = device pointer to rows*cols float2 normalized offsets.
 cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows);
+
+// lvk::upscale — easu_scale (FSR.cl:326-358, Image.cpp:155-201): p.width x p.height -> p.dst_width x p.dst_height.
+cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p);
+// lvk::sharpen — rcas (FSR.cl:460-535, Image.cpp:205-233), out of place; kernel_sharpness = exp2(-2 (1 - sharpness)).
+cudaError_t launch_rcas(cudaStream_t cs, const uint8_t* src, size_t src_pitch, uint8_t* dst, size_t dst_pitch, int width,
+                        int height, float kernel_sharpness);
 
 }  // namespace lvkb200

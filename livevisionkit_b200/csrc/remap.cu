@@ -1,7 +1,8 @@
 // K8 — FSR-EASU warp/remap for sm_100a.
 //
 // Replaces lvk::remap (LiveVisionKit/Functions/Image.cpp:28-151) and its OpenCL kernels
-// easu_remap / easu_remap_homography / easu (Functions/OpenCL/Sources/FSR.cl:98-318,362-452).
+// easu_remap / easu_remap_homography / easu (Functions/OpenCL/Sources/FSR.cl:98-318,362-452), and lvk::upscale
+// (Image.cpp:155-201) with its kernel easu_scale (FSR.cl:326-358): the same kernel, MODE 2.
 //
 // Design (not a translation of the 8x8 OpenCL work-groups):
 //   * one CTA = a 32x8 destination tile, one destination pixel per thread;
@@ -377,7 +378,8 @@ constexpr int STG_W = 44;  // staged source tile capacity (pixels): 32 + 3 taps 
 constexpr int STG_H = 28;  // 16 + 3 taps + warp slack, <= 4 * TILE_H
 
 // Source position of destination pixel (x, y).  MODE 0: homography (FSR.cl:407-452).  MODE 1: mesh offsets with the
-// bilinear upsample of WarpMesh::apply fused in (WarpMesh.cpp:190-191 + FSR.cl:362-403).
+// bilinear upsample of WarpMesh::apply fused in (WarpMesh.cpp:190-191 + FSR.cl:362-403).  MODE 2: plain scaling,
+// sub = dst_coord * rscale with rscale = (T.r1x, T.r2x) (easu_scale, FSR.cl:336).
 struct MeshArgs
 {
     const float2* mesh;
@@ -390,6 +392,12 @@ __device__ __forceinline__ void source_position(int x, int y, int W, int H, cons
                                                 float& subx, float& suby)
 {
     const float fx = (float)x, fy = (float)y;
+    if (MODE == 2)
+    {
+        subx = fx * T.r1x;
+        suby = fy * T.r2x;
+        return;
+    }
     float offx, offy;
     if (MODE == 0)
     {
@@ -446,8 +454,9 @@ __device__ __forceinline__ PixelClass classify(float subx, float suby, int W, in
 template <int MODE, bool YUV, int OCC>
 __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
     k_easu_remap(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch, int W,
-                 int H, Transform T, MeshArgs M, uchar3 bg)
+                 int H, int dW, int dH, Transform T, MeshArgs M, uchar3 bg)
 {
+    // W x H = source image (border classification), dW x dH = destination image (== source except for MODE 2)
     __shared__ float4 tile[STG_H * STG_W];   // {c0, c1, c2, luma} / 255 of the staged source pixels
     __shared__ float4 terms[STG_H * STG_W];  // easu_direction_terms of the same pixels (interior only)
     __shared__ float luma[STG_H * STG_W];    // tile[].w again, contiguous: the 5-point cross reads are conflict-free
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
     const int ty = threadIdx.x / TILE_W;
     const int x = blockIdx.x * TILE_W + tx;
     const int yA = blockIdx.y * CTA_H + ty, yB = yA + PAIR_DY;
-    const bool insideA = (x < W) && (yA < H), insideB = (x < W) && (yB < H);
+    const bool insideA = (x < dW) && (yA < dH), insideB = (x < dW) && (yB < dH);
 
     if (threadIdx.x == 0)
     {
@@ -880,13 +889,16 @@ static int remap_kernel_version()
 template <int MODE, bool YUV, int OCC>
 static void launch_easu_occ(cudaStream_t cs, const RemapParams& p, const Transform& T, const MeshArgs& M, uchar3 bg)
 {
-    const int tiles_x = div_up(p.width, TILE_W), tiles_y = div_up(p.height, CTA_H);
-    if (remap_kernel_version() == 2)
+    const int dw = MODE == 2 ? p.dst_width : p.width, dh = MODE == 2 ? p.dst_height : p.height;
+    const int tiles_x = div_up(dw, TILE_W), tiles_y = div_up(dh, CTA_H);
+    if (MODE == 2 || remap_kernel_version() == 2)
     {
         k_easu_remap<MODE, YUV, OCC><<<dim3(tiles_x, tiles_y), TILE_W * TILE_H, 0, cs>>>(
-            p.src, p.src_pitch, p.dst, p.dst_pitch, p.width, p.height, T, M, bg);
+            p.src, p.src_pitch, p.dst, p.dst_pitch, p.width, p.height, dw, dh, T, M, bg);
         return;
     }
+    if constexpr (MODE != 2)
+    {
     static const int ctas = [] {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -899,6 +911,7 @@ static void launch_easu_occ(cudaStream_t cs, const RemapParams& p, const Transfo
     const int bulk = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15u) == 0) ? 1 : 0;
     k_easu_remap_pipelined<MODE, YUV, OCC><<<min(ctas, n_tiles), TILE_W * TILE_H, V3_SMEM, cs>>>(
         p.src, p.src_pitch, p.dst, p.dst_pitch, p.width, p.height, T, M, bg, tiles_x, n_tiles, bulk);
+    }
 }
 
 template <int MODE, bool YUV>
@@ -920,6 +933,21 @@ cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const
         launch_easu<0, true>(cs, p, T, MeshArgs{}, bg);
     else
         launch_easu<0, false>(cs, p, T, MeshArgs{}, bg);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p)
+{
+    // Image.cpp:191-194: rscale = (float)src / (float)dst per axis
+    Transform T{};
+    T.r1x = static_cast<float>(p.width) / static_cast<float>(p.dst_width);
+    T.r2x = static_cast<float>(p.height) / static_cast<float>(p.dst_height);
+    const uchar3 bg = make_uchar3(0, 0, 0);  // never used: every source position lies inside the source
+    if (p.yuv)
+        launch_easu<2, true>(cs, p, T, MeshArgs{}, bg);
+    else
+        launch_easu<2, false>(cs, p, T, MeshArgs{}, bg);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -1149,7 +1149,7 @@ void lvkb200_stream::release()
     }
     planes_in.release(); planes_out.release(); obs_frame_in.release(); obs_frame_out.release();
     format_plan.xtab.release(); format_plan.ytab.release();
-    stage_in.release(); stage_out.release(); mesh_dev.release(); mesh_pinned.release(); mesh_device.release();
+    stage_in.release(); stage_out.release(); scaling_scratch.release(); mesh_dev.release(); mesh_pinned.release(); mesh_device.release();
     ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
     deblock.release(); deblock_stage.release();
     destroy_graphs();

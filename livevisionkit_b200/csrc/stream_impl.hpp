@@ -26,6 +26,7 @@ struct lvkb200_stream
 
     // ---- scratch used by the stage-level entry points when the caller hands host memory
     lvkb200::DeviceBuffer stage_in, stage_out, mesh_dev;
+    lvkb200::DeviceBuffer scaling_scratch;  // ScalingFilter: the upscaled frame between EASU and RCAS
     lvkb200::PinnedBuffer mesh_pinned;
     cudaEvent_t user_events[LVKB200_EVENT_SLOTS] = {};
 

@@ -10,6 +10,7 @@
  *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:181-318 (easu)
  *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:362-403 (easu_remap, per-pixel offset map)
  *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:407-452 (easu_remap_homography)
+ *   LiveVisionKit/Functions/OpenCL/Sources/FSR.cl:326-358 (easu_scale), :460-535 (rcas) — lvk::upscale / lvk::sharpen
  * and of the host side that launches them
  *   LiveVisionKit/Functions/Image.cpp:28-81, 85-151.
  *
@@ -289,6 +290,126 @@ void oracle_easu_remap_map(const uint8_t* src, int src_step, int src_rows, int s
 {
     map_ctx c = {src, src_step, src_rows, src_cols, dst, dst_step, map, map_step, map_cols, bg, yuv};
     parallel_rows(map_rows_fn, &c, map_rows, threads);
+}
+
+/* ---- lvk::upscale: FSR.cl:326-358 (easu_scale) + Image.cpp:155-201 ------------------------------------------------
+ * rscale = {(float)src.cols / (float)dst.cols, (float)src.rows / (float)dst.rows} (Image.cpp:191-194).
+ * Source pixels with src_coord.x == 0 || src_coord.y == 0 || src_coord.x >= src_cols-4 || src_coord.y >= src_rows-4
+ * are copied (nearest), everything else runs EASU.  size == src.size() is a plain copy (Image.cpp:162-166). */
+typedef struct
+{
+    const uint8_t* src; int src_step, src_rows, src_cols; uint8_t* dst; int dst_step, dst_cols;
+    float rsx, rsy; int yuv;
+} scale_ctx;
+
+static void scale_rows_fn(int y0, int y1, void* p)
+{
+    const scale_ctx* c = (const scale_ctx*)p;
+    for (int y = y0; y < y1; y++)
+    {
+        for (int x = 0; x < c->dst_cols; x++)
+        {
+            float subx = (float)x * c->rsx, suby = (float)y * c->rsy;
+            int sx = (int)subx, sy = (int)suby; /* convert_int2_rtz */
+            subx -= floorf(subx);
+            suby -= floorf(suby);
+            uint8_t* q = c->dst + (size_t)y * c->dst_step + 3 * x;
+            if (sx == 0 || sy == 0 || sx >= c->src_cols - 4 || sy >= c->src_rows - 4)
+            {
+                const uint8_t* s = c->src + (size_t)sy * c->src_step + 3 * sx;
+                q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+                continue;
+            }
+            easu(c->src, c->src_step, sx, sy, subx, suby, c->yuv, q);
+        }
+    }
+}
+
+void oracle_easu_scale(const uint8_t* src, int src_step, int src_rows, int src_cols, uint8_t* dst, int dst_step,
+                       int dst_rows, int dst_cols, int yuv, int threads)
+{
+    if (dst_rows == src_rows && dst_cols == src_cols)
+    {
+        for (int y = 0; y < src_rows; y++) memcpy(dst + (size_t)y * dst_step, src + (size_t)y * src_step, 3 * (size_t)src_cols);
+        return;
+    }
+    scale_ctx c = {src, src_step, src_rows, src_cols, dst, dst_step, dst_cols,
+                   (float)src_cols / (float)dst_cols, (float)src_rows / (float)dst_rows, yuv};
+    parallel_rows(scale_rows_fn, &c, dst_rows, threads);
+}
+
+/* ---- lvk::sharpen: FSR.cl:460-535 (rcas) + Image.cpp:205-233 --------------------------------------------------------
+ * `sharpness` is the KERNEL argument exp2(-2*(1-s)) (Image.cpp:227; computed by the caller in float).
+ * Latitude taken (the reference leaves these undefined):
+ *   - ScalingFilter runs it IN PLACE (sharpen(output, output), ScalingFilter.cpp:57), a data race between work-groups
+ *     in the reference; here src and dst are distinct images (every tap reads the unsharpened input);
+ *   - the border test copies `coord.x <= cols || coord.y <= rows` (an always-true OR that also writes the padding
+ *     threads' pixels out of bounds); here exactly the in-image border pixels are copied;
+ *   - min()/max() on NaN (0 * inf when a ring is all 0 or all 1): the non-NaN operand wins (fminf/fmaxf, what GPU
+ *     min/max instructions do);
+ *   - convert_uchar3 of an out-of-range value: truncation then saturation to [0, 255]. */
+static inline float aprx_med_rcp(float a) /* FSR.cl:70 */
+{
+    float b = as_float(0x7ef19fffu - as_uint(a));
+    return b * FMA(-b, a, 2.0f);
+}
+
+typedef struct
+{
+    const uint8_t* src; int src_step, rows, cols; uint8_t* dst; int dst_step; float sharp;
+} rcas_ctx;
+
+static void rcas_rows_fn(int y0, int y1, void* p)
+{
+    const rcas_ctx* c = (const rcas_ctx*)p;
+    const float norm = 0.00392156862f;
+    for (int y = y0; y < y1; y++)
+    {
+        for (int x = 0; x < c->cols; x++)
+        {
+            const uint8_t* s = c->src + (size_t)y * c->src_step + 3 * x;
+            uint8_t* q = c->dst + (size_t)y * c->dst_step + 3 * x;
+            if (x == 0 || x >= c->cols - 1 || y == 0 || y >= c->rows - 1)
+            {
+                q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+                continue;
+            }
+            float lobe_c[3], sum[3], e[3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const float b = (float)s[ch - c->src_step] * norm, h = (float)s[ch + c->src_step] * norm;
+                const float d = (float)s[ch - 3] * norm, f = (float)s[ch + 3] * norm;
+                e[ch] = (float)s[ch] * norm;
+                const float mn4 = fminf(b, fminf(d, fminf(f, h)));
+                const float mx4 = fmaxf(b, fmaxf(d, fmaxf(f, h)));
+                const float hit_min = fminf(mn4, e[ch]) * (1.0f / (4.0f * mx4));
+                const float hit_max = (1.0f - fmaxf(mx4, e[ch])) * (1.0f / FMA(4.0f, mn4, -4.0f));
+                lobe_c[ch] = fmaxf(-hit_min, hit_max);
+                sum[ch] = ((b + d) + h) + f;
+            }
+            /* lobeR = ch2, lobeG = ch1, lobeB = ch0: max(lobeR, max(lobeG, lobeB)) */
+            float lobe = fmaxf(lobe_c[2], fmaxf(lobe_c[1], lobe_c[0]));
+            lobe = fminf(fmaxf(lobe, -0.1875f), 0.0f) * c->sharp; /* clamp(x, lo, hi) = min(max(x, lo), hi) */
+            const float rcpL = aprx_med_rcp(FMA(4.0f, lobe, 1.0f));
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const float v = FMA(sum[ch], lobe, e[ch]) * rcpL;
+                int iv = (int)(v * 255.0f);
+                q[ch] = (uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+            }
+        }
+    }
+}
+
+/* Image.cpp:227: std::exp2(-2.0f * (1.0f - sharpness)), the float overload = the platform's exp2f (NumPy's exp2 differs
+ * from glibc's in the last bit for 20% of the settings, so the oracle calls libm like the reference does). */
+float oracle_rcas_kernel_sharpness(float sharpness) { return exp2f(-2.0f * (1.0f - sharpness)); }
+
+void oracle_rcas(const uint8_t* src, int src_step, int rows, int cols, uint8_t* dst, int dst_step, float kernel_sharpness,
+                 int threads)
+{
+    rcas_ctx c = {src, src_step, rows, cols, dst, dst_step, kernel_sharpness};
+    parallel_rows(rcas_rows_fn, &c, rows, threads);
 }
 
 int oracle_max_threads(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }

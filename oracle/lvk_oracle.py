@@ -75,6 +75,14 @@ def native():
         lib.oracle_lscg_solve.argtypes = [ctypes.c_int, ctypes.c_int, i32p, i32p, f32p, f32p, f32p, ctypes.c_int,
                                           ctypes.c_float]
         lib.oracle_lscg_solve.restype = ctypes.c_int
+        lib.oracle_easu_scale.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.oracle_easu_scale.restype = None
+        lib.oracle_rcas.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_float,
+                                    ctypes.c_int]
+        lib.oracle_rcas.restype = None
+        lib.oracle_rcas_kernel_sharpness.argtypes = [ctypes.c_float]
+        lib.oracle_rcas_kernel_sharpness.restype = ctypes.c_float
         lib.oracle_max_threads.restype = ctypes.c_int
         _LIB = lib
     return _LIB
@@ -141,6 +149,53 @@ def remap_map(src: np.ndarray, offset_map: np.ndarray, background=(255, 0, 255),
                                    _ptr(dst, ctypes.c_uint8), dst.strides[0], _ptr(m, ctypes.c_float), m.strides[0],
                                    rows, cols, _ptr(bg, ctypes.c_uint8), int(yuv), threads)
     return dst
+
+
+def upscale(src: np.ndarray, size: tuple[int, int], yuv: bool = False, threads: int = 0) -> np.ndarray:
+    """lvk::upscale(src, dst, size, yuv) — Image.cpp:155-201, FSR.cl:326-358.  size = (width, height)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    w, h = int(size[0]), int(size[1])
+    assert w >= src.shape[1] and h >= src.shape[0] and src.shape[2] == 3  # Image.cpp:157-160
+    dst = np.empty((h, w, 3), dtype=np.uint8)
+    native().oracle_easu_scale(_ptr(src, ctypes.c_uint8), src.strides[0], src.shape[0], src.shape[1],
+                               _ptr(dst, ctypes.c_uint8), dst.strides[0], h, w, int(yuv), threads)
+    return dst
+
+
+def rcas_kernel_sharpness(sharpness: float) -> np.float32:
+    """std::exp2(-2.0f * (1.0f - sharpness)) in float — Image.cpp:227."""
+    assert 0.0 <= sharpness <= 1.0  # LVK_ASSERT_01, Image.cpp:209
+    return f32(native().oracle_rcas_kernel_sharpness(float(f32(sharpness))))
+
+
+def sharpen(src: np.ndarray, sharpness: float, threads: int = 0) -> np.ndarray:
+    """lvk::sharpen(src, dst, sharpness) — Image.cpp:205-233, FSR.cl:460-535 (out of place, see easu_ref.c)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.empty_like(src)
+    native().oracle_rcas(_ptr(src, ctypes.c_uint8), src.strides[0], src.shape[0], src.shape[1],
+                         _ptr(dst, ctypes.c_uint8), dst.strides[0], float(rcas_kernel_sharpness(sharpness)), threads)
+    return dst
+
+
+@dataclass
+class ScalingFilterSettings:
+    """Filters/ScalingFilter.hpp:27-32."""
+    output_size: tuple = (1920, 1080)
+    sharpness: float = 0.8
+    yuv_input: bool = True
+
+
+class ScalingFilter:
+    """lvk::ScalingFilter — Filters/ScalingFilter.cpp:28-59: upscale (EASU) then sharpen (RCAS)."""
+
+    def __init__(self, settings: "ScalingFilterSettings | None" = None):
+        self.settings = settings or ScalingFilterSettings()
+        s = self.settings
+        assert 0.0 <= s.sharpness <= 1.0 and s.output_size[0] > 0 and s.output_size[1] > 0  # ScalingFilter.cpp:43-45
+
+    def apply(self, frame: np.ndarray, threads: int = 0) -> np.ndarray:
+        s = self.settings
+        return sharpen(upscale(frame, s.output_size, s.yuv_input, threads), s.sharpness, threads)
 
 
 def mesh_to_inverse_homography(offsets: np.ndarray, width: int, height: int) -> np.ndarray:

@@ -61,5 +61,42 @@ int main(int argc, char** argv)
     filter.configure(bad);
     if (failures != before + 1) return 4;
     std::printf("timing_ms %.3f\n", filter.timings().elapsed_ms());
+
+    // ---- the editor's other filters on the last frame (FilterParser.tpp style): Scaling, Deblocking, a Composite chain
+    auto checksum = [](const lvk::VideoFrame& f) {
+        unsigned long long sum = 0;
+        for (int y = 0; y < f.rows; y++)
+            for (size_t b = 0; b < static_cast<size_t>(f.cols) * 3; b++) sum += static_cast<unsigned long long>(f.data[y * f.step + b]) * (1 + (b + y) % 7);
+        return sum;
+    };
+    {
+        lvk::ScalingFilter scaler(lvk::ScalingFilterSettings{{960, 540}, 0.8f, false});
+        lvk::VideoFrame input(pixels.data(), w, h, static_cast<size_t>(w) * 3, lvk::VideoFrame::BGR, 77), output;
+        scaler.apply(input, output);
+        if (output.empty() || output.cols != 960 || output.rows != 540 || output.timestamp != 77) return 5;
+        std::printf("scaling %llu\n", checksum(output));
+
+        lvk::DeblockingFilter deblocker;
+        lvk::VideoFrame output2;
+        deblocker.apply(input, output2);
+        if (output2.empty() || output2.cols != w || deblocker.filter_region().width != w / 16 * 16) return 6;
+        std::printf("deblocking %llu\n", checksum(output2));
+
+        lvk::CompositeFilter chain({std::make_shared<lvk::DeblockingFilter>(),
+                                    std::make_shared<lvk::ScalingFilter>(lvk::ScalingFilterSettings{{960, 540}, 0.8f, false})});
+        lvk::VideoFrame output3;
+        chain.apply(input, output3);
+        if (output3.empty() || output3.cols != 960 || chain.filter_count() != 2) return 7;
+        std::printf("composite %llu\n", checksum(output3));
+        chain.disable_filter(0);
+        lvk::VideoFrame output4, output5;
+        chain.apply(input, output4);
+        scaler.apply(input, output5);  // (the in-place deblockers above have modified `pixels`: scale them again)
+        if (checksum(output4) != checksum(output5)) return 8;  // with the deblocker disabled the chain is the scaler alone
+
+        const int before2 = failures;
+        scaler.reconfigure([](lvk::ScalingFilterSettings& s) { s.sharpness = 1.5f; });  // LVK_ASSERT_01 (ScalingFilter.cpp:43)
+        if (failures != before2 + 1) return 9;
+    }
     return 0;
 }

@@ -42,3 +42,20 @@ def test_cpp_compat_layer_matches_python_mirror(tmp_path):
             assert int(ts) == v.timestamp == 1000 + i - 10
             assert int(total) == int(v.data.astype(np.uint64).sum())
     assert lines[14][0] == "timing_ms" and float(lines[14][1]) > 0.0
+
+    # lvk::ScalingFilter / lvk::DeblockingFilter / lvk::CompositeFilter of the compat header on the last frame
+    def checksum(a):
+        hh, ww = a.shape[:2]
+        wgt = 1 + (np.arange(ww * 3)[None, :] + np.arange(hh)[:, None]) % 7
+        return int((a.reshape(hh, ww * 3).astype(np.uint64) * wgt.astype(np.uint64)).sum())
+
+    named = {l[0]: int(l[1]) for l in lines[15:]}
+    frame = _frame(13)
+    scaler = L.ScalingFilter(L.ScalingFilterSettings((960, 540), 0.8, False), 0)
+    assert named["scaling"] == checksum(scaler.apply(L.VideoFrame(frame, 77, L.BGR)).data)
+    deblocked = L.DeblockingFilter(device=0).apply(L.VideoFrame(frame.copy(), 77, L.BGR)).data
+    assert named["deblocking"] == checksum(deblocked)
+    # the C++ deblocker worked in place on the caller's pixels (shallow copy, VideoFilter.cpp:55-58): the chain saw them
+    twice = L.DeblockingFilter(device=0).apply(L.VideoFrame(deblocked.copy(), 77, L.BGR)).data
+    assert named["composite"] == checksum(scaler.apply(L.VideoFrame(twice, 77, L.BGR)).data)
+    assert "sharpness" in out.stderr  # ScalingFilter::configure precondition reached the assert handler
