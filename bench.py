@@ -400,7 +400,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_easu_remap<homography>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "avg_kernel_us": remap_us, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "EASU is FP32-issue bound (665 executed instr/px, 74% issue utilisation), not HBM "
+                         "note": "EASU is instruction-issue bound (483 executed thread-instructions/px, 62% issue "
+                                 "utilisation, DRAM 2% busy: profiles/r01_remap_1080p_final_ncu_full.json), not HBM "
                                  "bound; see DESIGN.md 5.1"},
             "stage_us": {k: (ptotals[k] / pcounts[k] if pcounts[k] else 0.0) for k in ptotals},
             "stage_us_note": "separate untimed pass with per-stage CUDA events (profiling mode, eager launches)",
