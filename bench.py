@@ -347,11 +347,11 @@ def main():
     warm = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup)]
     timed = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup, n_frames)]
     sink = []
-    flt3.stream(warm, lambda vf: True, pinned_out[:3])
+    flt3.stream(warm, lambda vf: False, pinned_out[:3])
     barrier()
     tp = time.perf_counter()
     flt3.stream.event_record(0)
-    delivered = flt3.stream(timed, lambda vf: sink.append(vf.timestamp) or True, pinned_out[:3])
+    delivered = flt3.stream(timed, lambda vf: sink.append(vf.timestamp), pinned_out[:3])
     flt3.stream.event_record(1)
     flt3.stream.sync()
     barrier()

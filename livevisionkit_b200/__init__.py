@@ -216,14 +216,14 @@ class Stream:
                 tk, vf = pending.pop(0)
                 self.wait_output(tk)
                 delivered += 1
-                if callback(vf) is False:
+                if callback(vf):  # VideoFilter.cpp:180: a true return terminates the stream
                     for tk, _ in pending:  # let the queued downloads finish before the buffers are handed back
                         self.wait_output(tk)
                     return delivered
         for tk, vf in pending:
             self.wait_output(tk)
             delivered += 1
-            if callback(vf) is False:
+            if callback(vf):
                 break
         for tk, _ in pending:
             self.wait_output(tk)
@@ -704,7 +704,7 @@ class StabilizationFilter:
         """lvk::VideoFilter::stream(input, callback, profile) (Filters/VideoFilter.cpp:62-209); also reachable as
         `filter.stream(frames, callback)` because the `stream` attribute is callable.  Pushes every frame of
         `frames` (a sequence of VideoFrame with HOST data) through the filter and hands each non-empty output to
-        `callback(VideoFrame) -> bool` (False stops the stream, like the reference).  The reference overlaps input,
+        `callback(VideoFrame) -> bool` (a true return terminates the stream, VideoFilter.cpp:180-206; None/False continue).  The reference overlaps input,
         filtering and output with three threads; here the upload of frame t+1 and the download of output t-1 overlap
         the processing of frame t on separate CUDA streams.  `outputs`: optional list of >= 3 reusable host buffers
         (pinned memory makes the copies truly asynchronous).  Returns the number of outputs delivered."""

@@ -190,12 +190,33 @@ public:
     // VideoFilter.cpp:55-58
     void apply(const VideoFrame& input, VideoFrame& output, const bool profile = false) { apply(Frame(input), output, profile); }
 
+    // VideoFilter.cpp:62-209: reads frames until the input is exhausted, filters them and hands every non-empty output
+    // to `callback`; a TRUE return terminates the stream (:180-206).  `Capture` is cv::VideoCapture in the reference;
+    // here anything with `bool read(VideoFrame&)` (format / timestamp set by the reader).  The reference overlaps
+    // input, filtering and output with three host threads; filters with a device pipeline override stream_frames().
+    template <typename Capture>
+    void stream(Capture& input, const std::function<bool(Frame&)>& callback, const bool profile = false)
+    {
+        stream_frames([&input](Frame& f) { return input.read(f); }, callback, profile);
+    }
+
     void set_timing_samples(const size_t samples) { m_FrameTimer.set_history(samples); }
     const Stopwatch& timings() const { return m_FrameTimer; }
 
 protected:
     virtual void filter(VideoFrame&& input, VideoFrame& output) { output = std::move(input); }  // VideoFilter.cpp:229-233
     virtual void sync_device() {}
+    virtual void stream_frames(const std::function<bool(Frame&)>& read, const std::function<bool(Frame&)>& callback,
+                               const bool profile)
+    {
+        Frame input_frame, filtered_frame;
+        while (read(input_frame))
+        {
+            apply(std::move(input_frame), filtered_frame, profile);
+            if (filtered_frame.empty()) continue;  // VideoFilter.cpp:137-138
+            if (callback(filtered_frame)) return;
+        }
+    }
 private:
     Stopwatch m_FrameTimer;
     const std::string m_Alias;
@@ -312,6 +333,64 @@ private:
         output.format = static_cast<VideoFrame::Format>(m_Result.out_format);         // WarpMesh.cpp:222
     }
     void sync_device() override { lvkb200_stream_sync(m_Stream); }  // Stopwatch::sync_gpu (Timing/Stopwatch.cpp:127-131)
+
+    // VideoFilter::stream on the device pipeline: the upload of frame t+1 (lvkb200_stream_prefetch) and the download of
+    // output t-1 (submit_async / wait_output) overlap the processing of frame t; two outputs stay in flight, so output
+    // t is delivered after submit t+2.  Same outputs as apply(), frame for frame.
+    void stream_frames(const std::function<bool(Frame&)>& read, const std::function<bool(Frame&)>& callback,
+                       const bool profile) override
+    {
+        struct Pending { uint64_t ticket; size_t slot; lvkb200_result res; };
+        Frame current, next;
+        if (!read(current)) return;
+        if (profile || current.on_device)  // profiling synchronises around every frame; device frames need no copies
+        {
+            Frame out;
+            do
+            {
+                apply(std::move(current), out, profile);
+                if (!out.empty() && callback(out)) return;
+            } while (read(current));
+            return;
+        }
+        VideoFrame outputs[3];
+        std::vector<Pending> pending;
+        auto deliver_front = [&]() -> bool {
+            const Pending p = pending.front();
+            pending.erase(pending.begin());
+            check(lvkb200_stream_wait_output(m_Stream, p.ticket), "StabilizationFilter::stream");
+            VideoFrame& out = outputs[p.slot];
+            out.timestamp = p.res.out_timestamp;
+            out.format = static_cast<VideoFrame::Format>(p.res.out_format);
+            return callback(out);
+        };
+        auto drain = [&]() { for (const Pending& p : pending) lvkb200_stream_wait_output(m_Stream, p.ticket); pending.clear(); };
+        bool have = true;
+        for (size_t i = 0; have; i++)
+        {
+            LVK_ASSERT(current.has_known_format());
+            LVK_ASSERT(!current.empty());
+            m_LastWidth = current.cols; m_LastHeight = current.rows;
+            const bool have_next = read(next);
+            if (have_next && !next.empty() && !next.on_device)
+                check(lvkb200_stream_prefetch(m_Stream, next.data, next.step, next.cols, next.rows), "StabilizationFilter::stream");
+            VideoFrame& out = outputs[i % 3];
+            if (out.empty() || out.cols != current.cols || out.rows != current.rows) out.create(current.rows, current.cols);
+            Pending p{0, i % 3, {}};
+            const lvkb200_status st = lvkb200_stream_submit_async(
+                m_Stream, current.data, current.step, current.cols, current.rows, static_cast<lvkb200_format>(current.format),
+                current.timestamp, LVKB200_MEM_HOST, out.data, out.step, LVKB200_MEM_HOST, &p.res, &p.ticket);
+            if (!check(st, "StabilizationFilter::stream")) { drain(); return; }
+            m_Result = p.res;
+            if (p.res.has_output) pending.push_back(p);
+            while (pending.size() > 2)
+                if (deliver_front()) { drain(); return; }
+            current = std::move(next);  // keeps the prefetched pointer
+            have = have_next;
+        }
+        while (!pending.empty())
+            if (deliver_front()) { drain(); return; }
+    }
 
     void link_motion_resolution()  // StabilizationFilter.cpp:57-58
     {

@@ -29,17 +29,21 @@ int main(int argc, char** argv)
     if (filter.frame_delay() != 10 || filter.alias() != "Stabilization Filter") return 2;
 
     std::vector<uint8_t> pixels(static_cast<size_t>(w) * h * 3);
-    for (int i = 0; i < frames; i++)
-    {
-        // deterministic textured frame, shifted by i pixels
+    // deterministic textured frame, shifted by i pixels
+    auto render = [&](int i, uint8_t* dst) {
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++)
             {
                 const int xs = x + 2 * i, ys = y + i;
                 const uint8_t v = static_cast<uint8_t>(((xs / 16 + ys / 16) % 2) * 120 + ((xs * 7 + ys * 13) % 61) + 40);
-                uint8_t* p = &pixels[(static_cast<size_t>(y) * w + x) * 3];
+                uint8_t* p = dst + (static_cast<size_t>(y) * w + x) * 3;
                 p[0] = v; p[1] = static_cast<uint8_t>(v * 9 / 10); p[2] = static_cast<uint8_t>(v * 8 / 10);
             }
+    };
+    std::vector<std::pair<unsigned long long, unsigned long long>> applied;  // (timestamp, byte sum) of every output
+    for (int i = 0; i < frames; i++)
+    {
+        render(i, pixels.data());
         lvk::VideoFrame input(pixels.data(), w, h, static_cast<size_t>(w) * 3, lvk::VideoFrame::BGR, 1000 + i);
         lvk::VideoFrame output;
         filter.apply(input, output, /*profile=*/i == frames - 1);
@@ -51,6 +55,7 @@ int main(int argc, char** argv)
             for (int y = 0; y < output.rows; y++)
                 for (size_t b = 0; b < static_cast<size_t>(output.cols) * 3; b++) sum += output.data[y * output.step + b];
             std::printf("%d %llu %llu\n", i, static_cast<unsigned long long>(output.timestamp), sum);
+            applied.emplace_back(output.timestamp, sum);
             if (output.format != lvk::VideoFrame::BGR) return 3;
         }
     }
@@ -61,6 +66,48 @@ int main(int argc, char** argv)
     filter.configure(bad);
     if (failures != before + 1) return 4;
     std::printf("timing_ms %.3f\n", filter.timings().elapsed_ms());
+
+    // ---- VideoFilter::stream (VideoFilter.cpp:62-209) on a fresh filter: the pipelined device path must deliver exactly
+    // the frames apply() produced, and a true return from the callback must terminate it
+    {
+        struct Capture  // stands in for cv::VideoCapture: read() fills a frame the reader owns
+        {
+            int next = 0, count = 0, w = 0, h = 0;
+            const std::function<void(int, uint8_t*)>* render = nullptr;
+            bool read(lvk::VideoFrame& f)
+            {
+                if (next >= count) return false;
+                f.create(h, w);
+                (*render)(next, f.data);
+                f.format = lvk::VideoFrame::BGR;
+                f.timestamp = 1000 + next;
+                next++;
+                return true;
+            }
+        };
+        const std::function<void(int, uint8_t*)> render_fn = render;
+        lvk::StabilizationFilter streamed(settings);
+        streamed.reconfigure([](lvk::StabilizationFilterSettings& s) { s.crop_to_stable_region = false; });
+        Capture cap{0, frames, w, h, &render_fn};
+        size_t k = 0;
+        bool same = true;
+        streamed.stream(cap, [&](lvk::Frame& out) {
+            unsigned long long sum = 0;
+            for (int y = 0; y < out.rows; y++)
+                for (size_t b = 0; b < static_cast<size_t>(out.cols) * 3; b++) sum += out.data[y * out.step + b];
+            same = same && k < applied.size() && applied[k].first == out.timestamp && applied[k].second == sum;
+            k++;
+            return false;
+        });
+        if (!same || k != applied.size()) { std::fprintf(stderr, "stream: %zu outputs, expected %zu\n", k, applied.size()); return 10; }
+        lvk::StabilizationFilter stopped(settings);
+        Capture cap2{0, frames, w, h, &render_fn};
+        size_t seen = 0;
+        stopped.stream(cap2, [&](lvk::Frame&) { return ++seen >= 2; });
+        if (seen != 2) return 11;
+        std::printf("stream %zu\n", k);
+    }
+    render(frames - 1, pixels.data());
 
     // ---- the editor's other filters on the last frame (FilterParser.tpp style): Scaling, Deblocking, a Composite chain
     auto checksum = [](const lvk::VideoFrame& f) {

@@ -49,7 +49,8 @@ def test_cpp_compat_layer_matches_python_mirror(tmp_path):
         wgt = 1 + (np.arange(ww * 3)[None, :] + np.arange(hh)[:, None]) % 7
         return int((a.reshape(hh, ww * 3).astype(np.uint64) * wgt.astype(np.uint64)).sum())
 
-    named = {l[0]: int(l[1]) for l in lines[15:]}
+    assert lines[15] == ["stream", "4"]  # VideoFilter::stream delivered the 4 outputs apply() produced (checked in C++)
+    named = {l[0]: int(l[1]) for l in lines[16:]}
     frame = _frame(13)
     scaler = L.ScalingFilter(L.ScalingFilterSettings((960, 540), 0.8, False), 0)
     assert named["scaling"] == checksum(scaler.apply(L.VideoFrame(frame, 77, L.BGR)).data)

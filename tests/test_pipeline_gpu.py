@@ -158,10 +158,10 @@ def test_pipelined_stream_equals_apply(oracle):
     assert n == len(expected) == 16
     for (te, de), (tg, dg) in zip(expected, got):
         assert te == tg and (de == dg).all()
-    # early stop: the callback returning False ends the stream like the reference's
+    # early stop: a true return from the callback terminates the stream (VideoFilter.cpp:180-206)
     pipe2 = L.StabilizationFilter(s, 0)
     seen = []
-    n2 = pipe2.stream(frames, lambda vf: (seen.append(vf.timestamp), len(seen) < 3)[1], outs)
+    n2 = pipe2.stream(frames, lambda vf: (seen.append(vf.timestamp), len(seen) >= 3)[1], outs)
     assert n2 == 3 and seen == [100, 101, 102]
 
 

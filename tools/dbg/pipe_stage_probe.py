@@ -41,9 +41,9 @@ flt.stream.close()
 flt = L.StabilizationFilter(settings, device=0)
 flt.stream.set_profiling(True)
 frames = [L.VideoFrame(host[i], i, L.BGR) for i in range(N)]
-flt.stream(frames[:40], lambda vf: True, outs)
+flt.stream(frames[:40], lambda vf: False, outs)
 flt.stream.stage_totals_us(reset=True)
-flt.stream(frames[40:], lambda vf: True, outs)
+flt.stream(frames[40:], lambda vf: False, outs)
 show("pipelined host :", flt.stream)
 flt.stream.close()
 
