@@ -174,6 +174,15 @@ lvkb200_status lvkb200_stream_sync(lvkb200_stream* s);
  * flight (three output buffers): output t's remap is launched inside submit t+1 and its download overlaps frame
  * t+2, so collect it after submit t+2 (waiting earlier is correct, it only gives up part of the overlap). */
 lvkb200_status lvkb200_stream_prefetch(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height);
+/* The same announcement with the frame's format and memory space (host: upload, device: copy into the stream's ring
+ * on the copy-in stream).  Knowing the format, the library also builds the announced frame's detection image and
+ * optical-flow pyramid right behind the CURRENT frame's tracking kernels — while the host digests their results and
+ * the GPU would idle — so the next submit starts at the optical flow (the input thread of VideoFilter::stream running
+ * ahead of the filter thread, Filters/VideoFilter.cpp:76-105).  Results are identical to submitting without it.  The
+ * announced frame is processed with the chained-deblocking setting in force at the submit that follows the
+ * announcement. */
+lvkb200_status lvkb200_stream_prefetch_frame(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                             lvkb200_format format, lvkb200_memspace frame_space);
 lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
                                            lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
                                            void* out, size_t out_pitch, lvkb200_memspace out_space,

@@ -207,7 +207,7 @@ class Stream:
         pending, delivered = [], 0
         for i, f in enumerate(frames):
             if i + 1 < len(frames):
-                self.prefetch(frames[i + 1].data)
+                self.prefetch(frames[i + 1].data, frames[i + 1].format)
             out = outputs[i % len(outputs)]
             res, ticket = self.submit_async(f.data, out, f.format, f.timestamp)
             if res.has_output:
@@ -229,11 +229,19 @@ class Stream:
             self.wait_output(tk)
         return delivered
 
-    def prefetch(self, frame):
+    def prefetch(self, frame, fmt: "int | None" = None):
+        """Announces the NEXT frame (call it before submitting the current one).  Without `fmt`: starts the upload of
+        a host frame (lvkb200_stream_prefetch).  With `fmt`: host or device frame, and the library also builds its
+        detection image and pyramid behind the current frame's tracking chain (lvkb200_stream_prefetch_frame)."""
         ptr, pitch, h, w, ch, space = _buffer_info(frame)
-        if space != _capi.MEM_HOST or ch != 3:
-            raise ValueError("prefetch takes packed 8UC3 host frames")
-        _capi.check(self._lib.lvkb200_stream_prefetch(self._h, ptr, pitch, w, h))
+        if ch != 3:
+            raise ValueError("prefetch takes packed 8UC3 frames")
+        if fmt is None:
+            if space != _capi.MEM_HOST:
+                raise ValueError("prefetch of a device frame needs its format")
+            _capi.check(self._lib.lvkb200_stream_prefetch(self._h, ptr, pitch, w, h))
+        else:
+            _capi.check(self._lib.lvkb200_stream_prefetch_frame(self._h, ptr, pitch, w, h, int(fmt), space))
 
     def submit_async(self, frame, out, fmt: int = BGR, timestamp: int = 0):
         """-> (Result, ticket).  Like submit(); a host `out` is filled after the call (see wait_output)."""

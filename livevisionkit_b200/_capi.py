@@ -96,6 +96,7 @@ SYMBOLS = {
     "lvkb200_stream_submit": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, C.c_uint64, _i, _vp, _sz, _i, C.POINTER(Result)]),
     "lvkb200_stream_sync": (C.c_int, [_vp]),
     "lvkb200_stream_prefetch": (C.c_int, [_vp, _vp, _sz, _i, _i]),
+    "lvkb200_stream_prefetch_frame": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i]),
     "lvkb200_stream_submit_async": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, C.c_uint64, _i, _vp, _sz, _i, C.POINTER(Result),
                                               C.POINTER(C.c_uint64)]),
     "lvkb200_stream_wait_output": (C.c_int, [_vp, C.c_uint64]),

@@ -373,7 +373,9 @@ private:
             m_LastWidth = current.cols; m_LastHeight = current.rows;
             const bool have_next = read(next);
             if (have_next && !next.empty() && !next.on_device)
-                check(lvkb200_stream_prefetch(m_Stream, next.data, next.step, next.cols, next.rows), "StabilizationFilter::stream");
+                check(lvkb200_stream_prefetch_frame(m_Stream, next.data, next.step, next.cols, next.rows,
+                                                    static_cast<lvkb200_format>(next.format), LVKB200_MEM_HOST),
+                      "StabilizationFilter::stream");
             VideoFrame& out = outputs[i % 3];
             if (out.empty() || out.cols != current.cols || out.rows != current.rows) out.create(current.rows, current.cols);
             Pending p{0, i % 3, {}};

@@ -263,6 +263,15 @@ lvkb200_status lvkb200_stream_prefetch(lvkb200_stream* s, const void* frame, siz
     return s->prefetch(frame, pitch, width, height);
 }
 
+lvkb200_status lvkb200_stream_prefetch_frame(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
+                                             lvkb200_format format, lvkb200_memspace frame_space)
+{
+    LVKB_REQUIRE(s != nullptr);
+    LVKB_REQUIRE(format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    return s->prefetch(frame, pitch, width, height, format, frame_space);
+}
+
 lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame, size_t pitch, int width, int height,
                                            lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
                                            void* out, size_t out_pitch, lvkb200_memspace out_space,

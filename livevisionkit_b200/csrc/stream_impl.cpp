@@ -107,7 +107,8 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
         features.clear();
         grid.reset();
         frame_initialized = false;
-        pyr[0].valid = pyr[1].valid = false;
+        for (auto& py : pyr) py.valid = false;
+        for (auto& la : lookahead) la.built = false;
         if (cs) cudaStreamSynchronize(cs);
         destroy_graphs();   // the pyramids will be re-allocated for the new detection resolution
         point_capacity = 0;  // and the point capacity follows the new suppression grid
@@ -311,7 +312,8 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
         io.prm_in = h_params.device_view<TrackParams>();
     }
     if (with_events) stage_begin(ST_LK);
-    LVKB_TRY(lk_track(cs, pyr[parity ^ 1], pyr[parity], (n + 3) / 4 * 4, io, inline_points ? &lk_pack : nullptr));
+    LVKB_TRY(lk_track(cs, pyr[(parity + PYR_COUNT - 1) % PYR_COUNT], pyr[parity], (n + 3) / 4 * 4, io,
+                      inline_points ? &lk_pack : nullptr));
     if (!global && mesh_on_device())
     {
         // swap-erase compaction -> k_mesh_cgls, which also delivers the LK results
@@ -467,7 +469,9 @@ lvkb200_status lvkb200_stream::fetch_tracking(int n, bool with_model, std::vecto
     matched.resize(static_cast<size_t>(n) * 2);
     status.resize(n);
     if (n == 0) return LVKB200_OK;
-    LVKB_CUDA(cudaStreamSynchronize(cs));
+    // the chain's last kernel has written the results into mapped pinned memory; work queued behind it on cs (the next
+    // frame's pre_ingest) is not waited for
+    LVKB_CUDA(track_done ? cudaEventSynchronize(track_done) : cudaStreamSynchronize(cs));
     const uint8_t* base = h_track_out.as<uint8_t>();
     std::memcpy(matched.data(), base, sizeof(float) * matched.size());
     std::memcpy(status.data(), base + off_status, n);
@@ -589,20 +593,23 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     tracking_stability = 0.0f;  // FrameTracker.cpp:113
 
     // ---- advance time and import the next frame (FrameTracker.cpp:116-117; gray view StabilizationFilter.cpp:98)
-    cur ^= 1;
+    cur = next_pyr();
     det_pitch = align_up(static_cast<size_t>(det_w), 16);
     LVKB_CUDA(d_det.ensure(det_pitch * det_h));
     LVKB_TRY(ingest.prepare(frame.w, frame.h, det_w, det_h, cs));
     LVKB_TRY(fast.prepare(det_w, det_h));
-    LVKB_TRY(pyr[0].prepare(det_w, det_h));
-    LVKB_TRY(pyr[1].prepare(det_w, det_h));
+    for (auto& py : pyr) LVKB_TRY(py.prepare(det_w, det_h));
 
+    // the previous submit may already have built this frame's detection image and pyramid (pre_ingest)
+    const bool prebuilt = frame_prebuilt && pyr[cur].valid;
+    frame_prebuilt = false;
     stage_begin(ST_INGEST);
-    LVKB_TRY(ingest.launch(cs, frame.buf.as<uint8_t>(), frame.pitch, frame.format, d_det.as<uint8_t>(), det_pitch));
+    if (!prebuilt)
+        LVKB_TRY(ingest.launch(cs, frame.buf.as<uint8_t>(), frame.pitch, frame.format, d_det.as<uint8_t>(), det_pitch));
     stage_end(ST_INGEST);
     // FAST reads the detection image only, the pyramid is needed by LK only: FAST goes first and the pyramid is
     // queued behind it, so it is built while the host waits for and digests the FAST keypoints.
-    const bool can_track = frame_initialized && pyr[cur ^ 1].valid;
+    const bool can_track = frame_initialized && pyr[prev_pyr()].valid;
     std::vector<FastRegion> regions;
     std::vector<int> region_index;
     std::vector<std::vector<FastPoint>> fast_points;
@@ -615,7 +622,7 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
         stage_end(ST_FAST);
     }
     stage_begin(ST_PYRAMID);
-    LVKB_TRY(pyr[cur].build(cs, d_det.as<uint8_t>(), det_pitch));
+    if (!prebuilt) LVKB_TRY(pyr[cur].build(cs, d_det.as<uint8_t>(), det_pitch));
     stage_end(ST_PYRAMID);
     host_tick(HP_ENQ_DETECT);
 
@@ -663,7 +670,10 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
     host_tick(HP_DETECT);
     LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold, model_kind));
+    if (!track_done) LVKB_CUDA(cudaEventCreateWithFlags(&track_done, cudaEventDisableTiming));
+    LVKB_CUDA(cudaEventRecord(track_done, cs));
     LVKB_TRY(flush_remap());  // the previous output's remap runs beside LK + RANSAC (see apply_mesh)
+    LVKB_TRY(pre_ingest());   // the announced next frame's detection image + pyramid, behind this frame's chain
     host_tick(HP_ENQ_TRACK);
     RansacResult model{};
     std::vector<uint8_t> inliers;
@@ -881,9 +891,11 @@ lvkb200_status lvkb200_stream::ensure_pipeline()
     return LVKB200_OK;
 }
 
-// Starts the upload of the NEXT input frame (host memory) on the copy-in stream; the following submit of the same
-// pointer adopts the uploaded buffer instead of copying.
-lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int width, int height)
+// Starts the upload (host memory) or the copy (device memory) of the NEXT input frame on the copy-in stream; the
+// following submit of the same pointer adopts the buffer instead of copying.  With a known format the frame is also
+// eligible for pre_ingest.
+lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int width, int height, lvkb200_format format,
+                                        lvkb200_memspace space)
 {
     LVKB_REQUIRE(frame != nullptr && width > 0 && height > 0);
     const size_t row = static_cast<size_t>(width) * 3;
@@ -902,9 +914,44 @@ lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int wid
     }
     // this buffer was a ring buffer until the last swap: wait for the last remap that could have read it
     LVKB_TRY(wait_frame_buffers_free(cs_in));
-    LVKB_CUDA(cudaMemcpy2DAsync(ps.buf.ptr, ps.pitch, frame, pitch, row, height, cudaMemcpyHostToDevice, cs_in));
+    LVKB_CUDA(cudaMemcpy2DAsync(ps.buf.ptr, ps.pitch, frame, pitch, row, height,
+                                space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs_in));
     LVKB_CUDA(cudaEventRecord(prefetch_done[k], cs_in));
     prefetched_ptr[k] = frame;
+    lookahead[k] = Lookahead{};
+    lookahead[k].announced = format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV;
+    lookahead[k].format = format;
+    return LVKB200_OK;
+}
+
+// Builds the detection image and the pyramid of the announced NEXT frame on cs, right behind the current frame's
+// tracking chain (whose completion the host waits for through track_done, not through the stream): the ~20 us of
+// ingest + pyramid run while the host digests the chain's results instead of at the head of the next submit.
+// Everything here only moves work earlier on the same in-order stream; the next submit's results are unchanged.
+lvkb200_status lvkb200_stream::pre_ingest()
+{
+    if (profile_stages || debug_capture || !settings.stabilize_output) return LVKB200_OK;
+    for (int k = 0; k < 2; k++)
+    {
+        Lookahead& la = lookahead[k];
+        QueuedFrame& ps = prefetch_slot[k];
+        if (!la.announced || la.built || prefetched_ptr[k] == nullptr) continue;
+        const QueuedFrame& now = ring[(ring_start + ring_size - 1) % ring.size()];
+        if (ps.w != now.w || ps.h != now.h) continue;  // geometry change: the ordinary path re-plans the ingest
+        LVKB_CUDA(cudaStreamWaitEvent(cs, prefetch_done[k], 0));
+        if (deblock_enabled)
+        {
+            // CompositeFilter chain: the tracker sees the deblocked frame
+            LVKB_TRY(deblock.prepare(ps.w, ps.h, deblock_settings, cs));
+            LVKB_TRY(deblock.launch(cs, ps.buf.as<uint8_t>(), ps.pitch, la.format));
+            la.deblocked = true;
+        }
+        LVKB_TRY(ingest.launch(cs, ps.buf.as<uint8_t>(), ps.pitch, la.format, d_det.as<uint8_t>(), det_pitch));
+        la.pyr_index = next_pyr();
+        LVKB_TRY(pyr[la.pyr_index].build(cs, d_det.as<uint8_t>(), det_pitch));
+        la.built = true;
+        break;
+    }
     return LVKB200_OK;
 }
 
@@ -956,11 +1003,13 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     }
     QueuedFrame& q = ring[slot];
     int pk = -1;
-    for (int k = 0; k < 2 && frame_space == LVKB200_MEM_HOST; k++)
+    for (int k = 0; k < 2; k++)
         if (prefetched_ptr[k] == frame && prefetch_slot[k].w == width && prefetch_slot[k].h == height &&
             prefetch_slot[k].pitch == align_up(row, 16))
             pk = k;
     const bool prefetched = pk >= 0;
+    bool deblocked = false;
+    frame_prebuilt = false;
     if (prefetched)
     {
         // lvkb200_stream_prefetch already uploaded this frame into a spare buffer on the copy-in stream:
@@ -969,6 +1018,14 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
         q.pitch = prefetch_slot[pk].pitch;
         LVKB_CUDA(cudaStreamWaitEvent(cs, prefetch_done[pk], 0));
         prefetched_ptr[pk] = nullptr;
+        // look-ahead work of the previous submit (pre_ingest): only valid for the format it was announced with and
+        // for the pyramid slot this frame is about to take
+        const Lookahead& la = lookahead[pk];
+        const bool usable = la.announced && la.format == format;
+        deblocked = usable && la.deblocked;
+        frame_prebuilt = usable && la.built && la.pyr_index == next_pyr() && la.deblocked == deblock_enabled;
+        LVKB_REQUIRE(!la.deblocked || usable);  // the slot's pixels were deblocked for another format: caller error
+        lookahead[pk] = Lookahead{};
     }
     else
     {
@@ -979,7 +1036,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
                                     frame_space == LVKB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
     }
     q.w = width; q.h = height; q.format = format; q.timestamp = timestamp;
-    if (deblock_enabled)
+    if (deblock_enabled && !deblocked)
     {
         // CompositeFilter{Deblocking, Stabilization} (CompositeFilter.cpp:58-88): the first filter's output is the
         // second one's input — here the frame never leaves its ring slot
@@ -1150,7 +1207,8 @@ void lvkb200_stream::release()
     planes_in.release(); planes_out.release(); obs_frame_in.release(); obs_frame_out.release();
     format_plan.xtab.release(); format_plan.ytab.release();
     stage_in.release(); stage_out.release(); scaling_scratch.release(); mesh_dev.release(); mesh_pinned.release(); mesh_device.release();
-    ingest.release(); fast.release(); pyr[0].release(); pyr[1].release(); d_det.release();
+    ingest.release(); fast.release(); for (auto& py : pyr) py.release(); d_det.release();
+    if (track_done) { cudaEventDestroy(track_done); track_done = nullptr; }
     deblock.release(); deblock_stage.release();
     destroy_graphs();
     d_pts_prev.release(); d_src.release(); d_dst.release(); d_models.release(); d_scores.release();

@@ -42,8 +42,14 @@ struct lvkb200_stream
     // ---- device-side stages
     lvkb200::IngestPlan ingest;
     lvkb200::FastDetector fast;
-    lvkb200::LkPyramid pyr[2];
-    int cur = 0;  // pyr[cur] = current frame, pyr[cur ^ 1] = previous frame
+    // Three pyramids rotate: pyr[cur] = current frame, pyr[prev_pyr()] = previous frame, pyr[next_pyr()] = the NEXT
+    // frame's, built ahead of time when the caller announced it (pre_ingest)
+    static constexpr int PYR_COUNT = 3;
+    lvkb200::LkPyramid pyr[PYR_COUNT];
+    int cur = 0;
+    int prev_pyr() const { return (cur + PYR_COUNT - 1) % PYR_COUNT; }
+    int next_pyr() const { return (cur + 1) % PYR_COUNT; }
+    cudaEvent_t track_done = nullptr;  // recorded on cs behind the tracking chain: the host waits for THIS, not for cs
     lvkb200::DeviceBuffer d_det;
     size_t det_pitch = 0;
     lvkb200::DeviceBuffer d_pts_prev, d_src, d_dst, d_models, d_scores;
@@ -112,6 +118,19 @@ struct lvkb200_stream
     cudaStream_t cs_in = nullptr, cs_out = nullptr;
     // two spare buffers: the caller prefetches frame t+1 BEFORE submitting frame t, so two uploads are outstanding
     QueuedFrame prefetch_slot[2];
+    // Look-ahead (lvkb200_stream_prefetch_frame): the announced frame's format is known, so its detection image and
+    // pyramid are built on cs right behind the CURRENT frame's tracking chain — while the host digests that chain's
+    // results the GPU would otherwise idle — and the next submit finds them ready (pre_ingest / track).
+    struct Lookahead
+    {
+        bool announced = false;  // format known: eligible for pre_ingest
+        lvkb200_format format = LVKB200_UNKNOWN;
+        bool built = false;      // detection image + pyr[pyr_index] hold this frame
+        int pyr_index = -1;
+        bool deblocked = false;  // the chained deblocking stage already ran on the slot's buffer
+    } lookahead[2];
+    lvkb200_status pre_ingest();
+    bool frame_prebuilt = false;  // the frame being submitted was adopted from a slot whose look-ahead was built
     const void* prefetched_ptr[2] = {nullptr, nullptr};
     cudaEvent_t prefetch_done[2] = {nullptr, nullptr};  // recorded on cs_in after each upload
     int prefetch_next = 0;
@@ -150,7 +169,8 @@ struct lvkb200_stream
     uint64_t async_tickets = 0;
     bool deferred_output = false;  // set for the duration of a submit_async call
     uint64_t last_ticket = 0;
-    lvkb200_status prefetch(const void* frame, size_t pitch, int width, int height);
+    lvkb200_status prefetch(const void* frame, size_t pitch, int width, int height, lvkb200_format format = LVKB200_UNKNOWN,
+                            lvkb200_memspace space = LVKB200_MEM_HOST);
     lvkb200_status wait_output(uint64_t ticket);
     lvkb200_status ensure_pipeline();
 

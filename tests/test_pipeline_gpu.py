@@ -165,6 +165,56 @@ def test_pipelined_stream_equals_apply(oracle):
     assert n2 == 3 and seen == [100, 101, 102]
 
 
+@pytest.mark.parametrize("preset,deblock", [("H", False), ("D", False), ("H", True), ("F", False)])
+def test_lookahead_equals_plain_submit(oracle, preset, deblock):
+    """lvkb200_stream_prefetch_frame (the next frame's copy, detection image and pyramid queued behind the current
+    frame's tracking chain) only moves work earlier: every output byte and every tracker observable must equal the
+    plain submit sequence — device-resident frames, with and without the chained deblocking stage, including a
+    frame that was announced but replaced, a restart and a reconfiguration in mid-stream."""
+    torch = pytest.importorskip("torch")
+    import livevisionkit_b200 as L
+    from livevisionkit_b200 import _capi as K
+    from tools.synth import Clip
+    n = 30
+    clip = Clip("720p", "shake", frames=n)
+    mk = {"H": L.StabilizationFilterSettings.obs_homography_preset, "D": L.StabilizationFilterSettings,
+          "F": L.StabilizationFilterSettings.obs_field_preset}[preset]
+    dev = [torch.from_numpy(clip[i]).cuda() for i in range(n)]
+    decoy = torch.from_numpy(clip[3]).cuda()
+
+    def run(lookahead):
+        flt = L.StabilizationFilter(mk(), 0)
+        if deblock:
+            flt.stream.set_deblocking(L.DeblockingFilterSettings())
+        outs, results = [], []
+        for i in range(n):
+            if i == 17:
+                flt.restart()
+            if i == 22:
+                s2 = mk()
+                s2.crop_to_stable_region = not s2.crop_to_stable_region
+                flt.configure(s2)
+            if lookahead and i + 1 < n:
+                # frame 12 is announced with a buffer that is then NOT the one submitted: its look-ahead must be dropped
+                flt.stream.prefetch(decoy if i + 1 == 12 else dev[i + 1], L.BGR)
+            out = torch.empty_like(dev[0])
+            r = flt.stream.submit(dev[i], out, L.BGR, i)
+            flt.stream.sync()
+            results.append((r.has_output, r.out_timestamp, r.feature_count, round(r.tracking_stability, 6), r.has_motion))
+            outs.append(out.cpu().numpy() if r.has_output else None)
+        flt.stream.close()
+        return outs, results
+
+    plain_o, plain_r = run(False)
+    ahead_o, ahead_r = run(True)
+    assert plain_r == ahead_r
+    assert sum(o is not None for o in plain_o) >= 8  # the restart empties the 10-frame queue once
+    for a, b in zip(plain_o, ahead_o):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert (a == b).all()
+
+
 def test_stabilize_output_off_is_a_pure_delay(oracle):
     import livevisionkit_b200 as L
     from tools.synth import Clip
