@@ -869,7 +869,7 @@ static int remap_occupancy()
     static const int occ = [] {
         const char* e = getenv("LVKB200_REMAP_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
         const int v = e ? atoi(e) : 4;
-        return (v == 2 || v == 3) ? v : 4;
+        return (v == 2 || v == 3 || v == 5) ? v : 4;
     }();
     return occ;
 }
@@ -921,6 +921,7 @@ static void launch_easu(cudaStream_t cs, const RemapParams& p, const Transform& 
     {
     case 2: launch_easu_occ<MODE, YUV, 2>(cs, p, T, M, bg); break;
     case 3: launch_easu_occ<MODE, YUV, 3>(cs, p, T, M, bg); break;
+    case 5: launch_easu_occ<MODE, YUV, 5>(cs, p, T, M, bg); break;
     default: launch_easu_occ<MODE, YUV, 4>(cs, p, T, M, bg);
     }
 }
