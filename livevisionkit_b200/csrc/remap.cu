@@ -430,6 +430,19 @@ __device__ __forceinline__ void source_position(int x, int y, int W, int H, cons
     suby = fy + offy;
 }
 
+// ceil(65536 / d) for d = 1 .. STG_W: row = (i * c_inv16[width]) >> 16 == i / width for i < 65536 / width
+struct Inv16Table
+{
+    unsigned short v[STG_W + 1];
+    constexpr Inv16Table() : v{}
+    {
+        v[0] = 0;
+        for (int d = 1; d <= STG_W; d++) v[d] = (unsigned short)((65536 + d - 1) / d > 65535 ? 65535 : (65536 + d - 1) / d);
+    }
+};
+__constant__ Inv16Table c_inv16_table = Inv16Table();
+#define c_inv16 c_inv16_table.v
+
 struct PixelClass
 {
     int sx, sy;        // convert_int2_rtz(sub)
@@ -504,51 +517,37 @@ __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
 
     if (staged)
     {
-        // thread (tx, ty) stages columns tx and tx+32 of rows ty, ty+8, ty+16, ty+24: no integer division, lanes read
-        // consecutive pixels of one row
-        static_assert(STG_W <= 2 * TILE_W && STG_H <= 4 * TILE_H, "staging pattern covers the tile");
-        const uint8_t* p0 = src + (size_t)(y0 + ty) * src_pitch + 3 * (x0 + tx);
-#pragma unroll
-        for (int rr = 0; rr < 4; rr++)
-        {
-            const int r = ty + TILE_H * rr;
-            if (r < bh)
-            {
-                const uint8_t* p = p0 + (size_t)(TILE_H * rr) * src_pitch;
-                if (tx < bw)
-                {
-                    const float4 v = load_texel<YUV>(p);
-                    tile[r * STG_W + tx] = v;
-                    luma[r * STG_W + tx] = v.w;
-                }
-                if (tx + TILE_W < bw)
-                {
-                    const float4 v = load_texel<YUV>(p + 3 * TILE_W);
-                    tile[r * STG_W + tx + TILE_W] = v;
-                    luma[r * STG_W + tx + TILE_W] = v.w;
-                }
-            }
-        }
+        // The window's bw x bh texels as ONE linear index space, 256 consecutive texels per pass: every pass but the
+        // last keeps all lanes busy (a fixed row/column slot grid ran 8 slots per thread for ~2.8 texels of work,
+        // with all of their instructions issued predicated-off).  row = i / bw by multiply-shift, exact for
+        // i < 65536 / (bw - 1) (i < 1232, bw <= 44).  Lanes read consecutive pixels of a row.
+        static_assert(STG_W * STG_H <= 5 * TILE_W * TILE_H && STG_W * STG_H * (STG_W - 1) < 65536, "flat staging index");
+        constexpr int CTA = TILE_W * TILE_H;
+        const int n_tex = bw * bh;
+        const unsigned inv_bw = c_inv16[bw];  // ceil(65536 / bw): a table, not a per-thread integer division
+        const uint8_t* const p00 = src + (size_t)y0 * src_pitch + 3 * x0;
+        auto stage_texel = [&](int i) {
+            const int r = (int)(((unsigned)i * inv_bw) >> 16), c = i - r * bw;
+            const float4 v = load_texel<YUV>(p00 + (size_t)r * src_pitch + 3 * c);
+            tile[r * STG_W + c] = v;
+            luma[r * STG_W + c] = v.w;
+        };
+        // a full tile's window has > 2 * 256 texels: two unconditional-shaped passes, then the (short) rest
+        if ((int)threadIdx.x < n_tex) stage_texel((int)threadIdx.x);
+        if ((int)threadIdx.x + CTA < n_tex) stage_texel((int)threadIdx.x + CTA);
+        for (int i = (int)threadIdx.x + 2 * CTA; i < n_tex; i += CTA) stage_texel(i);
         __syncthreads();
-        // direction terms of the pixels that can be a corner f/g/j/k: columns 1 .. bw-2, rows 1 .. bh-2
-#pragma unroll
-        for (int rr = 0; rr < 4; rr++)
-        {
-            const int r = 1 + ty + TILE_H * rr;
-            if (r < bh - 1)
-            {
-#pragma unroll
-                for (int cc = 0; cc < 2; cc++)
-                {
-                    const int c = 1 + tx + TILE_W * cc;
-                    if (c < bw - 1)
-                    {
-                        const float* l = &luma[r * STG_W + c];
-                        terms[r * STG_W + c] = easu_direction_terms(l[-STG_W], l[-1], l[0], l[1], l[STG_W]);
-                    }
-                }
-            }
-        }
+        // direction terms of the texels that can be a corner f/g/j/k: columns 1 .. bw-2, rows 1 .. bh-2, same flat walk
+        const int iw = bw - 2, n_int = iw * (bh - 2);
+        const unsigned inv_iw = c_inv16[iw];
+        auto terms_texel = [&](int i) {
+            const int r = (int)(((unsigned)i * inv_iw) >> 16), c = i - r * iw;
+            const float* l = &luma[(r + 1) * STG_W + c + 1];
+            terms[(r + 1) * STG_W + c + 1] = easu_direction_terms(l[-STG_W], l[-1], l[0], l[1], l[STG_W]);
+        };
+        if ((int)threadIdx.x < n_int) terms_texel((int)threadIdx.x);
+        if ((int)threadIdx.x + CTA < n_int) terms_texel((int)threadIdx.x + CTA);
+        for (int i = (int)threadIdx.x + 2 * CTA; i < n_int; i += CTA) terms_texel(i);
     }
     __syncthreads();
 
