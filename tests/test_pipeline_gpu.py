@@ -215,6 +215,53 @@ def test_lookahead_equals_plain_submit(oracle, preset, deblock):
             assert (a == b).all()
 
 
+def test_concurrent_streams_from_two_host_threads(oracle):
+    """SURVEY 8(b) threading contract: a handle is externally synchronised, DIFFERENT handles are fully concurrent (own
+    CUDA streams, no shared mutable state).  Two host threads drive two stabilizers (different presets, different
+    clips) on the same GPU at the same time (ctypes releases the GIL inside every call); each must produce exactly the
+    bytes of its own sequential run."""
+    import threading
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    n = 24
+    jobs = [(L.StabilizationFilterSettings.obs_homography_preset, Clip("720p", "shake", frames=n, seed=5)),
+            (L.StabilizationFilterSettings, Clip((960, 540), "pan", frames=n, seed=6))]
+    frames = [[c[i] for i in range(n)] for _, c in jobs]
+
+    def run(k, sink):
+        flt = L.StabilizationFilter(jobs[k][0](), 0)
+        for i in range(n):
+            v = flt.apply(L.VideoFrame(frames[k][i], i, L.BGR))
+            sink.append(None if v.empty() else (v.timestamp, v.data.copy()))
+        flt.stream.close()
+
+    sequential = [[], []]
+    for k in range(2):
+        run(k, sequential[k])
+    concurrent = [[], []]
+    errors = []
+
+    def guarded(k):
+        try:
+            run(k, concurrent[k])
+        except Exception as e:  # surfaced below: an exception in a thread must fail the test
+            errors.append(e)
+
+    threads = [threading.Thread(target=guarded, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(2):
+        assert len(sequential[k]) == len(concurrent[k]) == n
+        assert sum(o is not None for o in sequential[k]) == n - 10
+        for a, b in zip(sequential[k], concurrent[k]):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert a[0] == b[0] and (a[1] == b[1]).all()
+
+
 def test_stabilize_output_off_is_a_pure_delay(oracle):
     import livevisionkit_b200 as L
     from tools.synth import Clip
