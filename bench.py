@@ -117,20 +117,28 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
         self.halt = threading.Event()
+        # NVML is initialised HERE (before the timed region starts), so the thread samples from its first millisecond
+        self.nvml = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = (nv, h, nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def _run_nvml(self):
         """NVML polled every ~2 ms: the timed region is only tens of milliseconds long, far below nvidia-smi's period."""
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        if self.nvml is None:
+            raise RuntimeError("NVML unavailable")
+        nv, h, smax = self.nvml
         bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
         while not self.halt.is_set():
             sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
             mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             self.rows.append([str(sm), str(smax), "0"] + ["Active" if mask & b else "Not Active" for _, b in bits])
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def run(self):
         try:
@@ -411,8 +419,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_easu_remap<homography>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "avg_kernel_us": remap_us, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "EASU is instruction-issue bound (483 executed thread-instructions/px, 62% issue "
-                                 "utilisation, DRAM 2% busy: profiles/r01_remap_1080p_final_ncu_full.json), not HBM "
+                         "note": "EASU is instruction-issue bound (471 executed thread-instructions/px, 61% issue "
+                                 "utilisation, DRAM 2% busy: profiles/r01_remap_1080p_committed_ncu_full.json), not HBM "
                                  "bound; see DESIGN.md 5.1"},
             "stage_us": {k: (ptotals[k] / pcounts[k] if pcounts[k] else 0.0) for k in ptotals},
             "stage_us_note": "separate untimed pass with per-stage CUDA events (profiling mode, eager launches)",
