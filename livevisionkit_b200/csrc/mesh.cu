@@ -167,6 +167,51 @@ __device__ __forceinline__ float spmv_t_col(const Ctx& c, const float* __restric
     return acc;
 }
 
+// (A^T u)[col], the feature part gathered by the two lanes of a vertex TOGETHER: lane `comp` (= col & 1) walks the two
+// cells 2*comp and 2*comp + 1 around the vertex and accumulates BOTH components (the x and the y row of a feature share
+// their weight and sit next to each other in u), then the lanes swap the half the other one needs.  Half the
+// sequential chain of spmv_t_col (the dependent shared-memory loads of the gather bound the CG step), one weight load
+// instead of two per feature.  Must be called by all 32 lanes with col = lane-consecutive values (col >= n: idle lane).
+__device__ __forceinline__ float spmv_t_col_pair(const Ctx& c, const float* __restrict__ u, int col)
+{
+    const int cols = c.sys.cols, rows = c.sys.rows, gw = cols - 1, gh = rows - 1;
+    const bool live = col < c.n;
+    const int comp = col & 1;
+    float acc = 0.0f, ax = 0.0f, ay = 0.0f;
+    if (live)
+    {
+        acc = c.ts * u[col];
+        for (int k = c.csc_ptr[col]; k < c.csc_ptr[col + 1]; k++) acc += c.csc_val[k] * u[c.csc_row[k]];
+        const int vtx = col >> 1;
+        const int vy = vtx / cols, vx = vtx - vy * cols;
+        const float* fwf = reinterpret_cast<const float*>(c.fw);
+        const float2* uf = reinterpret_cast<const float2*>(u + c.n + c.S);  // (x row, y row) of feature f: n + S is even
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+            // the vertex is corner i00 of cell (vx, vy) [w0], i10 of (vx-1, vy) [w3], i01 of (vx, vy-1) [w1],
+            // i11 of (vx-1, vy-1) [w2]
+            const int q = 2 * comp + h;
+            const int dx = (q & 1) ? -1 : 0, dy = (q & 2) ? -1 : 0;
+            const int wsel = (q == 0) ? 0 : (q == 1) ? 3 : (q == 2) ? 1 : 2;
+            const int cx = vx + dx, cy = vy + dy;
+            if (cx < 0 || cy < 0 || cx >= gw || cy >= gh) continue;
+            const int cell = cy * gw + cx;
+            for (int k = c.cell_start[cell]; k < c.cell_start[cell + 1]; k++)
+            {
+                const int f = c.forder[k];
+                const float a = fwf[4 * f + wsel];
+                const float2 uv = uf[f];
+                ax += a * uv.x;
+                ay += a * uv.y;
+            }
+        }
+    }
+    // lane comp = 0 owns the x column: it needs the partner's ax; lane comp = 1 owns the y column
+    const float other = __shfl_xor_sync(0xffffffffu, comp ? ax : ay, 1);
+    return acc + ((comp ? ay : ax) + other);
+}
+
 __device__ __forceinline__ void copy16(const uint8_t* src, uint8_t* dst, int bytes)
 {
     for (int i = threadIdx.x; i < (bytes + 15) / 16; i += T)
@@ -308,15 +353,19 @@ __global__ void __launch_bounds__(T, 1)
         else
         {
             const float threshold = FLT_EPSILON * FLT_EPSILON * rhs_norm2;
+            const int n_up = (n + 31) & ~31;  // whole warps enter the paired gather
             float ss = 0.0f, sz = 0.0f;
-            for (int col = tid; col < n; col += T)
+            for (int col = tid; col < n_up; col += T)
             {
-                const float v = spmv_t_col<false>(c, r, col);
-                s[col] = v;
-                const float z = invd[col] * v;
-                p[col] = z;
-                ss += v * v;
-                sz += v * z;
+                const float v = spmv_t_col_pair(c, r, col);
+                if (col < n)
+                {
+                    s[col] = v;
+                    const float z = invd[col] * v;
+                    p[col] = z;
+                    ss += v * v;
+                    sz += v * z;
+                }
             }
             const float2 t0 = block_sum2(ss, sz, red + NW);
             float abs_new = t0.y;
@@ -345,12 +394,15 @@ __global__ void __launch_bounds__(T, 1)
                     __syncthreads();
                     // s = A^T residual ; z = M^-1 s
                     ss = 0.0f; sz = 0.0f;
-                    for (int col = tid; col < n; col += T)
+                    for (int col = tid; col < n_up; col += T)
                     {
-                        const float v = spmv_t_col<false>(c, r, col);
-                        s[col] = v;
-                        ss += v * v;
-                        sz += v * (invd[col] * v);
+                        const float v = spmv_t_col_pair(c, r, col);
+                        if (col < n)
+                        {
+                            s[col] = v;
+                            ss += v * v;
+                            sz += v * (invd[col] * v);
+                        }
                     }
                     const float2 t1 = block_sum2(ss, sz, red + NW);
                     if (t1.x < threshold) break;
