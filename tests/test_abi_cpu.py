@@ -76,3 +76,18 @@ def test_no_cpu_fallback():
             continue
         src = open(os.path.join(ROOT, "livevisionkit_b200", "csrc", f)).read()
         assert "oracle/" not in src.replace("oracle/easu_ref.c", "").replace("tests/", ""), f"{f} references the oracle"
+
+
+def test_compat_header_compiles_and_links(tmp_path):
+    """The C++ mirror of the reference interface (lvk-compat) must compile as a reference caller would use it and link
+    against the in-tree library; running it needs a GPU (tests/test_compat_gpu.py)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    libdir = os.path.join(ROOT, "livevisionkit_b200")
+    exe = str(tmp_path / "test_compat")
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp", "test_compat.cpp"), "-o", exe, f"-L{libdir}",
+                           "-l:liblvkb200.so", f"-Wl,-rpath,{libdir}"])
+    assert os.path.exists(exe)
