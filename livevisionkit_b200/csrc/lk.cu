@@ -469,6 +469,11 @@ __global__ void __launch_bounds__(128)
         nextPt.y -= half;
         float2 prevDelta = make_float2(0.f, 0.f);
         const uint8_t* Jbase = a.next[level];
+        // the lane's window offsets at this level, once: the iteration below is a latency-bound dependent chain and
+        // its 64-bit address arithmetic was a tenth of the instructions on it
+        int joff[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) joff[q] = wy[q] * (int)ipitch + wx[q];
 
         for (int j = 0; j < 5; j++)
         {
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(128)
             {
                 if (lane + 32 * q < WIN * WIN)
                 {
-                    const uint8_t* s = J + (size_t)wy[q] * ipitch + wx[q];
+                    const uint8_t* s = J + joff[q];
                     const int diff = descale((int)s[0] * iw00 + (int)s[1] * iw01 + (int)s[ipitch] * iw10 +
                                                  (int)s[ipitch + 1] * iw11, 9) - Ival[q];
                     pb1 += diff * Ix[q];
