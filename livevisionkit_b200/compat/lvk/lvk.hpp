@@ -617,23 +617,25 @@ public:
     size_t filter_count() const { return m_Settings.filter_chain.size(); }
 
 private:
-    void filter(VideoFrame&& input, VideoFrame& output) override  // CompositeFilter.cpp:58-88
+    // CompositeFilter.cpp:58-88: every enabled filter consumes the previous one's output; an empty frame (a filter
+    // that is still buffering, e.g. the stabilizer's look-ahead queue) ends the pass; with save_outputs each stage's
+    // result is also kept for outputs().
+    void filter(VideoFrame&& input, VideoFrame& output) override
     {
         LVK_ASSERT(!input.empty());
-        VideoFrame& prev_filter_output = input;
-        for (size_t i = 0; i < m_Settings.filter_chain.size(); i++)
+        VideoFrame carried = std::move(input);
+        const size_t stages = m_Settings.filter_chain.size();
+        for (size_t stage = 0; stage < stages && !carried.empty(); stage++)
         {
-            if (!is_filter_enabled(i)) continue;
-            VideoFrame& filter_input = prev_filter_output;
-            VideoFrame& filter_output = m_FilterOutputs[i];
-            if (filter_input.empty()) break;  // exit the chain if a filter input is empty
-            m_Settings.filter_chain[i]->apply(std::move(filter_input), filter_output);
+            if (!m_FilterRunState[stage]) continue;
+            VideoFrame& produced = m_FilterOutputs[stage];
+            m_Settings.filter_chain[stage]->apply(std::move(carried), produced);
             if (m_Settings.save_outputs)
-                prev_filter_output = filter_output;  // clone
+                carried = produced;             // keep the stage's result, hand a copy on
             else
-                prev_filter_output = std::move(filter_output);
+                carried = std::move(produced);
         }
-        output = std::move(prev_filter_output);
+        output = std::move(carried);
     }
     std::vector<bool> m_FilterRunState;
     std::vector<Frame> m_FilterOutputs;
