@@ -120,3 +120,15 @@ def test_full_size_properties(gpu_stream, res):
     k = w // 480
     blocks = frame[:, :, 0].astype(np.int64).reshape(270, k, 480, k).sum(axis=(1, 3))
     assert (np.rint(blocks.astype(np.float32) * np.float32(1.0 / (k * k))).astype(np.uint8) == det).all()
+
+
+def test_scaling_golden(gpu_stream):
+    import livevisionkit_b200 as L
+    g = _load("scaling_golden.npz")
+    size = (int(g["size"][0]), int(g["size"][1]))
+    assert (gpu_stream.upscale(g["src"], size, False) == g["up_bgr"]).all()
+    assert (gpu_stream.upscale(g["src"], size, True) == g["up_yuv"]).all()
+    for key, sharpness in (("sharp_08", 0.8), ("sharp_00", 0.0), ("sharp_10", 1.0)):
+        assert (gpu_stream.sharpen(g["src"], sharpness) == g[key]).all(), key
+    got = gpu_stream.scaling_filter(g["src"], L.ScalingFilterSettings(size, 0.8, True))
+    assert (got == g["filter_yuv_08"]).all()

@@ -114,3 +114,15 @@ def test_upscale_properties(oracle):
     assert (f.apply(src) == oracle.sharpen(up, 0.8)).all()
     with pytest.raises(AssertionError):
         oracle.upscale(src, (60, 50))  # LVK_ASSERT(size >= src) — Image.cpp:157
+
+
+def test_oracle_reproduces_the_committed_golden(oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scaling_golden.npz"), allow_pickle=False)
+    size = (int(g["size"][0]), int(g["size"][1]))
+    assert (oracle.upscale(g["src"], size, False) == g["up_bgr"]).all()
+    assert (oracle.upscale(g["src"], size, True) == g["up_yuv"]).all()
+    assert (oracle.sharpen(g["src"], 0.8) == g["sharp_08"]).all()
+    assert (oracle.sharpen(g["src"], 0.0) == g["sharp_00"]).all()
+    assert (oracle.sharpen(g["src"], 1.0) == g["sharp_10"]).all()
+    assert (oracle.ScalingFilter(oracle.ScalingFilterSettings(size, 0.8, True)).apply(g["src"]) == g["filter_yuv_08"]).all()
