@@ -249,7 +249,10 @@ def main():
     ap.add_argument("--deblock", action="store_true",
                     help="BASELINE configs[4]: DeblockingFilter -> StabilizationFilter chained (per stream)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    # the stabilizer delivers frame t-10: the look-ahead queue must be full before the timed region starts, so that
+    # every timed step does a step's whole work (tracking AND a remap) and produces an output; the JSON line reports
+    # the warm-up actually run
+    args.warmup = max(args.warmup, 12)
     _select_workload(args.resolution, args.preset)
     if args.deblock:
         global DEBLOCK, WORKLOAD
