@@ -91,6 +91,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
             std::swap(fresh[i], ring[(ring_start + (ring_size - keep) + i) % ring.size()]);
         for (auto& f : ring) f.buf.release();
         ring.swap(fresh);
+        frame_pool_bytes = 0;  // fresh slots are empty: the next submit fills the pool again
         ring_start = 0;
         ring_size = keep;
     }
@@ -154,6 +155,20 @@ lvkb200_status lvkb200_stream::wait_frame_buffers_free(cudaStream_t stream)
     // read by the one before it or earlier.
     const uint64_t issued = remaps_launched + (pending.active ? 1 : 0);
     if (issued >= 2) LVKB_CUDA(cudaStreamWaitEvent(stream, remap_done[(issued - 2) & 1], 0));
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream::ensure_frame_pool(size_t bytes)
+{
+    if (bytes <= frame_pool_bytes) return LVKB200_OK;
+    // only EMPTY buffers are touched: a buffer that holds a queued frame (of a smaller geometry) keeps it and grows the
+    // old way, when its slot is overwritten
+    for (QueuedFrame& q : ring)
+        if (q.buf.capacity == 0) LVKB_CUDA(q.buf.ensure(bytes));
+    for (QueuedFrame& p : prefetch_slot)
+        if (p.buf.capacity == 0) LVKB_CUDA(p.buf.ensure(bytes));
+    if (spare_buf.capacity == 0) LVKB_CUDA(spare_buf.ensure(bytes));
+    frame_pool_bytes = bytes;
     return LVKB200_OK;
 }
 
@@ -901,6 +916,7 @@ lvkb200_status lvkb200_stream::prefetch(const void* frame, size_t pitch, int wid
     const size_t row = static_cast<size_t>(width) * 3;
     LVKB_REQUIRE(pitch >= row);
     LVKB_TRY(ensure_pipeline());
+    LVKB_TRY(ensure_frame_pool(align_up(row, 16) * height));
     const int k = prefetch_next;
     prefetch_next ^= 1;
     QueuedFrame& ps = prefetch_slot[k];
@@ -989,6 +1005,7 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
     dbg_matched.clear(); dbg_inliers.clear(); dbg_motion.clear(); dbg_correction.clear(); dbg_fast_counts.clear();
 
     // ---- m_FrameQueue.push(std::move(input)): the frame becomes resident in the device ring
+    LVKB_TRY(ensure_frame_pool(align_up(row, 16) * height));
     const size_t cap = ring.size();
     size_t slot;
     if (ring_size == cap)

@@ -160,6 +160,11 @@ struct lvkb200_stream
         lvkb200_memspace out_space = LVKB200_MEM_DEVICE;
     } pending;
     lvkb200_status flush_remap();
+    // Allocates every still-empty frame buffer of the rotation (ring, prefetch slots, parked buffer) at once.  Lazily,
+    // each of the first ~14 frames of a stream paid a cudaMalloc — and, in pipelined operation, a full sync_all in
+    // front of it — exactly while a short measurement (or a live stream's first quarter second) was running.
+    lvkb200_status ensure_frame_pool(size_t bytes);
+    size_t frame_pool_bytes = 0;
     lvkb200_status wait_frame_buffers_free(cudaStream_t stream);
     lvkb200_status join_remap(cudaStream_t stream);  // makes `stream` wait for every remap queued so far
     lvkb200_status sync_all();                       // host waits for cs and cs_remap
