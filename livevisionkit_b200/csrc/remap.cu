@@ -401,9 +401,10 @@ __device__ __forceinline__ void source_position(int x, int y, int W, int H, cons
     float offx, offy;
     if (MODE == 0)
     {
-        const float dz = 1.0f / (T.r3x * fx + T.r3y * fy + T.r3z);
-        offx = (T.r1x * fx + T.r1y * fy + T.r1z) * dz - fx;
-        offy = (T.r2x * fx + T.r2y * fy + T.r2z) * dz - fy;
+        // FSR.cl:423-427 under the contraction rule of oracle/easu_ref.c: (a*x + b*y) + c -> fma(a, x, b*y) + c
+        const float dz = 1.0f / (__fmaf_rn(T.r3x, fx, T.r3y * fy) + T.r3z);
+        offx = __fmaf_rn(__fmaf_rn(T.r1x, fx, T.r1y * fy) + T.r1z, dz, -fx);
+        offy = __fmaf_rn(__fmaf_rn(T.r2x, fx, T.r2y * fy) + T.r2z, dz, -fy);
     }
     else
     {

@@ -14,14 +14,18 @@
  * and of the host side that launches them
  *   LiveVisionKit/Functions/Image.cpp:28-81, 85-151.
  *
- * Semantics chosen where OpenCL leaves latitude (the reference has no OpenCL-independent definition):
- * IEEE float32; multiply-add contraction — which an OpenCL compiler is free to apply — is made EXPLICIT: every
- * a*b+c that the kernel source writes as one expression is ONE fused operation (FMA(a,b,c) below, fmaf), and
- * nothing else is contracted (compile with -ffp-contract=off); native_recip(x) := 1.0f/x;
- * convert_*_rtz/convert_uchar := C truncation.  This is the arithmetic a GPU OpenCL compiler produces for FSR.cl
- * (mad/fma contraction is on by default in OpenCL C) and it is what the CUDA kernel implements with __fmaf_rn.
- * Parity status: UNPINNED by the reference (it ships no test vectors and no OpenCL device
- * exists in the build container); pinned only against itself via tests/golden.
+ * Semantics chosen where OpenCL leaves latitude: IEEE float32; multiply-add contraction — which an OpenCL compiler is
+ * free to apply (FP_CONTRACT is ON by default in OpenCL C) — is made EXPLICIT by ONE rule: a product whose only use
+ * is one addition/subtraction is fused into it (FMA(a,b,c) below = fmaf); when both operands of the addition are such
+ * products the LEFT one is fused (a*b + c*d -> fma(a, b, c*d)); nothing else is contracted (-ffp-contract=off).
+ * The rule applies to the whole kernel text: easu_tap, easu_accumulate, easu AND the position arithmetic of the
+ * __kernel wrappers (FSR.cl:423-427).  native_recip(x) := 1.0f/x; convert_*_rtz / convert_uchar := C truncation.
+ * It is the arithmetic the exact build of the CUDA kernel implements with __fmaf_rn (0 LSB between the two).
+ * Parity status: PINNED against the reference's own kernel source compiled for the CPU (oracle/_ref/, built by
+ * oracle/ref_build/build_ref.sh from FSR.cl where it lies, strict = no contraction and contract = gcc's
+ * -ffp-contract=fast): tests/test_fsr_ref_cpu.py and the fixtures tests/golden/fsr_ref_golden.npz, which those
+ * libraries generated.  Two legal builds of the reference differ from EACH OTHER by up to 2 LSB on ~1.3e-4 of the
+ * bytes; this restatement lies inside that spread (<= 1 LSB from either, on ~1e-5 of the bytes).
  *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -pthread -shared -fPIC).
  */
@@ -241,9 +245,10 @@ static void homog_rows(int y0, int y1, void* p)
         for (int x = 0; x < c->cols; x++)
         {
             float fx = (float)x, fy = (float)y;
-            float dz = 1.0f / (r3x * fx + r3y * fy + r3z);
-            float offx = (r1x * fx + r1y * fy + r1z) * dz - fx;
-            float offy = (r2x * fx + r2y * fy + r2z) * dz - fy;
+            /* FSR.cl:423-427, contracted by the rule in the header: (a*x + b*y) + c -> fma(a, x, b*y) + c, n*dz - f -> fma */
+            float dz = 1.0f / (FMA(r3x, fx, r3y * fy) + r3z);
+            float offx = FMA(FMA(r1x, fx, r1y * fy) + r1z, dz, -fx);
+            float offy = FMA(FMA(r2x, fx, r2y * fy) + r2z, dz, -fy);
             float subx = (float)x + offx;
             float suby = (float)y + offy;
             remap_pixel(c->src, c->src_step, c->rows, c->cols, c->dst + (size_t)y * c->dst_step + 3 * x, subx, suby,
