@@ -354,6 +354,13 @@ lvkb200_status lvkb200_stream_stage_totals_us(lvkb200_stream* s, double totals[L
 lvkb200_status lvkb200_stream_set_profiling(lvkb200_stream* s, int enable);
 /* Number of CUDA kernels this library has launched in this process (all streams). */
 uint64_t lvkb200_kernel_launch_count(void);
+/* Arithmetic build of the FSR-EASU kernels (lvk::remap / lvk::upscale, Functions/OpenCL/Sources/FSR.cl:98-452), process
+ * wide.  0 (default): the "contract" build — multiply-adds fused by the compiler and native_recip = one hardware
+ * reciprocal, the liberties OpenCL C gives the reference's own device compiler (<= 1 LSB from the reference's kernels
+ * compiled with contraction).  1: the exact build — bit-identical to oracle/easu_ref.c (one explicit
+ * contraction rule, IEEE division), ~2x slower; also the initial value when LVKB200_REMAP_EXACT=1 is set. */
+void lvkb200_set_remap_exact(int exact);
+int lvkb200_remap_exact(void);
 
 /* ---- stage-level entry points (used by the parity tests: oracle inputs -> one GPU stage) --------------------- */
 

@@ -28,6 +28,16 @@ def device_count() -> int:
     return _capi.load().lvkb200_device_count()
 
 
+def set_remap_exact(exact: bool) -> None:
+    """Selects the arithmetic build of the EASU kernels (lvk::remap / lvk::upscale): False = contract build (default),
+    True = exact build, bit-identical to oracle/easu_ref.c.  Process wide; see include/lvkb200.h."""
+    _capi.load().lvkb200_set_remap_exact(1 if exact else 0)
+
+
+def remap_exact() -> bool:
+    return bool(_capi.load().lvkb200_remap_exact())
+
+
 @dataclass
 class StabilizationFilterSettings:
     """lvk::StabilizationFilterSettings (+ bases); field names and defaults are the reference's

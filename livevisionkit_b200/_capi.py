@@ -108,6 +108,8 @@ SYMBOLS = {
     "lvkb200_stream_stage_totals_us": (C.c_int, [_vp, _dp, C.POINTER(C.c_uint64), _i]),
     "lvkb200_stream_set_profiling": (C.c_int, [_vp, _i]),
     "lvkb200_kernel_launch_count": (C.c_uint64, []),
+    "lvkb200_set_remap_exact": (None, [_i]),
+    "lvkb200_remap_exact": (C.c_int, []),
     "lvkb200_remap_homography": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _dp, _u8p, _i]),
     "lvkb200_remap_mesh": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _fp, _i, _i, _u8p, _i]),
     "lvkb200_warp_mesh_apply": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _vp, _sz, _i, _fp, _i, _i, _u8p, _i, _dp]),

@@ -63,6 +63,9 @@ const char* lvkb200_last_error(void) { return last_error().c_str(); }
 
 uint64_t lvkb200_kernel_launch_count(void) { return launch_count(); }
 
+void lvkb200_set_remap_exact(int exact) { set_remap_exact(exact); }
+int lvkb200_remap_exact(void) { return remap_exact(); }
+
 const char* lvkb200_status_string(lvkb200_status s)
 {
     switch (s)

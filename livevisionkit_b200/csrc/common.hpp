@@ -89,6 +89,9 @@ cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float
 
 // lvk::upscale — easu_scale (FSR.cl:326-358, Image.cpp:155-201): p.width x p.height -> p.dst_width x p.dst_height.
 cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p);
+// Arithmetic build of the EASU launchers above: 0 = contract (remap_fast.cu, default), 1 = exact (remap.cu).
+void set_remap_exact(int exact);
+int remap_exact();
 // lvk::sharpen — rcas (FSR.cl:460-535, Image.cpp:205-233), out of place; kernel_sharpness = exp2(-2 (1 - sharpness)).
 cudaError_t launch_rcas(cudaStream_t cs, const uint8_t* src, size_t src_pitch, uint8_t* dst, size_t dst_pitch, int width,
                         int height, float kernel_sharpness);

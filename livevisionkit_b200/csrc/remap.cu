@@ -1,4 +1,6 @@
-// K8 — FSR-EASU warp/remap for sm_100a.
+// K8 (exact build; the default build is remap_fast.cu) — FSR-EASU warp/remap for sm_100a, bit-exact twin of
+// oracle/easu_ref.c.  Selected by LVKB200_REMAP_EXACT=1 / lvkb200_set_remap_exact(1), and used for sources that are not
+// 4-byte aligned.
 //
 // Replaces lvk::remap (LiveVisionKit/Functions/Image.cpp:28-151) and its OpenCL kernels
 // easu_remap / easu_remap_homography / easu (Functions/OpenCL/Sources/FSR.cl:98-318,362-452), and lvk::upscale
@@ -20,6 +22,7 @@
 #include <cstdlib>
 
 #include "common.hpp"
+#include "remap_common.cuh"
 
 namespace lvkb200
 {
@@ -28,15 +31,6 @@ namespace
 
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 8;
-
-struct Transform
-{
-    float r1x, r1y, r1z, r2x, r2y, r2z, r3x, r3y, r3z;
-};
-
-__device__ __forceinline__ float aprx_lo_rsq(float a) { return __uint_as_float(0x5f347d74u - (__float_as_uint(a) >> 1)); }
-__device__ __forceinline__ float aprx_lo_rcp(float a) { return __uint_as_float(0x7ef07ebbu - __float_as_uint(a)); }
-__device__ __forceinline__ float sat01(float x) { return fmaxf(0.0f, fminf(1.0f, x)); }
 
 // FSR.cl:131-176
 template <int CORNER>
@@ -153,9 +147,6 @@ __device__ __forceinline__ uchar3 easu(const Tap& tap, float ppx, float ppy)
     return out;
 }
 
-// (float)byte, exactly, without the quarter-rate conversion pipe (I2F): 2^23 + v has v in its low mantissa bits.
-__device__ __forceinline__ float u8_to_float(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
-
 template <bool YUV>
 __device__ __forceinline__ float4 load_texel(const uint8_t* __restrict__ p)
 {
@@ -186,47 +177,6 @@ __device__ __noinline__ uchar3 easu_global(const uint8_t* __restrict__ base, siz
     GlobalTap<YUV> tap{base, pitch};
     return easu(tap, ppx, ppy);
 }
-
-// ---- packed float32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE-RN float32 operations per issue slot) --------
-// Lane .x carries pixel A of the thread's pair, lane .y pixel B; each lane is exactly the scalar operation.
-using f2 = float2;
-__device__ __forceinline__ f2 pk(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ f2 pk1(float a) { return make_float2(a, a); }
-// Inline PTX with explicit .rn.  NOTE: nvcc 12.9 contracts a packed multiply whose only use is a packed add into
-// FFMA2 -- for the __fmul2_rn/__fadd2_rn intrinsics AND for explicit mul.rn.f32x2/add.rn.f32x2, --fmad=false
-// notwithstanding (seen in SASS and as 1-ulp parity breaks).  So no expression below feeds a mul2 result straight
-// into an add2: those few sites use scalar __fadd_rn.
-__device__ __forceinline__ unsigned long long f2_bits(f2 a)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-    return r;
-}
-__device__ __forceinline__ f2 bits_f2(unsigned long long r)
-{
-    f2 a;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
-    return a;
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return bits_f2(r);
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b)
-{
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(r);
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b)
-{
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(r);
-}
-__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
 
 // FSR.cl:131-176, the part that depends only on the SOURCE pixel C and its cross A(up) B(left) D(right) E(down):
 // {dirX, dirY, sat(|dirX|*rcp(max(|D-C|,|C-B|)))^2, sat(|dirY|*rcp(max(|E-C|,|C-A|)))^2}.  Evaluated once per source
@@ -377,60 +327,6 @@ constexpr int CTA_H = 2 * PAIR_DY;
 constexpr int STG_W = 44;  // staged source tile capacity (pixels): 32 + 3 taps + warp slack, <= 2 * TILE_W
 constexpr int STG_H = 28;  // 16 + 3 taps + warp slack, <= 4 * TILE_H
 
-// Source position of destination pixel (x, y).  MODE 0: homography (FSR.cl:407-452).  MODE 1: mesh offsets with the
-// bilinear upsample of WarpMesh::apply fused in (WarpMesh.cpp:190-191 + FSR.cl:362-403).  MODE 2: plain scaling,
-// sub = dst_coord * rscale with rscale = (T.r1x, T.r2x) (easu_scale, FSR.cl:336).
-struct MeshArgs
-{
-    const float2* mesh;
-    int cols, rows;
-    double sx, sy;
-};
-
-template <int MODE>
-__device__ __forceinline__ void source_position(int x, int y, int W, int H, const Transform& T, const MeshArgs& M,
-                                                float& subx, float& suby)
-{
-    const float fx = (float)x, fy = (float)y;
-    if (MODE == 2)
-    {
-        subx = fx * T.r1x;
-        suby = fy * T.r2x;
-        return;
-    }
-    float offx, offy;
-    if (MODE == 0)
-    {
-        // FSR.cl:423-427 under the contraction rule of oracle/easu_ref.c: (a*x + b*y) + c -> fma(a, x, b*y) + c
-        const float dz = 1.0f / (__fmaf_rn(T.r3x, fx, T.r3y * fy) + T.r3z);
-        offx = __fmaf_rn(__fmaf_rn(T.r1x, fx, T.r1y * fy) + T.r1z, dz, -fx);
-        offy = __fmaf_rn(__fmaf_rn(T.r2x, fx, T.r2y * fy) + T.r2z, dz, -fy);
-    }
-    else
-    {
-        // cv::resize(mesh -> WxH, INTER_LINEAR) on CV_32FC2, then cv::multiply by (W, H).
-        float mx = (float)(((double)x + 0.5) * M.sx - 0.5);
-        float my = (float)(((double)y + 0.5) * M.sy - 0.5);
-        int cx = (int)floorf(mx), cy = (int)floorf(my);
-        mx -= (float)cx;
-        my -= (float)cy;
-        if (cx < 0) { mx = 0.0f; cx = 0; }
-        if (cx >= M.cols - 1) { mx = 0.0f; cx = M.cols - 1; }
-        if (cy < 0) { my = 0.0f; cy = 0; }
-        if (cy >= M.rows - 1) { my = 0.0f; cy = M.rows - 1; }
-        const int cx1 = min(cx + 1, M.cols - 1), cy1 = min(cy + 1, M.rows - 1);
-        const float2 m00 = __ldg(&M.mesh[cy * M.cols + cx]), m01 = __ldg(&M.mesh[cy * M.cols + cx1]);
-        const float2 m10 = __ldg(&M.mesh[cy1 * M.cols + cx]), m11 = __ldg(&M.mesh[cy1 * M.cols + cx1]);
-        const float ax0 = 1.0f - mx, ax1 = mx, ay0 = 1.0f - my, ay1 = my;
-        const float h0x = m00.x * ax0 + m01.x * ax1, h0y = m00.y * ax0 + m01.y * ax1;
-        const float h1x = m10.x * ax0 + m11.x * ax1, h1y = m10.y * ax0 + m11.y * ax1;
-        offx = (h0x * ay0 + h1x * ay1) * (float)W;
-        offy = (h0y * ay0 + h1y * ay1) * (float)H;
-    }
-    subx = fx + offx;
-    suby = fy + offy;
-}
-
 // ceil(65536 / d) for d = 1 .. STG_W: row = (i * c_inv16[width]) >> 16 == i / width for i < 65536 / width
 struct Inv16Table
 {
@@ -443,27 +339,6 @@ struct Inv16Table
 };
 __constant__ Inv16Table c_inv16_table = Inv16Table();
 #define c_inv16 c_inv16_table.v
-
-struct PixelClass
-{
-    int sx, sy;        // convert_int2_rtz(sub)
-    float ppx, ppy;    // sub - floor(sub)
-    bool border, in_src, do_easu;
-};
-
-__device__ __forceinline__ PixelClass classify(float subx, float suby, int W, int H, bool inside)
-{
-    PixelClass c;
-    c.sx = __float2int_rz(subx);
-    c.sy = __float2int_rz(suby);
-    c.ppx = subx - floorf(subx);
-    c.ppy = suby - floorf(suby);
-    // FSR.cl:387-399
-    c.border = (c.sx < 1) || (c.sy < 1) || (c.sx >= W - 4) || (c.sy >= H - 4);
-    c.in_src = (c.sx >= 0) && (c.sx < W) && (c.sy >= 0) && (c.sy < H);
-    c.do_easu = inside && !c.border;
-    return c;
-}
 
 template <int MODE, bool YUV, int OCC>
 __global__ void __launch_bounds__(TILE_W* TILE_H, OCC)
@@ -926,7 +801,7 @@ static void launch_easu(cudaStream_t cs, const RemapParams& p, const Transform& 
     }
 }
 
-cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9])
+cudaError_t launch_remap_homography_exact(cudaStream_t cs, const RemapParams& p, const float t[9])
 {
     const Transform T{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]};
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
@@ -938,7 +813,7 @@ cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const
     return cudaGetLastError();
 }
 
-cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p)
+cudaError_t launch_upscale_exact(cudaStream_t cs, const RemapParams& p)
 {
     // Image.cpp:191-194: rscale = (float)src / (float)dst per axis
     Transform T{};
@@ -953,7 +828,7 @@ cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p)
     return cudaGetLastError();
 }
 
-cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
+cudaError_t launch_remap_mesh_exact(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
 {
     const uchar3 bg = make_uchar3(p.bg[0], p.bg[1], p.bg[2]);
     // cv::resize: scale = 1 / (dsize / ssize), in double

@@ -1,0 +1,536 @@
+// K8 (default build) — FSR-EASU warp/remap for sm_100a, the "contract" arithmetic.
+//
+// Replaces lvk::remap / lvk::upscale (LiveVisionKit/Functions/Image.cpp:28-201) and the OpenCL kernels easu_remap,
+// easu_remap_homography, easu_scale, easu (Functions/OpenCL/Sources/FSR.cl:98-452).
+//
+// Arithmetic contract.  OpenCL C lets the device compiler fuse multiply-adds (FP_CONTRACT ON) and gives `/` and
+// native_recip implementation-defined last-bit behaviour, so the reference has no single bit-exact result: its own
+// source compiled strict vs contracted differs by up to 2 LSB on ~1.3e-4 of the bytes (oracle/_ref,
+// tests/test_fsr_ref_cpu.py).  This translation unit takes exactly those liberties and no others: it is compiled with
+// mul-add contraction ON, native_recip(aW) is one MUFU.RCP, operations are never re-associated.  The SOURCE POSITIONS
+// (remap_common.cuh) are computed with the explicit roundings of the exact build, so both builds classify every pixel
+// identically and sample the same 12 texels; only the last bits of the filter weights differ.  Measured against the
+// reference's compiled kernels: tests/test_remap_gpu.py (<= 1 LSB vs the contract build, inside the strict-contract
+// spread vs the strict build).  The exact build (remap.cu, LVKB200_REMAP_EXACT=1 / lvkb200_set_remap_exact) stays the
+// bit-exact twin of oracle/easu_ref.c.
+//
+// Design — what changed against remap.cu and why (profiles/r01_remap_1080p_committed_*: 471 instr/px, 61 % issue):
+//   * 128 threads per 32x16 destination tile, FOUR pixels per thread (rows ty, ty+4, ty+8, ty+12 of one column) as
+//     two float32x2 pairs: the per-thread prologue, the source-window reduction and the column terms of the
+//     projective map are paid once per four pixels, 96 registers per thread leave no spills;
+//   * staging reads the window with 32-bit loads (each lane: the two words that hold its texel, funnel-shifted),
+//     one PRMT + half an FFMA2 per byte ((2^23 + b) * norm - 2^23 * norm is exactly fl(b * norm));
+//   * the window's bounding box comes from one REDUX per warp and ONE barrier (no shared atomics);
+//   * nearest-texel min/max as FMNMX3, reciprocal as MUFU.RCP, contraction everywhere.
+//   Unchanged: the staged float4 {c0,c1,c2,luma}/255 tile, direction terms once per SOURCE pixel, LDS.128 gathers,
+//   conflict-free because a warp's lanes are 32 consecutive destination columns.
+// Roofline: 6 B/px algorithmic (3 read + 3 written); bound by instruction issue and shared-memory bandwidth
+// (16 LDS.128 per pixel = 2 clk/px/SM), not by HBM — DESIGN.md 5.1.
+
+#include <atomic>
+#include <cstdlib>
+
+#include "common.hpp"
+#include "remap_common.cuh"
+
+namespace lvkb200
+{
+
+// exact-build launchers (remap.cu)
+cudaError_t launch_remap_homography_exact(cudaStream_t cs, const RemapParams& p, const float t[9]);
+cudaError_t launch_remap_mesh_exact(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows);
+cudaError_t launch_upscale_exact(cudaStream_t cs, const RemapParams& p);
+
+namespace
+{
+
+constexpr int FT_W = 32;        // destination tile
+constexpr int FT_H = 16;
+constexpr int FT_THREADS = 128;  // 4 warps: thread (tx = lane, ty = warp) owns rows ty + 4k, k = 0..3, of column tx
+constexpr int FT_CTAS = 7;       // default resident CTAs per SM the kernel is compiled for (<= 72 registers, 31 KB shared)
+constexpr int FW = 40;           // staged source window capacity, texels (32 + 3 taps + 5 slack), <= 64
+constexpr int FH = 22;           // 16 + 3 taps + 3 slack
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// FSR.cl:131-176, the part that depends only on SOURCE pixel C and its cross A(up) B(left) D(right) E(down):
+// {dirX, dirY, sat(|dirX| * rcp(max(|D-C|, |C-B|)))^2, sat(|dirY| * rcp(max(|E-C|, |C-A|)))^2}
+__device__ __forceinline__ float4 direction_terms(float lA, float lB, float lC, float lD, float lE)
+{
+    const float dc = lD - lC, cb = lC - lB, dirX = lD - lB;
+    const float ec = lE - lC, ca = lC - lA, dirY = lE - lA;
+    float lenX = __saturatef(fabsf(dirX) * aprx_lo_rcp(fmaxf(fabsf(dc), fabsf(cb))));
+    float lenY = __saturatef(fabsf(dirY) * aprx_lo_rcp(fmaxf(fabsf(ec), fabsf(ca))));
+    return make_float4(dirX, dirY, lenX * lenX, lenY * lenY);
+}
+
+// FSR.cl:98-126 for the two pixels of a pair (lane .x = pixel A, .y = pixel B); t1 = offy*diry, t2 = offy*dirx.
+// mul2 -> add2 chains are fused into FFMA2 by ptxas (this translation unit allows contraction).
+__device__ __forceinline__ void tap2(float (&aA)[3], float (&aB)[3], f2& aW, f2 offx, f2 t1, f2 t2, f2 dirx, f2 ndiry,
+                                     f2 lenx, f2 leny, f2 lob, f2 clp, const float4& cA, const float4& cB)
+{
+    f2 vx = fma2(offx, dirx, t1);
+    f2 vy = fma2(offx, ndiry, t2);
+    vx = mul2(vx, lenx);
+    vy = mul2(vy, leny);
+    f2 d2 = fma2(vx, vx, mul2(vy, vy));
+    d2.x = fminf(d2.x, clp.x);
+    d2.y = fminf(d2.y, clp.y);
+    f2 wA = fma2(lob, d2, pk1(-1.0f));
+    f2 wB = fma2(pk1(2.0f / 5.0f), d2, pk1(-1.0f));
+    wA = mul2(wA, wA);
+    wB = fma2(pk1(25.0f / 16.0f), mul2(wB, wB), pk1(-(25.0f / 16.0f - 1.0f)));
+    const f2 w = mul2(wB, wA);
+    aA[0] = fmaf(cA.x, w.x, aA[0]);
+    aA[1] = fmaf(cA.y, w.x, aA[1]);
+    aA[2] = fmaf(cA.z, w.x, aA[2]);
+    aB[0] = fmaf(cB.x, w.y, aB[0]);
+    aB[1] = fmaf(cB.y, w.y, aB[1]);
+    aB[2] = fmaf(cB.z, w.y, aB[2]);
+    aW = add2(aW, w);
+}
+
+// FSR.cl:284-296, 316-317: dering clamp to the 4 nearest texels, normalise, truncate.  Returns 0x00c2c1c0.
+__device__ __forceinline__ unsigned resolve(const float (&a)[3], float aW, const float4& f, const float4& g, const float4& j,
+                                            const float4& k)
+{
+    const float mi0 = fminf(fminf(f.x, g.x), fminf(j.x, k.x)), ma0 = fmaxf(fmaxf(f.x, g.x), fmaxf(j.x, k.x));
+    const float mi1 = fminf(fminf(f.y, g.y), fminf(j.y, k.y)), ma1 = fmaxf(fmaxf(f.y, g.y), fmaxf(j.y, k.y));
+    const float mi2 = fminf(fminf(f.z, g.z), fminf(j.z, k.z)), ma2 = fmaxf(fmaxf(f.z, g.z), fmaxf(j.z, k.z));
+    const float rcpW = rcp_approx(aW);  // native_recip
+    const float v0 = fminf(ma0, fmaxf(mi0, a[0] * rcpW));
+    const float v1 = fminf(ma1, fmaxf(mi1, a[1] * rcpW));
+    const float v2 = fminf(ma2, fmaxf(mi2, a[2] * rcpW));
+    // convert_uchar3: truncation (values lie in [0, 1] * 255)
+    const unsigned b0 = (unsigned)__float2int_rz(v0 * 255.0f), b1 = (unsigned)__float2int_rz(v1 * 255.0f),
+                   b2 = (unsigned)__float2int_rz(v2 * 255.0f);
+    return b0 | (b1 << 8) | (b2 << 16);
+}
+
+// FSR.cl:181-318 for a pixel pair; tA / tB = &tile[f], dA / dB = &terms[f] of pixel A / B.
+__device__ __forceinline__ void easu_pair(const float4* __restrict__ tA, const float4* __restrict__ tB,
+                                          const float4* __restrict__ dA, const float4* __restrict__ dB, f2 ppx, f2 ppy,
+                                          unsigned& outA, unsigned& outB)
+{
+    constexpr int S = FW;
+    // ---- direction / length: bilinear blend of the four corners' terms, corner order f, g, j, k (FSR.cl:246-249)
+    const f2 omx = add2(pk1(1.0f), neg2(ppx)), omy = add2(pk1(1.0f), neg2(ppy));
+    const f2 w0 = mul2(omx, omy), w1 = mul2(ppx, omy), w2 = mul2(omx, ppy), w3 = mul2(ppx, ppy);
+    f2 dirx, diry, len;
+    {
+        float lenA = 0.0f, dxA = 0.0f, dyA = 0.0f, lenB = 0.0f, dxB = 0.0f, dyB = 0.0f;
+#define LVKB_ACC(OFF, WA, WB)                                                                                         \
+    {                                                                                                                 \
+        const float4 qa = dA[OFF], qb = dB[OFF];                                                                      \
+        dxA = fmaf(qa.x, WA, dxA); lenA = fmaf(qa.z, WA, lenA);                                                       \
+        dyA = fmaf(qa.y, WA, dyA); lenA = fmaf(qa.w, WA, lenA);                                                       \
+        dxB = fmaf(qb.x, WB, dxB); lenB = fmaf(qb.z, WB, lenB);                                                       \
+        dyB = fmaf(qb.y, WB, dyB); lenB = fmaf(qb.w, WB, lenB);                                                       \
+    }
+        LVKB_ACC(0, w0.x, w0.y)
+        LVKB_ACC(1, w1.x, w1.y)
+        LVKB_ACC(S, w2.x, w2.y)
+        LVKB_ACC(S + 1, w3.x, w3.y)
+#undef LVKB_ACC
+        dirx = pk(dxA, dxB); diry = pk(dyA, dyB); len = pk(lenA, lenB);
+    }
+
+    f2 dirR = fma2(dirx, dirx, mul2(diry, diry));
+    const bool zA = dirR.x < (1.0f / 32768.0f), zB = dirR.y < (1.0f / 32768.0f);
+    dirR = pk(zA ? 1.0f : aprx_lo_rsq(dirR.x), zB ? 1.0f : aprx_lo_rsq(dirR.y));
+    dirx = pk(zA ? 1.0f : dirx.x, zB ? 1.0f : dirx.y);
+    dirx = mul2(dirx, dirR);
+    diry = mul2(diry, dirR);
+
+    len = mul2(len, pk1(0.5f));
+    len = mul2(len, len);
+
+    f2 stretch = fma2(dirx, dirx, mul2(diry, diry));
+    stretch = mul2(stretch, pk(aprx_lo_rcp(fmaxf(fabsf(dirx.x), fabsf(diry.x))),
+                               aprx_lo_rcp(fmaxf(fabsf(dirx.y), fabsf(diry.y)))));
+    const f2 len2x = fma2(add2(stretch, pk1(-1.0f)), len, pk1(1.0f));
+    const f2 len2y = fma2(pk1(-0.5f), len, pk1(1.0f));
+    const f2 lob = fma2(pk1((1.0f / 4.0f - 0.04f) - 0.5f), len, pk1(0.5f));
+    const f2 clp = pk(aprx_lo_rcp(lob.x), aprx_lo_rcp(lob.y));
+    const f2 ndiry = neg2(diry);
+
+    // ---- the 12 taps, in the accumulation order of FSR.cl:302-313 (b c i j f e k l h g n o)
+    const f2 nppx = neg2(ppx), nppy = neg2(ppy);
+    const f2 oxm = add2(pk1(-1.0f), nppx), ox0 = nppx, ox1 = add2(pk1(1.0f), nppx), ox2 = add2(pk1(2.0f), nppx);
+    const f2 oym = add2(pk1(-1.0f), nppy), oy0 = nppy, oy1 = add2(pk1(1.0f), nppy), oy2 = add2(pk1(2.0f), nppy);
+    const f2 t1m = mul2(oym, diry), t10 = mul2(oy0, diry), t11 = mul2(oy1, diry), t12 = mul2(oy2, diry);
+    const f2 t2m = mul2(oym, dirx), t20 = mul2(oy0, dirx), t21 = mul2(oy1, dirx), t22 = mul2(oy2, dirx);
+
+    float aA[3] = {0.0f, 0.0f, 0.0f}, aB[3] = {0.0f, 0.0f, 0.0f};
+    f2 aW = pk1(0.0f);
+    const float4 fA = tA[0], gA = tA[1], jA = tA[S], kA = tA[S + 1];
+    const float4 fB = tB[0], gB = tB[1], jB = tB[S], kB = tB[S + 1];
+#define LVKB_TAP(DX, DY, OX, T1, T2)                                                                                  \
+    tap2(aA, aB, aW, OX, T1, T2, dirx, ndiry, len2x, len2y, lob, clp, tA[(DY) * S + (DX)], tB[(DY) * S + (DX)]);
+#define LVKB_TAPR(CA, CB, OX, T1, T2) tap2(aA, aB, aW, OX, T1, T2, dirx, ndiry, len2x, len2y, lob, clp, CA, CB);
+    LVKB_TAP(0, -1, ox0, t1m, t2m)   // b
+    LVKB_TAP(1, -1, ox1, t1m, t2m)   // c
+    LVKB_TAP(-1, 1, oxm, t11, t21)   // i
+    LVKB_TAPR(jA, jB, ox0, t11, t21) // j
+    LVKB_TAPR(fA, fB, ox0, t10, t20) // f
+    LVKB_TAP(-1, 0, oxm, t10, t20)   // e
+    LVKB_TAPR(kA, kB, ox1, t11, t21) // k
+    LVKB_TAP(2, 1, ox2, t11, t21)    // l
+    LVKB_TAP(2, 0, ox2, t10, t20)    // h
+    LVKB_TAPR(gA, gB, ox1, t10, t20) // g
+    LVKB_TAP(0, 2, ox0, t12, t22)    // n
+    LVKB_TAP(1, 2, ox1, t12, t22)    // o
+#undef LVKB_TAP
+#undef LVKB_TAPR
+
+    outA = resolve(aA, aW.x, fA, gA, jA, kA);
+    outB = resolve(aB, aW.y, fB, gB, jB, kB);
+}
+
+// Slow path for pixels whose taps do not lie in the staged window (extreme warps): straight from global memory with
+// the same contracted arithmetic.  One pixel, scalar.
+template <bool YUV>
+__device__ __noinline__ unsigned easu_global(const uint8_t* __restrict__ base, size_t pitch, float ppx, float ppy)
+{
+    const float norm = 0.00392156862f;
+    auto tex = [&](int dx, int dy) {
+        const uint8_t* p = base + (ptrdiff_t)dy * (ptrdiff_t)pitch + 3 * dx;
+        float4 t;
+        t.x = (float)__ldg(p) * norm; t.y = (float)__ldg(p + 1) * norm; t.z = (float)__ldg(p + 2) * norm;
+        t.w = YUV ? fmaf(t.z, 0.5f, fmaf(t.x, 0.5f, t.y)) : t.x;
+        return t;
+    };
+    const float4 b = tex(0, -1), c = tex(1, -1), e = tex(-1, 0), f = tex(0, 0), g = tex(1, 0), h = tex(2, 0);
+    const float4 i = tex(-1, 1), j = tex(0, 1), k = tex(1, 1), l = tex(2, 1), n = tex(0, 2), o = tex(1, 2);
+    const float4 qf = direction_terms(b.w, e.w, f.w, g.w, j.w), qg = direction_terms(c.w, f.w, g.w, h.w, k.w);
+    const float4 qj = direction_terms(f.w, i.w, j.w, k.w, n.w), qk = direction_terms(g.w, j.w, k.w, l.w, o.w);
+    const float w0 = (1.0f - ppx) * (1.0f - ppy), w1 = ppx * (1.0f - ppy), w2 = (1.0f - ppx) * ppy, w3 = ppx * ppy;
+    float dirx = 0.0f, diry = 0.0f, len = 0.0f;
+    dirx = fmaf(qf.x, w0, dirx); len = fmaf(qf.z, w0, len); diry = fmaf(qf.y, w0, diry); len = fmaf(qf.w, w0, len);
+    dirx = fmaf(qg.x, w1, dirx); len = fmaf(qg.z, w1, len); diry = fmaf(qg.y, w1, diry); len = fmaf(qg.w, w1, len);
+    dirx = fmaf(qj.x, w2, dirx); len = fmaf(qj.z, w2, len); diry = fmaf(qj.y, w2, diry); len = fmaf(qj.w, w2, len);
+    dirx = fmaf(qk.x, w3, dirx); len = fmaf(qk.z, w3, len); diry = fmaf(qk.y, w3, diry); len = fmaf(qk.w, w3, len);
+    float dirR = fmaf(dirx, dirx, diry * diry);
+    const bool zro = dirR < (1.0f / 32768.0f);
+    dirR = zro ? 1.0f : aprx_lo_rsq(dirR);
+    dirx = zro ? 1.0f : dirx;
+    dirx *= dirR;
+    diry *= dirR;
+    len = len * 0.5f;
+    len *= len;
+    const float stretch = fmaf(dirx, dirx, diry * diry) * aprx_lo_rcp(fmaxf(fabsf(dirx), fabsf(diry)));
+    const float len2x = fmaf(stretch - 1.0f, len, 1.0f), len2y = fmaf(-0.5f, len, 1.0f);
+    const float lob = fmaf((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f), clp = aprx_lo_rcp(lob);
+    float a[3] = {0.0f, 0.0f, 0.0f}, aW = 0.0f;
+    auto tap = [&](float offx, float offy, const float4& cc) {
+        float vx = fmaf(offx, dirx, offy * diry), vy = fmaf(offx, -diry, offy * dirx);
+        vx *= len2x;
+        vy *= len2y;
+        const float d2 = fminf(fmaf(vx, vx, vy * vy), clp);
+        float wA = fmaf(lob, d2, -1.0f), wB = fmaf(2.0f / 5.0f, d2, -1.0f);
+        wA *= wA;
+        wB = fmaf(25.0f / 16.0f, wB * wB, -(25.0f / 16.0f - 1.0f));
+        const float w = wB * wA;
+        a[0] = fmaf(cc.x, w, a[0]); a[1] = fmaf(cc.y, w, a[1]); a[2] = fmaf(cc.z, w, a[2]);
+        aW += w;
+    };
+    tap(0.0f - ppx, -1.0f - ppy, b); tap(1.0f - ppx, -1.0f - ppy, c); tap(-1.0f - ppx, 1.0f - ppy, i);
+    tap(0.0f - ppx, 1.0f - ppy, j); tap(0.0f - ppx, 0.0f - ppy, f); tap(-1.0f - ppx, 0.0f - ppy, e);
+    tap(1.0f - ppx, 1.0f - ppy, k); tap(2.0f - ppx, 1.0f - ppy, l); tap(2.0f - ppx, 0.0f - ppy, h);
+    tap(1.0f - ppx, 0.0f - ppy, g); tap(0.0f - ppx, 2.0f - ppy, n); tap(1.0f - ppx, 2.0f - ppy, o);
+    return resolve(a, aW, f, g, j, k);
+}
+
+template <int MODE, bool YUV, int CTAS>
+__global__ void __launch_bounds__(FT_THREADS, CTAS)
+    k_easu_remap_fast(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch, int W,
+                      int H, int dW, int dH, Transform T, MeshArgs M, unsigned bg)
+{
+    // W x H = source image (border classification), dW x dH = destination image (== source except for MODE 2)
+    __shared__ float4 tile[FH * FW];   // {c0, c1, c2, luma} / 255 of the staged source texels
+    __shared__ float4 terms[FH * FW];  // direction_terms of the same texels (interior only)
+    __shared__ float luma[FH * FW];    // tile[].w again, contiguous: the 5-point cross reads are conflict-free
+    __shared__ int4 wbox[FT_THREADS / 32];
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * FT_W + tx;
+    const int ybase = blockIdx.y * FT_H + ty;
+
+    // ---- source positions + classification of this thread's four pixels (rows ybase + 4k).  Kept per pixel: the
+    // fractional position and ONE linear texel index lin = sy * FW + sx (the staged path needs nothing else; the rare
+    // nearest / direct paths recompute the position).
+    int lin[4];
+    float ppx[4], ppy[4];
+    unsigned easu_mask = 0, nearest_mask = 0, inside_mask = 0;
+    int minx = INT_MAX, miny = INT_MAX, maxx = INT_MIN, maxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const int y = ybase + 4 * k;
+        float fx, fy;
+        source_position<MODE>(x, y, W, H, T, M, fx, fy);
+        const int sx = __float2int_rz(fx), sy = __float2int_rz(fy);  // convert_int2_rtz
+        ppx[k] = fx - floorf(fx);
+        ppy[k] = fy - floorf(fy);
+        lin[k] = sy * FW + sx;
+        const bool inside = (x < dW) && (y < dH);
+        // FSR.cl:387-399: EASU iff 1 <= sx < W-4 and 1 <= sy < H-4; nearest neighbour iff inside the source otherwise
+        const bool easu = inside && (unsigned)(sx - 1) < (unsigned)(W - 5) && (unsigned)(sy - 1) < (unsigned)(H - 5);
+        const bool in_src = (unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H;
+        if (inside) inside_mask |= 1u << k;
+        if (easu) easu_mask |= 1u << k;
+        if (inside && !easu && in_src) nearest_mask |= 1u << k;
+        minx = min(minx, easu ? sx : INT_MAX); maxx = max(maxx, easu ? sx : INT_MIN);
+        miny = min(miny, easu ? sy : INT_MAX); maxy = max(maxy, easu ? sy : INT_MIN);
+    }
+
+    // ---- bounding box of f over the tile's EASU pixels: one REDUX per component and warp, one barrier
+    {
+        const int wminx = __reduce_min_sync(0xffffffffu, minx), wminy = __reduce_min_sync(0xffffffffu, miny);
+        const int wmaxx = __reduce_max_sync(0xffffffffu, maxx), wmaxy = __reduce_max_sync(0xffffffffu, maxy);
+        if (tx == 0) wbox[ty] = make_int4(wminx, wminy, wmaxx, wmaxy);
+    }
+    __syncthreads();
+    int bx0, by0, bx1, by1;
+    {
+        const int4 a = wbox[0], b = wbox[1], c = wbox[2], d = wbox[3];
+        bx0 = min(min(a.x, b.x), min(c.x, d.x)); by0 = min(min(a.y, b.y), min(c.y, d.y));
+        bx1 = max(max(a.z, b.z), max(c.z, d.z)); by1 = max(max(a.w, b.w), max(c.w, d.w));
+    }
+    const bool any_easu = bx0 != INT_MAX;
+    const int x0 = bx0 - 1, y0 = by0 - 1;                  // taps reach f-1 .. f+2
+    const int bw = bx1 + 2 - x0 + 1, bh = by1 + 2 - y0 + 1;  // all inside the image (the border band is excluded)
+    const bool staged = any_easu && bw <= FW && bh <= FH;
+
+    if (staged)
+    {
+        // ---- stage the window.  A texel's 3 bytes lie in the aligned word pair at byte offset (3c) & ~3 of its row: two
+        // 32-bit loads (neighbouring lanes share words, L1 serves them), one funnel shift (SHF takes the shift modulo
+        // 32), then one PRMT + one FFMA per byte.  All loops have compile-time trip counts and predicated bodies: the
+        // windows are a handful of rows per warp, loop control would cost more than the work.
+        const uint8_t* const p00 = src + (size_t)y0 * src_pitch + 3 * x0;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p00) & 3u);  // src and src_pitch are 4-byte aligned
+        const uint8_t* const a00 = p00 - mis;
+        const unsigned pitch32 = (unsigned)src_pitch;
+        const float norm = 0.00392156862f, bias = -(8388608.0f * 0.00392156862f);
+        // texel (r, c) of the window -> tile[r * FW + c], luma[...]
+        auto stage = [&](const uint8_t* wordp, unsigned shift, int o) {
+            const unsigned* wp = reinterpret_cast<const unsigned*>(wordp);
+            const unsigned px = __funnelshift_r(__ldg(wp), __ldg(wp + 1), shift);  // bytes c0 c1 c2 (+ one foreign byte)
+            float4 v;
+            v.x = fmaf(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440)), norm, bias);
+            v.y = fmaf(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7441)), norm, bias);
+            v.z = fmaf(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442)), norm, bias);
+            // FSR.cl:229-241 (the #ifndef is inverted relative to its comments; reproduced as written)
+            v.w = YUV ? fmaf(v.z, 0.5f, fmaf(v.x, 0.5f, v.y)) : v.x;
+            tile[o] = v;
+            luma[o] = v.w;
+        };
+        constexpr int NW = FT_THREADS / 32;
+        constexpr int MAIN_IT = (FH + NW - 1) / NW;                    // rows per warp, columns 0 .. 31
+        constexpr int REM_ROWS = FT_THREADS / 8, REM_IT = (FH + REM_ROWS - 1) / REM_ROWS;  // columns 32 .. FW-1
+        static_assert(FW - 32 <= 8, "remainder pass covers 8 columns");
+        {
+            // columns 0 .. 31: lane = column, warp ty takes rows ty, ty + 4, ...; word offset and shift are per-lane
+            // constants, only the row pointer advances
+            const unsigned boff = mis + 3u * (unsigned)tx;
+            const uint8_t* rp = a00 + (boff & ~3u) + ty * pitch32;
+            const int o = ty * FW + tx;
+#pragma unroll
+            for (int k = 0; k < MAIN_IT; k++, rp += NW * pitch32)
+                if (tx < bw && ty + NW * k < bh) stage(rp, 8u * boff, o + k * NW * FW);
+        }
+        if (bw > 32)
+        {
+            // columns 32 .. bw-1: 8 lanes per row, 16 rows per pass
+            const int c = 32 + (tx & 7), r0 = (int)(threadIdx.x >> 3);
+            const unsigned boff = mis + 3u * (unsigned)c;
+            const uint8_t* rp = a00 + (boff & ~3u) + r0 * pitch32;
+#pragma unroll
+            for (int k = 0; k < REM_IT; k++, rp += REM_ROWS * pitch32)
+                if (c < bw && r0 + REM_ROWS * k < bh) stage(rp, 8u * boff, (r0 + REM_ROWS * k) * FW + c);
+        }
+        __syncthreads();
+        // ---- direction terms of the texels that can be a corner f/g/j/k: columns 1 .. bw-2, rows 1 .. bh-2
+        auto term = [&](int o) {
+            const float* l = &luma[o];
+            terms[o] = direction_terms(l[-FW], l[-1], l[0], l[1], l[FW]);
+        };
+        {
+            const int o = (ty + 1) * FW + tx + 1;
+#pragma unroll
+            for (int k = 0; k < MAIN_IT; k++)
+                if (tx + 1 < bw - 1 && ty + 1 + NW * k < bh - 1) term(o + k * NW * FW);
+        }
+        if (bw - 2 > 32)
+        {
+            const int c = 33 + (tx & 7), r0 = 1 + (int)(threadIdx.x >> 3);
+#pragma unroll
+            for (int k = 0; k < REM_IT; k++)
+                if (c < bw - 1 && r0 + REM_ROWS * k < bh - 1) term((r0 + REM_ROWS * k) * FW + c);
+        }
+    }
+    __syncthreads();
+
+    // ---- the four pixels as two float32x2 pairs: (row 0, row 1) and (row 2, row 3) of this thread
+    unsigned out[4] = {bg, bg, bg, bg};
+    if (staged)
+    {
+        const int base = y0 * FW + x0;  // lin - base = (sy - y0) * FW + (sx - x0)
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++)
+        {
+            const int a = 2 * pr, b = 2 * pr + 1;
+            const bool ea = (easu_mask >> a) & 1u, eb = (easu_mask >> b) & 1u;
+            if (ea || eb)
+            {
+                // a lane whose pixel is not an EASU pixel computes on its partner's taps and discards the result
+                const int iA = (ea ? lin[a] : lin[b]) - base, iB = (eb ? lin[b] : lin[a]) - base;
+                unsigned oA, oB;
+                easu_pair(&tile[iA], &tile[iB], &terms[iA], &terms[iB], pk(ppx[a], ppx[b]), pk(ppy[a], ppy[b]), oA, oB);
+                if (ea) out[a] = oA;
+                if (eb) out[b] = oB;
+            }
+        }
+    }
+    // rare pixels, behind one warp-wide test: EASU pixels of a tile whose footprint does not fit the staging window
+    // (extreme warps) -> direct global reads; border band (FSR.cl:387-399) -> nearest neighbour.  The position is
+    // recomputed (same arithmetic, same result).
+    if (__any_sync(0xffffffffu, nearest_mask != 0 || (!staged && easu_mask != 0)))
+    {
+#pragma unroll 1
+        for (int k = 0; k < 4; k++)
+        {
+            const bool direct = !staged && ((easu_mask >> k) & 1u), nearest = (nearest_mask >> k) & 1u;
+            if (!direct && !nearest) continue;
+            float fx, fy;
+            source_position<MODE>(x, ybase + 4 * k, W, H, T, M, fx, fy);
+            const int sx = __float2int_rz(fx), sy = __float2int_rz(fy);
+            const uint8_t* p = src + (size_t)sy * src_pitch + 3 * sx;
+            unsigned v;
+            if (direct)
+                v = easu_global<YUV>(p, src_pitch, fx - floorf(fx), fy - floorf(fy));
+            else
+                v = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
+            if (k == 0) out[0] = v;
+            if (k == 1) out[1] = v;
+            if (k == 2) out[2] = v;
+            if (k == 3) out[3] = v;
+        }
+    }
+    uint8_t* q = dst + (size_t)ybase * dst_pitch + 3 * x;
+    const size_t q_step = 4 * dst_pitch;
+    if (inside_mask == 0xFu)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++, q += q_step)
+        {
+            q[0] = (uint8_t)out[k]; q[1] = (uint8_t)(out[k] >> 8); q[2] = (uint8_t)(out[k] >> 16);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++, q += q_step)
+            if ((inside_mask >> k) & 1u)
+            {
+                q[0] = (uint8_t)out[k]; q[1] = (uint8_t)(out[k] >> 8); q[2] = (uint8_t)(out[k] >> 16);
+            }
+    }
+}
+
+std::atomic<int> g_exact{-1};
+
+bool use_exact(const RemapParams& p)
+{
+    int e = g_exact.load(std::memory_order_relaxed);
+    if (e < 0)
+    {
+        const char* v = getenv("LVKB200_REMAP_EXACT");
+        e = (v && atoi(v) != 0) ? 1 : 0;
+        g_exact.store(e, std::memory_order_relaxed);
+    }
+    // the staging loads of the default build are 32-bit: sources that are not 4-byte aligned take the exact build
+    return e != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3u) != 0 || (p.src_pitch & 3u) != 0;
+}
+
+int fast_occupancy()
+{
+    static const int occ = [] {
+        const char* e = getenv("LVKB200_REMAP_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
+        const int v = e ? atoi(e) : FT_CTAS;
+        return (v == 5 || v == 6 || v == 7) ? v : FT_CTAS;
+    }();
+    return occ;
+}
+
+template <int MODE, int CTAS>
+void launch_fast_occ(cudaStream_t cs, const RemapParams& p, const Transform& T, const MeshArgs& M)
+{
+    const int dw = MODE == 2 ? p.dst_width : p.width, dh = MODE == 2 ? p.dst_height : p.height;
+    const dim3 grid(div_up(dw, FT_W), div_up(dh, FT_H));
+    const unsigned bg = (unsigned)p.bg[0] | ((unsigned)p.bg[1] << 8) | ((unsigned)p.bg[2] << 16);
+    if (p.yuv)
+        k_easu_remap_fast<MODE, true, CTAS><<<grid, FT_THREADS, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
+                                                                         p.height, dw, dh, T, M, bg);
+    else
+        k_easu_remap_fast<MODE, false, CTAS><<<grid, FT_THREADS, 0, cs>>>(p.src, p.src_pitch, p.dst, p.dst_pitch, p.width,
+                                                                          p.height, dw, dh, T, M, bg);
+    count_launches(1);
+}
+
+template <int MODE>
+void launch_fast(cudaStream_t cs, const RemapParams& p, const Transform& T, const MeshArgs& M)
+{
+    switch (fast_occupancy())
+    {
+    case 5: launch_fast_occ<MODE, 5>(cs, p, T, M); break;
+    case 6: launch_fast_occ<MODE, 6>(cs, p, T, M); break;
+    default: launch_fast_occ<MODE, 7>(cs, p, T, M);
+    }
+}
+
+}  // namespace
+
+void set_remap_exact(int exact) { g_exact.store(exact ? 1 : 0, std::memory_order_relaxed); }
+int remap_exact()
+{
+    RemapParams aligned{};
+    return use_exact(aligned) ? 1 : 0;
+}
+
+cudaError_t launch_remap_homography(cudaStream_t cs, const RemapParams& p, const float t[9])
+{
+    if (use_exact(p)) return launch_remap_homography_exact(cs, p, t);
+    const Transform T{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]};
+    launch_fast<0>(cs, p, T, MeshArgs{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upscale(cudaStream_t cs, const RemapParams& p)
+{
+    if (use_exact(p)) return launch_upscale_exact(cs, p);
+    // Image.cpp:191-194: rscale = (float)src / (float)dst per axis
+    Transform T{};
+    T.r1x = static_cast<float>(p.width) / static_cast<float>(p.dst_width);
+    T.r2x = static_cast<float>(p.height) / static_cast<float>(p.dst_height);
+    launch_fast<2>(cs, p, T, MeshArgs{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_remap_mesh(cudaStream_t cs, const RemapParams& p, const float* mesh, int mesh_cols, int mesh_rows)
+{
+    if (use_exact(p)) return launch_remap_mesh_exact(cs, p, mesh, mesh_cols, mesh_rows);
+    // cv::resize: scale = 1 / (dsize / ssize), in double
+    const double sx = 1.0 / ((double)p.width / (double)mesh_cols), sy = 1.0 / ((double)p.height / (double)mesh_rows);
+    const MeshArgs M{reinterpret_cast<const float2*>(mesh), mesh_cols, mesh_rows, sx, sy};
+    launch_fast<1>(cs, p, Transform{}, M);
+    return cudaGetLastError();
+}
+
+}  // namespace lvkb200

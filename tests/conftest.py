@@ -27,3 +27,13 @@ def gpu_stream():
     s = L.Stream(L.StabilizationFilterSettings.obs_homography_preset(), device=0)
     yield s
     s.close()
+
+
+@pytest.fixture
+def exact_build():
+    """Runs a test with the EXACT arithmetic build of the EASU kernels (bit-identical to oracle/easu_ref.c); the
+    default is the contract build (include/lvkb200.h: lvkb200_set_remap_exact)."""
+    import livevisionkit_b200 as L
+    L.set_remap_exact(True)
+    yield
+    L.set_remap_exact(False)

@@ -5,7 +5,9 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# bit-exact comparisons with the oracle restatement: these modules run the EXACT arithmetic build of the EASU kernels
+# (tests that exercise the default contract build say so and switch it back on)
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_build")]
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

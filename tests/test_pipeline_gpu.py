@@ -11,7 +11,9 @@ What is asserted, per frame:
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# bit-exact comparisons with the oracle restatement: these modules run the EXACT arithmetic build of the EASU kernels
+# (tests that exercise the default contract build say so and switch it back on)
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_build")]
 
 cv2 = pytest.importorskip("cv2")
 

@@ -5,7 +5,9 @@ bit-exact bytes."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# bit-exact comparisons with the oracle restatement: these modules run the EXACT arithmetic build of the EASU kernels
+# (tests that exercise the default contract build say so and switch it back on)
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_build")]
 
 
 def _textured(h, w, seed=0):
@@ -124,3 +126,38 @@ def test_sharpen_every_ring_level(gpu_stream, oracle):
     for sharpness in (1.0, 0.37):
         got, ref = gpu_stream.sharpen(img, sharpness), oracle.sharpen(img, sharpness)
         assert (got == ref).all(), f"{int((got != ref).sum())} bytes differ"
+
+
+@pytest.mark.parametrize("src_wh,dst_wh", [((480, 270), (960, 540)), ((1280, 720), (1920, 1080)), ((333, 217), (500, 400)),
+                                           ((1920, 1080), (3840, 2160))])
+def test_upscale_contract_build_vs_reference(gpu_stream, oracle, src_wh, dst_wh):
+    """The DEFAULT (contract) build of lvk::upscale against the reference's own easu_scale compiled for the CPU
+    (oracle/_ref) and against the restatement: max 1 LSB vs the contract reference, texel flips excepted vs strict."""
+    import livevisionkit_b200 as L
+    from oracle import fsr_ref as R
+    src = _textured(src_wh[1], src_wh[0], 1) if src_wh[0] < 1000 else _clip_frame("1080p" if src_wh[0] == 1920 else "720p")
+    L.set_remap_exact(False)
+    try:
+        got = gpu_stream.upscale(src, dst_wh, False)
+    finally:
+        L.set_remap_exact(True)  # the module-wide fixture restores the default afterwards
+    n = got.size
+    ho = R.lsb_histogram(got, oracle.upscale(src, dst_wh, False))
+    hc = R.lsb_histogram(got, R.upscale(src, dst_wh, False, "contract"))
+    hs = R.lsb_histogram(got, R.upscale(src, dst_wh, False, "strict"))
+    print(f"upscale {src_wh}->{dst_wh} contract build: vs restatement {ho}, vs reference contract {hc}, strict {hs}")
+    assert ho[2] == 0 and ho[3] == 0 and ho[0] >= 0.999 * n
+    assert hc[2] == 0 and hc[3] == 0 and hc[0] >= 0.999 * n
+    assert hs[2] + hs[3] < 1e-4 * n and hs[0] >= 0.999 * n
+
+
+@pytest.mark.parametrize("sharpness", [0.0, 0.8, 1.0])
+def test_sharpen_vs_reference_rcas(gpu_stream, sharpness):
+    """k_rcas against the reference's own rcas kernel compiled for the CPU (oracle/_ref): max 1 LSB, >= 99.99 % equal."""
+    from oracle import fsr_ref as R
+    src = _clip_frame("720p")
+    got = gpu_stream.sharpen(src, sharpness)
+    for flavour in R.FLAVOURS:
+        h = R.lsb_histogram(got, R.sharpen(src, sharpness, flavour))
+        print(f"rcas s={sharpness} vs reference/{flavour}: {h}")
+        assert h[2] == 0 and h[3] == 0 and h[0] >= 0.9999 * got.size

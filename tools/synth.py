@@ -78,7 +78,19 @@ class Clip:
         self.width, self.height = RESOLUTIONS[resolution] if isinstance(resolution, str) else resolution
         self.kind, self.n, self.fps, self.seed = kind, frames, fps, seed
         self.canvas = make_canvas(self.width, self.height, canvas_seed)
-        self.tx, self.ty, self.rot, self.scale = camera_path(kind, frames, self.width, fps, seed)
+        self.occluder = None
+        if kind == "occluder":
+            # SURVEY 8(d) "occluder variant, seed 7": the hand-shake clip with an independently moving textured block
+            # covering 15 % of the frame (0.45 W x 1/3 H) - the features on it are RANSAC outliers
+            self.seed = seed = 7
+            bw, bh = int(round(0.45 * self.width)), int(round(self.height / 3.0))
+            tex = make_canvas(bw, bh, 7)
+            y0, x0 = (tex.shape[0] - bh) // 2, (tex.shape[1] - bw) // 2
+            self.occluder = np.ascontiguousarray(tex[y0:y0 + bh, x0:x0 + bw, ::-1])  # other channel gains than the scene
+            t = np.arange(frames, dtype=np.float64) / fps
+            self.occ_x = 0.5 * (self.width - bw) + 0.25 * (self.width - bw) * np.sin(2 * math.pi * 0.35 * t)
+            self.occ_y = 0.5 * (self.height - bh) + 0.30 * (self.height - bh) * np.sin(2 * math.pi * 0.23 * t + 1.0)
+        self.tx, self.ty, self.rot, self.scale = camera_path("shake" if kind == "occluder" else kind, frames, self.width, fps, seed)
         if kind == "pan":  # keep the pan inside the canvas margin by wrapping the ramp into a triangle wave
             m = 0.08 * max(self.width, self.height) * 0.9
             self.tx = np.abs(((self.tx + m) % (4 * m)) - 2 * m) - m
@@ -101,8 +113,20 @@ class Clip:
                          [sn, c, cy - sn * cx - c * cy + oy]], dtype=np.float64)
 
     def __getitem__(self, i: int) -> np.ndarray:
-        return cv2.warpAffine(self.canvas, self.matrix(i), (self.width, self.height),
-                              flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP, borderMode=cv2.BORDER_REFLECT)
+        frame = cv2.warpAffine(self.canvas, self.matrix(i), (self.width, self.height),
+                               flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP, borderMode=cv2.BORDER_REFLECT)
+        if self.occluder is not None:
+            m = np.array([[1, 0, self.occ_x[i]], [0, 1, self.occ_y[i]]], dtype=np.float64)
+            bh, bw = self.occluder.shape[:2]
+            block = cv2.warpAffine(self.occluder, m, (self.width, self.height), flags=cv2.INTER_LINEAR)
+            mask = cv2.warpAffine(np.full((bh, bw), 255, np.uint8), m, (self.width, self.height), flags=cv2.INTER_NEAREST)
+            frame[mask > 0] = block[mask > 0]
+        return frame
+
+    def occluder_rect(self, i: int):
+        """(x, y, w, h) of the moving block in frame i (occluder clips only)."""
+        bh, bw = self.occluder.shape[:2]
+        return float(self.occ_x[i]), float(self.occ_y[i]), bw, bh
 
     def frames(self, start=0, stop=None):
         for i in range(start, self.n if stop is None else stop):
