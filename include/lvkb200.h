@@ -132,6 +132,8 @@ void lvkb200_settings_obs_field(lvkb200_settings* s);
 
 /* StabilizationFilter::StabilizationFilter(settings) — Filters/StabilizationFilter.cpp:34-38. */
 lvkb200_status lvkb200_stream_create(int device, const lvkb200_settings* settings, lvkb200_stream** out);
+/* Destroying a stream never writes into caller memory: a device output whose remap is still held back (see
+ * lvkb200_stream_submit) is DISCARDED - call lvkb200_stream_sync first if that output is still wanted. */
 void lvkb200_stream_destroy(lvkb200_stream* s);
 
 /* StabilizationFilter::configure — StabilizationFilter.cpp:42-65. */
@@ -147,8 +149,11 @@ lvkb200_status lvkb200_stream_stable_region(const lvkb200_stream* s, int frame_w
 
 /* VideoFilter::apply(VideoFrame&& input, VideoFrame& output, profile) -> StabilizationFilter::filter
  * (Filters/VideoFilter.cpp:46-58, Filters/StabilizationFilter.cpp:69-135).
- * The input frame is copied into the stream's device ring before the call returns (the caller keeps its
- * buffer; the reference moves it into m_FrameQueue).  `out` may alias `frame` (OBS calls
+ * The input frame is copied into the stream's device ring (the caller keeps its buffer; the reference moves it into
+ * m_FrameQueue): a HOST frame has been consumed when the call returns; a DEVICE frame is copied by stream-ordered
+ * work of the library's own CUDA streams, so the caller must not overwrite it before lvkb200_stream_sync (or an
+ * event recorded with lvkb200_stream_event_record) has completed - reading it concurrently is fine.
+ * `out` may alias `frame` (OBS calls
  * apply(std::move(frame), frame), VSFilter.cpp:358).  When res->has_output == 0 `out` is untouched.
  * With out_space == HOST the call returns after the output has landed in `out`; with DEVICE the output is
  * produced by stream-ordered work that may still be pending (the library can hold the remap back until the next

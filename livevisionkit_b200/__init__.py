@@ -743,7 +743,11 @@ class StabilizationFilter:
         return self.stream(frames, callback, outputs)  # Stream.__call__ (the attribute doubles as the method)
 
     def apply(self, frame: VideoFrame, output=None) -> VideoFrame:
-        """`output`: optional preallocated buffer (numpy or CUDA tensor) receiving the result."""
+        """lvk::VideoFilter::apply.  `output`: optional preallocated buffer (numpy or CUDA tensor) receiving the result.
+        The returned frame is COMPLETE, as in the reference (a UMat access synchronises implicitly): for a CUDA output
+        the library may hold the remap back until the next submit (lvkb200.h), so this mirror synchronises the stream
+        before handing the buffer out.  Callers that want the overlap use `stream.submit` / `stream_frames` and order
+        against `stream.sync()` / `event_record` themselves."""
         data = frame.data
         if output is None:
             output = np.empty_like(data) if isinstance(data, np.ndarray) else data.new_empty(data.shape)
@@ -751,4 +755,6 @@ class StabilizationFilter:
         self.last_result = res
         if not res.has_output:
             return VideoFrame(None, 0, UNKNOWN)
+        if not isinstance(output, np.ndarray):
+            self.stream.sync()
         return VideoFrame(output, int(res.out_timestamp), int(res.out_format))

@@ -175,6 +175,10 @@ void lvkb200_stream_destroy(lvkb200_stream* s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
+    // A remap that is still held back would be launched into the caller's output buffer NOW - which the caller may
+    // already have freed (e.g. a garbage-collected tensor): it is discarded, never launched.  A caller that wants the
+    // last device output completes it with lvkb200_stream_sync before destroying the stream.
+    s->pending.active = false;
     s->sync_all();
     s->release();
     if (s->cs) cudaStreamDestroy(s->cs);

@@ -121,6 +121,9 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
 lvkb200_status lvkb200_stream::restart()
 {
     // StabilizationFilter::restart — StabilizationFilter.cpp:139-144
+    // an output that was already handed out is completed first (its remap may still be held back): after restart()
+    // nothing of this stream writes into a caller's buffer any more
+    LVKB_TRY(flush_remap());
     scene_quality = 1.0f;
     ring_start = 0;
     ring_size = 0;
@@ -625,9 +628,12 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     // FAST reads the detection image only, the pyramid is needed by LK only: FAST goes first and the pyramid is
     // queued behind it, so it is built while the host waits for and digests the FAST keypoints.
     const bool can_track = frame_initialized && pyr[prev_pyr()].valid;
-    std::vector<FastRegion> regions;
-    std::vector<int> region_index;
-    std::vector<std::vector<FastPoint>> fast_points;
+    // per-frame scratch lives in the stream (capacity is kept): a steady-state frame allocates nothing on the host
+    std::vector<FastRegion>& regions = scratch.regions;
+    std::vector<int>& region_index = scratch.region_index;
+    std::vector<std::vector<FastPoint>>& fast_points = scratch.fast_points;
+    regions.clear();
+    region_index.clear();
     if (can_track)
     {
         grid.plan_detection(regions, region_index);  // FeatureDetector::detect (FrameTracker.cpp:127)
@@ -672,8 +678,11 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     }
 
     // ---- sparse optical flow (FrameTracker.cpp:135-146)
-    std::vector<float> tracked(features.size() * 2), matched;
-    std::vector<uint8_t> status;
+    std::vector<float>&tracked = scratch.tracked, &matched = scratch.matched;
+    std::vector<uint8_t>& status = scratch.status;
+    tracked.resize(features.size() * 2);
+    matched.clear();
+    status.clear();
     for (size_t i = 0; i < features.size(); i++)
     {
         tracked[2 * i] = features[i].x;
@@ -691,7 +700,8 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     LVKB_TRY(pre_ingest());   // the announced next frame's detection image + pyramid, behind this frame's chain
     host_tick(HP_ENQ_TRACK);
     RansacResult model{};
-    std::vector<uint8_t> inliers;
+    std::vector<uint8_t>& inliers = scratch.inliers;
+    inliers.clear();
     LVKB_TRY(fetch_tracking(n_tracked, global, matched, status, &model, inliers));
     host_tick(HP_WAIT_TRACK);
     if (debug_capture)
@@ -1060,13 +1070,21 @@ lvkb200_status lvkb200_stream::submit(const void* frame, size_t pitch, int width
         LVKB_TRY(deblock.prepare(width, height, deblock_settings, cs));
         LVKB_TRY(deblock.launch(cs, q.buf.as<uint8_t>(), q.pitch, format));
     }
-    // The caller keeps ownership of its buffer: host memory must have been consumed before we return.
+    // The caller keeps ownership of its buffer: host memory must have been consumed before we return.  A prefetched
+    // host frame was uploaded on the copy-in stream: its upload event is waited for instead (almost always complete
+    // already; without it the paths that never wait on `cs` could return while the copy is still reading the buffer).
     struct InputGuard
     {
         lvkb200_stream* s;
         bool host;
-        ~InputGuard() { if (host && s->input_copied) cudaEventSynchronize(s->input_copied); }
-    } input_guard{this, frame_space == LVKB200_MEM_HOST && !prefetched};
+        cudaEvent_t upload;
+        ~InputGuard()
+        {
+            if (host && s->input_copied) cudaEventSynchronize(s->input_copied);
+            if (upload) cudaEventSynchronize(upload);
+        }
+    } input_guard{this, frame_space == LVKB200_MEM_HOST && !prefetched,
+                  (frame_space == LVKB200_MEM_HOST && prefetched) ? prefetch_done[pk] : nullptr};
     if (frame_space == LVKB200_MEM_HOST && !prefetched)
     {
         if (!input_copied) LVKB_CUDA(cudaEventCreateWithFlags(&input_copied, cudaEventDisableTiming));

@@ -30,6 +30,16 @@ struct lvkb200_stream
     lvkb200::PinnedBuffer mesh_pinned;
     cudaEvent_t user_events[LVKB200_EVENT_SLOTS] = {};
 
+    // ---- per-frame host scratch of track(): cleared, never freed, so a steady-state frame allocates nothing
+    struct TrackScratch
+    {
+        std::vector<lvkb200::FastRegion> regions;
+        std::vector<int> region_index;
+        std::vector<std::vector<lvkb200::FastPoint>> fast_points;
+        std::vector<float> tracked, matched;
+        std::vector<uint8_t> status, inliers;
+    } scratch;
+
     // ---- DeblockingFilter chained in front of the stabilizer (lvkb200_stream_set_deblocking) / stand-alone
     lvkb200::DeblockPlan deblock, deblock_stage;
     bool deblock_enabled = false;

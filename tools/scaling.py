@@ -6,9 +6,11 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-# counter struct layout (float64)
+# counter struct layout (float64).  DEV_MS / E2E_MS are the rank's MEDIAN window time; the optional tail carries the
+# rank's fastest and slowest window so that the record can tell rank skew from host noise.
 FRAMES, DEV_MS, E2E_MS, LAUNCHES, PARITY_FAIL, WALL_MS, WALL_E2E_MS, OUTPUTS = range(8)
 N_COUNTERS = 8
+DEV_MIN, DEV_MAX, E2E_MIN, E2E_MAX = range(8, 12)
 
 
 def stream_seed(rank: int) -> int:
@@ -32,7 +34,23 @@ def aggregate(allc: torch.Tensor) -> dict:
     frames = float(a[:, FRAMES].sum())
     t_dev = float(a[:, DEV_MS].max())
     t_e2e = float(a[:, E2E_MS].max())
+    per_rank = None
+    if a.shape[1] >= 12:
+        frames_r = a[:, FRAMES]
+        per_rank = {
+            "dev_ms_median": [float(v) for v in a[:, DEV_MS]], "dev_ms_min": [float(v) for v in a[:, DEV_MIN]],
+            "dev_ms_max": [float(v) for v in a[:, DEV_MAX]],
+            "e2e_ms_median": [float(v) for v in a[:, E2E_MS]], "e2e_ms_min": [float(v) for v in a[:, E2E_MIN]],
+            "e2e_ms_max": [float(v) for v in a[:, E2E_MAX]],
+            "e2e_fps": [float(f / (t * 1e-3)) if t > 0 else 0.0 for f, t in zip(frames_r, a[:, E2E_MS])],
+            "value_fps": [float(f / (t * 1e-3)) if t > 0 else 0.0 for f, t in zip(frames_r, a[:, DEV_MS])],
+            "slowest_rank_e2e": int(a[:, E2E_MS].argmax()), "slowest_rank_value": int(a[:, DEV_MS].argmax()),
+            # sum of the ranks' own rates: what the job delivers when no rank waits for another (streams are independent)
+            "sum_of_rank_e2e_fps": float(sum(f / (t * 1e-3) for f, t in zip(frames_r, a[:, E2E_MS]) if t > 0)),
+            "sum_of_rank_value_fps": float(sum(f / (t * 1e-3) for f, t in zip(frames_r, a[:, DEV_MS]) if t > 0)),
+        }
     return {
+        "per_rank": per_rank,
         "frames": frames,
         "value_fps": frames / (t_dev * 1e-3) if t_dev > 0 else 0.0,
         "e2e_fps": frames / (t_e2e * 1e-3) if t_e2e > 0 else 0.0,
