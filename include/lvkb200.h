@@ -164,6 +164,9 @@ lvkb200_status lvkb200_stream_submit(lvkb200_stream* s, const void* frame, size_
                                      lvkb200_format format, uint64_t timestamp, lvkb200_memspace frame_space,
                                      void* out, size_t out_pitch, lvkb200_memspace out_space, lvkb200_result* res);
 lvkb200_status lvkb200_stream_sync(lvkb200_stream* s);
+/* Stopwatch::sync_gpu (Timing/Stopwatch.cpp:127-131: cv::ocl::finish()) for callers that hold no stream handle: drains
+ * every CUDA stream of the calling thread's current device. */
+lvkb200_status lvkb200_device_synchronize(void);
 
 /* Pipelined operation — VideoFilter::stream(cap, callback, profile) (Filters/VideoFilter.cpp:62-209) overlaps input,
  * filtering and output with three host threads and bounded queues.  The GPU analogue uses two extra CUDA streams:

@@ -1,29 +1,40 @@
 // lvk-compat — C++ mirror of the reference's filter interface for the stabilization path, forwarding to the C-ABI
 // (include/lvkb200.h).  Same names, argument meaning and error behaviour as
-//   LiveVisionKit/Filters/VideoFilter.hpp:32-61          lvk::VideoFilter (apply / alias / timings / filter)
+//   LiveVisionKit/Filters/VideoFilter.hpp:32-61          lvk::VideoFilter (apply / stream / alias / timings / filter)
 //   LiveVisionKit/Filters/StabilizationFilter.hpp:28-77  lvk::StabilizationFilterSettings, lvk::StabilizationFilter
 //   LiveVisionKit/Filters/DeblockingFilter.hpp:26-59     lvk::DeblockingFilterSettings, lvk::DeblockingFilter
 //   LiveVisionKit/Filters/ScalingFilter.hpp:27-52        lvk::ScalingFilterSettings, lvk::ScalingFilter
 //   LiveVisionKit/Filters/CompositeFilter.hpp:27-75      lvk::CompositeFilterSettings, lvk::CompositeFilter
 //   LiveVisionKit/Vision/FrameTracker.hpp:31-44, FeatureDetector.hpp:28-37, PathSmoother.hpp:29-39  settings bases
 //   LiveVisionKit/Utility/Configurable.hpp:27-44         lvk::Configurable<T>
+//   LiveVisionKit/Utility/Unique.hpp:25-45               lvk::Unique<Scope>
+//   LiveVisionKit/Timing/Time.hpp:25-108, Stopwatch.hpp:25-75, Data/StreamBuffer.hpp  lvk::Time, lvk::Stopwatch, history
 //   LiveVisionKit/Data/VideoFrame.hpp:25-79              lvk::VideoFrame (format, timestamp, width/height)
 //   LiveVisionKit/Directives.hpp:37-95                   lvk::context::assert_handler, LVK_ASSERT
-// The reference's VideoFrame derives from cv::UMat; OpenCV is not available in this image, so VideoFrame here owns /
-// views a plain packed 8-bit buffer (host or CUDA device memory) and cv::Size / cv::Scalar / cv::Rect are replaced by
-// layout-compatible minimal structs in lvk::cvlite (define LVK_COMPAT_USE_OPENCV to use the real ones).
+// Two builds of lvk::VideoFrame:
+//   * default (no OpenCV in the build): VideoFrame owns / views a plain packed 8-bit buffer in host or CUDA device
+//     memory, reference-counted like a cv::UMat (copies are shallow, clone() is deep); cv::Size / Size2f / Scalar /
+//     Rect / Point are replaced by minimal structs in lvk::cvlite;
+//   * -DLVK_COMPAT_USE_OPENCV: `struct VideoFrame : public cv::UMat` exactly as Data/VideoFrame.hpp:28 declares it, the
+//     real cv:: geometry types, and VideoFilter::stream(cv::VideoCapture&, ...) — what the OBS plugin and the video
+//     editor compile against.  Pixels reach the library through cv::UMat::getMat (host mapping).
+//     tests/test_compat_cpu.py compiles the reference's own call sites (VSFilter.cpp, VideoProcessor.cpp) against this
+//     build with a mock opencv2/ (tests/cpp/mock_opencv).
 // Header-only; link with liblvkb200.so.
 #pragma once
 
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <initializer_list>
 #include <memory>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -31,16 +42,19 @@
 
 #ifdef LVK_COMPAT_USE_OPENCV
 #include <opencv2/core.hpp>
+#include <opencv2/videoio.hpp>
 #endif
 
 namespace lvk
 {
 
 #ifdef LVK_COMPAT_USE_OPENCV
-namespace cvlite { using Size = cv::Size; using Size2f = cv::Size2f; using Scalar = cv::Scalar; using Rect = cv::Rect; }
+namespace cvlite { using Size = cv::Size; using Size2f = cv::Size2f; using Scalar = cv::Scalar; using Rect = cv::Rect; using Point = cv::Point; }
 #else
 namespace cvlite
 {
+    struct Point { int x = 0, y = 0; Point() = default; Point(int px, int py) : x(px), y(py) {}
+                   Point operator+(const Point& o) const { return {x + o.x, y + o.y}; } };
     struct Size { int width = 0, height = 0; Size() = default; Size(int w, int h) : width(w), height(h) {}
                   bool operator==(const Size& o) const { return width == o.width && height == o.height; }
                   bool operator!=(const Size& o) const { return !(*this == o); } };
@@ -48,7 +62,9 @@ namespace cvlite
     struct Scalar { double val[4] = {0, 0, 0, 0}; Scalar() = default;
                     Scalar(double a, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
                     double operator[](int i) const { return val[i]; } double& operator[](int i) { return val[i]; } };
-    struct Rect { int x = 0, y = 0, width = 0, height = 0; };
+    struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() = default;
+                  Rect(int px, int py, int w, int h) : x(px), y(py), width(w), height(h) {}
+                  Point tl() const { return {x, y}; } Point br() const { return {x + width, y + height}; } };
 }
 #endif
 
@@ -70,7 +86,226 @@ namespace context
 #define LVK_ASSERT(assertion)
 #endif
 
+// ---- Utility/Unique.hpp:25-45, Unique.tpp:27-60 -----------------------------------------------------------------------
+struct GlobalScope;
+template <typename Scope = GlobalScope>
+class Unique
+{
+public:
+    Unique() : m_UID(next()) {}
+    Unique(const Unique&) : m_UID(next()) {}           // a copy is a new object
+    Unique(Unique&& other) noexcept : m_UID(other.m_UID) {}
+    Unique& operator=(const Unique&) { return *this; }
+    uint64_t uid() const { return m_UID; }
+private:
+    static uint64_t next() { static uint64_t s_NextUID = 1; return s_NextUID++; }
+    uint64_t m_UID;
+};
+
+// ---- Timing/Time.hpp:25-108 (Time.cpp) -----------------------------------------------------------------------------------
+class Time
+{
+public:
+    using TimePoint = std::chrono::high_resolution_clock::time_point;
+    static Time Now() { return Time(std::chrono::high_resolution_clock::now()); }
+    static std::string Timestamp(const char* format = "%F %T")
+    {
+        const std::time_t now = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now());
+        char buffer[128] = {0};
+        std::strftime(buffer, sizeof(buffer), format, std::localtime(&now));
+        return buffer;
+    }
+    static Time Hours(const double amount) { return Seconds(amount * 3600.0); }
+    static Time Minutes(const double amount) { return Seconds(amount * 60.0); }
+    static Time Seconds(const double amount) { return Time(static_cast<uint64_t>(amount * 1e9)); }
+    static Time Milliseconds(const double amount) { return Time(static_cast<uint64_t>(amount * 1e6)); }
+    static Time Microseconds(const double amount) { return Time(static_cast<uint64_t>(amount * 1e3)); }
+    static Time Nanoseconds(const uint64_t amount) { return Time(amount); }
+    static Time Timestep(const double frequency) { return Seconds(1.0 / frequency); }
+
+    Time() : m_Time(0) {}
+    explicit Time(const TimePoint& time) : m_Time(std::chrono::duration_cast<std::chrono::nanoseconds>(time.time_since_epoch())) {}
+    explicit Time(const uint64_t nanoseconds) : m_Time(static_cast<std::chrono::nanoseconds::rep>(nanoseconds)) {}
+    explicit Time(const std::chrono::nanoseconds nanoseconds) : m_Time(nanoseconds) {}
+    Time(const Time& other) = default;
+
+    double hours() const { return seconds() / 3600.0; }
+    double minutes() const { return seconds() / 60.0; }
+    double seconds() const { return nanoseconds() * 1e-9; }
+    double milliseconds() const { return nanoseconds() * 1e-6; }
+    double microseconds() const { return nanoseconds() * 1e-3; }
+    double nanoseconds() const { return static_cast<double>(m_Time.count()); }
+    double frequency() const { return 1.0 / seconds(); }
+    std::string hms() const
+    {
+        const uint64_t total = static_cast<uint64_t>(seconds());
+        char buffer[32];
+        std::snprintf(buffer, sizeof(buffer), "%02llu:%02llu:%02llu", static_cast<unsigned long long>(total / 3600),
+                      static_cast<unsigned long long>((total / 60) % 60), static_cast<unsigned long long>(total % 60));
+        return buffer;
+    }
+    bool is_zero() const { return m_Time.count() == 0; }
+
+    Time& operator=(const Time& other) = default;
+    void operator+=(const Time& other) { m_Time += other.m_Time; }
+    void operator-=(const Time& other) { m_Time -= other.m_Time; }
+    Time operator+(const Time& other) const { return Time(m_Time + other.m_Time); }
+    Time operator-(const Time& other) const { return Time(m_Time - other.m_Time); }
+    bool operator==(const Time& other) const { return m_Time == other.m_Time; }
+    bool operator!=(const Time& other) const { return m_Time != other.m_Time; }
+    bool operator>(const Time& other) const { return m_Time > other.m_Time; }
+    bool operator>=(const Time& other) const { return m_Time >= other.m_Time; }
+    bool operator<(const Time& other) const { return m_Time < other.m_Time; }
+    bool operator<=(const Time& other) const { return m_Time <= other.m_Time; }
+    Time operator*(const double multiplier) const { return Time(std::chrono::nanoseconds(static_cast<std::chrono::nanoseconds::rep>(nanoseconds() * multiplier))); }
+    Time operator/(const double divisor) const { return Time(std::chrono::nanoseconds(static_cast<std::chrono::nanoseconds::rep>(nanoseconds() / divisor))); }
+private:
+    std::chrono::nanoseconds m_Time;
+};
+
+// ---- Data/StreamBuffer.hpp (the part Stopwatch::history() exposes: a fixed-capacity ring, oldest -> newest) ----------------
+template <typename T>
+class StreamBuffer
+{
+public:
+    explicit StreamBuffer(const size_t capacity) : m_Capacity(capacity ? capacity : 1) {}
+    void push(const T& element)  // a full buffer overwrites its oldest element (StreamBuffer.tpp:37-84)
+    {
+        if (m_Data.size() == m_Capacity) m_Data.erase(m_Data.begin());
+        m_Data.push_back(element);
+    }
+    void resize(const size_t capacity)
+    {
+        m_Capacity = capacity ? capacity : 1;
+        while (m_Data.size() > m_Capacity) m_Data.erase(m_Data.begin());
+    }
+    void clear() { m_Data.clear(); }
+    T& at(const size_t index) { return m_Data.at(index); }
+    const T& at(const size_t index) const { return m_Data.at(index); }
+    T& operator[](const size_t index) { return m_Data[index]; }
+    const T& operator[](const size_t index) const { return m_Data[index]; }
+    const T& oldest(const int offset = 0) const { return m_Data[static_cast<size_t>(offset)]; }
+    const T& newest(const int offset = 0) const { return m_Data[m_Data.size() - 1 + static_cast<size_t>(offset)]; }
+    bool is_full() const { return m_Data.size() == m_Capacity; }
+    bool is_empty() const { return m_Data.empty(); }
+    size_t size() const { return m_Data.size(); }
+    size_t capacity() const { return m_Capacity; }
+    typename std::vector<T>::const_iterator begin() const { return m_Data.begin(); }
+    typename std::vector<T>::const_iterator end() const { return m_Data.end(); }
+private:
+    std::vector<T> m_Data;
+    size_t m_Capacity;
+};
+
+// ---- Timing/Stopwatch.hpp:25-75 (Stopwatch.cpp:27-166) -----------------------------------------------------------------------
+class Stopwatch
+{
+public:
+    explicit Stopwatch(const size_t history = 1) : m_History(history) {}
+    void start() { m_Running = true; m_StartTime = Time::Now(); }
+    Time stop()
+    {
+        if (is_running() || is_paused())
+        {
+            m_ElapsedTime = pause();
+            m_History.push(m_ElapsedTime);
+            m_Memory = Time(0);
+            return m_ElapsedTime;
+        }
+        return Time(0);
+    }
+    Time pause()
+    {
+        if (!is_running()) return m_Memory;
+        m_Memory += (Time::Now() - m_StartTime);
+        m_ElapsedTime = m_Memory;
+        m_Running = false;
+        return m_Memory;
+    }
+    Time restart() { const Time elapsed = stop(); start(); return elapsed; }
+    bool is_paused() const { return !m_Running && m_Memory.nanoseconds() > 0; }
+    bool is_running() const { return m_Running; }
+    Time wait_until(const Time& target_elapsed_time)
+    {
+        if (!is_running()) start();
+        Time elapsed_time = elapsed();
+        while (elapsed_time < target_elapsed_time)
+        {
+            std::this_thread::yield();
+            elapsed_time = elapsed();
+        }
+        return elapsed_time;
+    }
+    // Stopwatch.cpp:127-131 calls cv::ocl::finish(): here every CUDA stream of the calling thread's device is drained
+    Stopwatch& sync_gpu(const bool trigger = true)
+    {
+        if (trigger) lvkb200_device_synchronize();
+        return *this;
+    }
+    Time elapsed() const { return is_running() ? (m_Memory + (Time::Now() - m_StartTime)) : m_ElapsedTime; }
+    Time average() const
+    {
+        if (m_History.is_empty()) return Time(0);
+        Time total(0);
+        for (const Time& t : m_History) total += t;
+        return total / static_cast<double>(m_History.size());
+    }
+    Time deviation() const  // mean absolute deviation, Stopwatch.cpp:142-160
+    {
+        if (m_History.size() < 2) return Time(0);
+        const Time average_time = average();
+        Time total_deviation(0);
+        for (const Time& current_time : m_History)
+            total_deviation += (average_time > current_time) ? (average_time - current_time) : (current_time - average_time);
+        return total_deviation / static_cast<double>(m_History.size());
+    }
+    void reset_history() { m_History.clear(); }
+    const StreamBuffer<Time>& history() const { return m_History; }
+    void set_history_size(const size_t history) { m_History.resize(history); }
+private:
+    bool m_Running = false;
+    StreamBuffer<Time> m_History;
+    Time m_ElapsedTime{0}, m_StartTime{0}, m_Memory{0};
+};
+
 // ---- Data/VideoFrame.hpp:25-79 -------------------------------------------------------------------------------------
+#ifdef LVK_COMPAT_USE_OPENCV
+// The reference's own declaration: a cv::UMat with a timestamp and a format.  (reformat / reformatTo / viewAsFormat are
+// cv::cvtColor wrappers, VideoFrame.cpp:116-317, used by ConversionFilter and the drawing helpers - outside this path.)
+struct VideoFrame : public cv::UMat
+{
+    enum Format { BGR, BGRA, RGB, RGBA, YUV, GRAY, UNKNOWN };
+
+    uint64_t timestamp = 0;
+    Format format = UNKNOWN;
+    int& width = cols; int& height = rows;
+
+    VideoFrame() : cv::UMat() {}
+    VideoFrame(const VideoFrame& frame) : cv::UMat(frame), timestamp(frame.timestamp), format(frame.format) {}
+    VideoFrame(VideoFrame&& frame) noexcept : cv::UMat(std::move(frame)), timestamp(frame.timestamp), format(frame.format) {}
+    explicit VideoFrame(const uint64_t ts) : cv::UMat(), timestamp(ts) {}
+    explicit VideoFrame(const cv::UMat& frame, const uint64_t ts = 0, const Format fmt = UNKNOWN) : cv::UMat(frame), timestamp(ts), format(fmt) {}
+    explicit VideoFrame(cv::UMat&& frame, const uint64_t ts = 0, const Format fmt = UNKNOWN) noexcept : cv::UMat(std::move(frame)), timestamp(ts), format(fmt) {}
+    virtual ~VideoFrame() = default;
+
+    VideoFrame& operator=(VideoFrame&& frame) noexcept
+    {
+        timestamp = frame.timestamp; format = frame.format;
+        cv::UMat::operator=(std::move(frame));
+        return *this;
+    }
+    VideoFrame& operator=(const VideoFrame& frame) noexcept
+    {
+        timestamp = frame.timestamp; format = frame.format;
+        cv::UMat::operator=(frame);
+        return *this;
+    }
+    VideoFrame clone() const { return VideoFrame(cv::UMat::clone(), timestamp, format); }
+    void copyTo(VideoFrame& dst) const { cv::UMat::copyTo(dst); dst.timestamp = timestamp; dst.format = format; }
+    VideoFrame operator()(const cv::Rect& roi) const { return VideoFrame(cv::UMat::operator()(roi), timestamp, format); }
+    bool has_known_format() const { return format != UNKNOWN; }
+};
+#else
 struct VideoFrame
 {
     enum Format { BGR, BGRA, RGB, RGBA, YUV, GRAY, UNKNOWN };
@@ -88,72 +323,91 @@ struct VideoFrame
     // view onto caller memory (no ownership)
     VideoFrame(uint8_t* pixels, int w, int h, size_t row_step, Format fmt, uint64_t ts = 0, bool device = false)
         : data(pixels), step(row_step), cols(w), rows(h), on_device(device), timestamp(ts), format(fmt) {}
+    // Copies are SHALLOW, like the reference's cv::UMat base (VideoFrame.cpp:37-44, VideoFilter.cpp:55-58): owned pixels
+    // are reference-counted and shared; clone() makes the deep copy.
     VideoFrame(const VideoFrame& o) { *this = o; }
     VideoFrame(VideoFrame&& o) noexcept { *this = std::move(o); }
-    VideoFrame& operator=(const VideoFrame& o)
+    virtual ~VideoFrame() = default;
+    VideoFrame& operator=(const VideoFrame& o) noexcept
     {
         if (this == &o) return *this;
-        storage = o.storage;
-        if (!o.storage.empty()) data = storage.data(); else data = o.data;
+        storage = o.storage; data = o.data;
         step = o.step; cols = o.cols; rows = o.rows; on_device = o.on_device; timestamp = o.timestamp; format = o.format;
         return *this;
     }
     VideoFrame& operator=(VideoFrame&& o) noexcept
     {
         if (this == &o) return *this;
-        const bool owned = !o.storage.empty();
-        storage = std::move(o.storage);
-        data = owned ? storage.data() : o.data;
+        storage = std::move(o.storage); data = o.data;
         step = o.step; cols = o.cols; rows = o.rows; on_device = o.on_device; timestamp = o.timestamp; format = o.format;
         o.release();
         return *this;
     }
 
     bool empty() const { return data == nullptr || cols <= 0 || rows <= 0; }
-    void release() { storage.clear(); data = nullptr; step = 0; cols = rows = 0; on_device = false; }
-    // cv::UMat::create(rows, cols, CV_8UC3): (re)allocates an owned host buffer when the geometry differs
+    void release() { storage.reset(); data = nullptr; step = 0; cols = rows = 0; on_device = false; }
+    // cv::UMat::create(rows, cols, CV_8UC3): (re)allocates an owned host buffer when the geometry differs or the pixels are
+    // shared with another frame
     void create(int h, int w, int channels = 3)
     {
-        if (!storage.empty() && h == rows && w == cols && step == static_cast<size_t>(w) * channels) return;
-        storage.assign(static_cast<size_t>(w) * channels * h, 0);
-        data = storage.data(); step = static_cast<size_t>(w) * channels; cols = w; rows = h; on_device = false;
+        if (storage && storage.use_count() == 1 && h == rows && w == cols && step == static_cast<size_t>(w) * channels) return;
+        storage = std::make_shared<std::vector<uint8_t>>(static_cast<size_t>(w) * channels * h, 0);
+        data = storage->data(); step = static_cast<size_t>(w) * channels; cols = w; rows = h; on_device = false;
+    }
+    VideoFrame clone() const  // deep copy (host frames; a device view is cloned as the same view)
+    {
+        VideoFrame c;
+        if (empty() || on_device) { c = *this; return c; }
+        c.create(rows, cols, static_cast<int>(step / static_cast<size_t>(cols)) >= 3 ? 3 : 1);
+        copyTo(c);
+        return c;
+    }
+    void copyTo(VideoFrame& dst) const
+    {
+        if (empty() || on_device) { dst = *this; return; }
+        const int channels = 3;
+        dst.create(rows, cols, channels);
+        for (int y = 0; y < rows; y++) std::memcpy(dst.data + static_cast<size_t>(y) * dst.step, data + static_cast<size_t>(y) * step, static_cast<size_t>(cols) * channels);
+        dst.timestamp = timestamp; dst.format = format;
+    }
+    VideoFrame operator()(const cvlite::Rect& roi) const  // a view sharing the pixels (cv::UMat::operator())
+    {
+        VideoFrame v = *this;
+        v.data = data + static_cast<size_t>(roi.y) * step + static_cast<size_t>(roi.x) * 3;
+        v.cols = roi.width; v.rows = roi.height;
+        return v;
     }
     bool has_known_format() const { return format != UNKNOWN; }
 
 private:
-    std::vector<uint8_t> storage;
+    std::shared_ptr<std::vector<uint8_t>> storage;
 };
+#endif
 typedef VideoFrame Frame;
 
-// ---- Timing/Stopwatch (subset used through VideoFilter::timings()) ------------------------------------------------------
-class Stopwatch
+namespace detail
 {
-public:
-    explicit Stopwatch(size_t history = 1) : m_History(history ? history : 1) {}
-    Stopwatch& start() { m_Start = std::chrono::steady_clock::now(); m_Running = true; return *this; }
-    Stopwatch& stop()
-    {
-        if (!m_Running) return *this;
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - m_Start).count();
-        if (m_Samples.size() == m_History) m_Samples.erase(m_Samples.begin());
-        m_Samples.push_back(ms);
-        m_Running = false;
-        return *this;
-    }
-    double elapsed_ms() const { return m_Samples.empty() ? 0.0 : m_Samples.back(); }
-    double average_ms() const
-    {
-        if (m_Samples.empty()) return 0.0;
-        double s = 0; for (double v : m_Samples) s += v;
-        return s / static_cast<double>(m_Samples.size());
-    }
-    void set_history(size_t n) { m_History = n ? n : 1; }
-private:
-    std::chrono::steady_clock::time_point m_Start{};
-    std::vector<double> m_Samples;
-    size_t m_History;
-    bool m_Running = false;
+// Pixel access for the C-ABI: pointer, row pitch and memory space of a frame.  With cv::UMat frames the pixels are mapped
+// to the host (cv::UMat::getMat) for the duration of the call.
+#ifdef LVK_COMPAT_USE_OPENCV
+struct Pixels
+{
+    cv::Mat mapped;
+    uint8_t* data = nullptr; size_t step = 0; lvkb200_memspace space = LVKB200_MEM_HOST;
+    Pixels(const VideoFrame& f, bool write) : mapped(f.getMat(write ? cv::ACCESS_RW : cv::ACCESS_READ)), data(mapped.data), step(mapped.step) {}
 };
+inline bool on_device(const VideoFrame&) { return false; }
+inline void allocate(VideoFrame& f, int rows, int cols) { f.create(rows, cols, CV_8UC3); }
+#else
+struct Pixels
+{
+    uint8_t* data; size_t step; lvkb200_memspace space;
+    Pixels(const VideoFrame& f, bool) : data(f.data), step(f.step), space(f.on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST) {}
+};
+inline bool on_device(const VideoFrame& f) { return f.on_device; }
+inline void allocate(VideoFrame& f, int rows, int cols) { f.create(rows, cols); }
+#endif
+}  // namespace detail
 
 // ---- Utility/Configurable.hpp:27-44 -----------------------------------------------------------------------------------
 template <typename T>
@@ -171,7 +425,7 @@ protected:
 };
 
 // ---- Filters/VideoFilter.hpp:32-61 -------------------------------------------------------------------------------------
-class VideoFilter
+class VideoFilter : public Unique<VideoFilter>
 {
 public:
     explicit VideoFilter(const std::string& filter_name = "Identity Filter") : m_Alias(filter_name) {}
@@ -187,7 +441,7 @@ public:
         if (profile) sync_device();
         m_FrameTimer.stop();
     }
-    // VideoFilter.cpp:55-58
+    // VideoFilter.cpp:55-58: a reference-counted (shallow) copy of the input is moved in
     void apply(const VideoFrame& input, VideoFrame& output, const bool profile = false) { apply(Frame(input), output, profile); }
 
     // VideoFilter.cpp:62-209: reads frames until the input is exhausted, filters them and hands every non-empty output
@@ -199,8 +453,21 @@ public:
     {
         stream_frames([&input](Frame& f) { return input.read(f); }, callback, profile);
     }
+#ifdef LVK_COMPAT_USE_OPENCV
+    // the reference's signature (VideoFilter.hpp:47): frames read from the capture are BGR (VideoFilter.cpp:96-100)
+    void stream(cv::VideoCapture& input, const std::function<bool(Frame&)>& callback, const bool profile = false)
+    {
+        uint64_t index = 0;
+        stream_frames([&input, &index](Frame& f) {
+            if (!input.read(f)) return false;
+            f.timestamp = index++;
+            f.format = VideoFrame::BGR;
+            return true;
+        }, callback, profile);
+    }
+#endif
 
-    void set_timing_samples(const size_t samples) { m_FrameTimer.set_history(samples); }
+    void set_timing_samples(const size_t samples) { m_FrameTimer.set_history_size(samples); }
     const Stopwatch& timings() const { return m_FrameTimer; }
 
 protected:
@@ -311,18 +578,32 @@ private:
         LVK_ASSERT(input.has_known_format());
         LVK_ASSERT(!input.empty());
         m_LastWidth = input.cols; m_LastHeight = input.rows;
+        const int w = input.cols, h = input.rows;
+        const uint64_t ts = input.timestamp;
+        const lvkb200_format fmt = static_cast<lvkb200_format>(input.format);
+        const bool device = detail::on_device(input);
         // the reference moves `input` into its queue and overwrites `output`; OBS passes the same object for both
         const bool alias = (&input == &output);
         VideoFrame* dst = &output;
-        if (!alias && (output.empty() || output.cols != input.cols || output.rows != input.rows || output.on_device != input.on_device))
+        if (!alias && (output.empty() || output.cols != w || output.rows != h || detail::on_device(output) != device))
         {
-            if (input.on_device) { dst = &m_Scratch; if (m_Scratch.cols != input.cols || m_Scratch.rows != input.rows) m_Scratch.create(input.rows, input.cols); }
-            else output.create(input.rows, input.cols);
+            if (device) { dst = &m_Scratch; if (m_Scratch.cols != w || m_Scratch.rows != h) detail::allocate(m_Scratch, h, w); }
+            else detail::allocate(output, h, w);
         }
-        const lvkb200_memspace out_space = dst->on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST;
-        const lvkb200_status st = lvkb200_stream_submit(
-            m_Stream, input.data, input.step, input.cols, input.rows, static_cast<lvkb200_format>(input.format),
-            input.timestamp, input.on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST, dst->data, dst->step, out_space, &m_Result);
+        lvkb200_status st;
+        {
+            const detail::Pixels src(input, false);
+            if (alias)
+                st = lvkb200_stream_submit(m_Stream, src.data, src.step, w, h, fmt, ts, src.space, src.data, src.step, src.space, &m_Result);
+            else
+            {
+                const detail::Pixels out(*dst, true);
+                st = lvkb200_stream_submit(m_Stream, src.data, src.step, w, h, fmt, ts, src.space, out.data, out.step, out.space, &m_Result);
+            }
+            // A device output may still be pending (the library can hold the remap back, lvkb200.h): the reference hands out
+            // a complete frame (a UMat access synchronises), so does this mirror.  Callers that want the overlap use stream().
+            if (st == LVKB200_OK && m_Result.has_output && device) lvkb200_stream_sync(m_Stream);
+        }
         if (!check(st, "StabilizationFilter::filter") || !m_Result.has_output)
         {
             output.release();  // StabilizationFilter.cpp:94,134
@@ -343,7 +624,7 @@ private:
         struct Pending { uint64_t ticket; size_t slot; lvkb200_result res; };
         Frame current, next;
         if (!read(current)) return;
-        if (profile || current.on_device)  // profiling synchronises around every frame; device frames need no copies
+        if (profile || detail::on_device(current))  // profiling synchronises around every frame; device frames need no copies
         {
             Frame out;
             do
@@ -372,16 +653,20 @@ private:
             LVK_ASSERT(!current.empty());
             m_LastWidth = current.cols; m_LastHeight = current.rows;
             const bool have_next = read(next);
-            if (have_next && !next.empty() && !next.on_device)
-                check(lvkb200_stream_prefetch_frame(m_Stream, next.data, next.step, next.cols, next.rows,
+            if (have_next && !next.empty() && !detail::on_device(next))
+            {
+                const detail::Pixels np(next, false);
+                check(lvkb200_stream_prefetch_frame(m_Stream, np.data, np.step, next.cols, next.rows,
                                                     static_cast<lvkb200_format>(next.format), LVKB200_MEM_HOST),
                       "StabilizationFilter::stream");
+            }
             VideoFrame& out = outputs[i % 3];
-            if (out.empty() || out.cols != current.cols || out.rows != current.rows) out.create(current.rows, current.cols);
+            if (out.empty() || out.cols != current.cols || out.rows != current.rows) detail::allocate(out, current.rows, current.cols);
             Pending p{0, i % 3, {}};
+            const detail::Pixels cp(current, false), op(out, true);
             const lvkb200_status st = lvkb200_stream_submit_async(
-                m_Stream, current.data, current.step, current.cols, current.rows, static_cast<lvkb200_format>(current.format),
-                current.timestamp, LVKB200_MEM_HOST, out.data, out.step, LVKB200_MEM_HOST, &p.res, &p.ticket);
+                m_Stream, cp.data, cp.step, current.cols, current.rows, static_cast<lvkb200_format>(current.format),
+                current.timestamp, LVKB200_MEM_HOST, op.data, op.step, LVKB200_MEM_HOST, &p.res, &p.ticket);
             if (!check(st, "StabilizationFilter::stream")) { drain(); return; }
             m_Result = p.res;
             if (p.res.has_output) pending.push_back(p);
@@ -464,7 +749,6 @@ protected:
         context::assert_handler("lvkb200", where, lvkb200_last_error());
         return false;
     }
-    static lvkb200_memspace space_of(const VideoFrame& f) { return f.on_device ? LVKB200_MEM_DEVICE : LVKB200_MEM_HOST; }
     lvkb200_stream* m_Stream = nullptr;
 };
 }  // namespace detail
@@ -508,9 +792,12 @@ private:
         const int bs = static_cast<int>(m_Settings.block_size);
         m_FilterRegion.x = m_FilterRegion.y = 0;
         m_FilterRegion.width = input.cols / bs * bs; m_FilterRegion.height = input.rows / bs * bs;
-        check(lvkb200_deblock(m_Stream, &pod, input.data, input.step, input.cols, input.rows,
-                              static_cast<lvkb200_format>(input.format), space_of(input), input.data, input.step,
-                              space_of(input)), "DeblockingFilter::filter");
+        {
+            const detail::Pixels px(input, true);
+            check(lvkb200_deblock(m_Stream, &pod, px.data, px.step, input.cols, input.rows,
+                                  static_cast<lvkb200_format>(input.format), px.space, px.data, px.step, px.space),
+                  "DeblockingFilter::filter");
+        }
         if (&input != &output) output = std::move(input);
     }
     void sync_device() override { lvkb200_stream_sync(m_Stream); }
@@ -559,13 +846,16 @@ private:
         // a host output is (re)created at the output size (dst.create, Image.cpp:182); a device output must already have it
         VideoFrame result;
         VideoFrame* dst = &result;
-        if (&input != &output && output.on_device && output.cols == pod.output_width && output.rows == pod.output_height)
+        if (&input != &output && detail::on_device(output) && output.cols == pod.output_width && output.rows == pod.output_height)
             dst = &output;
         else
-            result.create(pod.output_height, pod.output_width);
-        const bool ok = check(lvkb200_scaling_filter(m_Stream, &pod, input.data, input.step, input.cols, input.rows,
-                                                     space_of(input), dst->data, dst->step, space_of(*dst)),
-                              "ScalingFilter::filter");
+            detail::allocate(result, pod.output_height, pod.output_width);
+        bool ok;
+        {
+            const detail::Pixels src(input, false), out(*dst, true);
+            ok = check(lvkb200_scaling_filter(m_Stream, &pod, src.data, src.step, input.cols, input.rows, src.space, out.data,
+                                              out.step, out.space), "ScalingFilter::filter");
+        }
         const uint64_t ts = input.timestamp;
         const VideoFrame::Format fmt = input.format;
         if (!ok) { output.release(); return; }

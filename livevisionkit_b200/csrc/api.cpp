@@ -232,6 +232,12 @@ lvkb200_status lvkb200_stream_sync(lvkb200_stream* s)
     return s->sync_all();
 }
 
+lvkb200_status lvkb200_device_synchronize(void)
+{
+    LVKB_CUDA(cudaDeviceSynchronize());
+    return LVKB200_OK;
+}
+
 lvkb200_status lvkb200_stream_event_record(lvkb200_stream* s, int index)
 {
     LVKB_REQUIRE(s != nullptr && index >= 0 && index < LVKB200_EVENT_SLOTS);

@@ -65,7 +65,7 @@ int main(int argc, char** argv)
     const int before = failures;
     filter.configure(bad);
     if (failures != before + 1) return 4;
-    std::printf("timing_ms %.3f\n", filter.timings().elapsed_ms());
+    std::printf("timing_ms %.3f\n", filter.timings().elapsed().milliseconds());
 
     // ---- VideoFilter::stream (VideoFilter.cpp:62-209) on a fresh filter: the pipelined device path must deliver exactly
     // the frames apply() produced, and a true return from the callback must terminate it

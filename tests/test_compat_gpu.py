@@ -60,3 +60,35 @@ def test_cpp_compat_layer_matches_python_mirror(tmp_path):
     twice = L.DeblockingFilter(device=0).apply(L.VideoFrame(deblocked.copy(), 77, L.BGR)).data
     assert named["composite"] == checksum(scaler.apply(L.VideoFrame(twice, 77, L.BGR)).data)
     assert "sharpness" in out.stderr  # ScalingFilter::configure precondition reached the assert handler
+
+
+def test_cpp_compat_layer_with_umat_videoframe(tmp_path):
+    """lvk-compat built with the reference's own `struct VideoFrame : cv::UMat` (mock opencv2/), driven like the OBS
+    plugin (apply(std::move(frame), frame), VSFilter.cpp:352-364) and through VideoFilter::stream(cv::VideoCapture&):
+    same outputs as the Python mirror, Stopwatch statistics available through timings()."""
+    import livevisionkit_b200 as L
+    exe = str(tmp_path / "test_compat_umat")
+    libdir = os.path.join(ROOT, "livevisionkit_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror",
+                           "-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv"),
+                           os.path.join(ROOT, "tests", "cpp", "test_compat_umat.cpp"), "-o", exe, f"-L{libdir}",
+                           "-l:liblvkb200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe, "14"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().splitlines()]
+    flt = L.StabilizationFilter(L.StabilizationFilterSettings.obs_homography_preset(), 0)
+    expected = []
+    for i in range(14):
+        v = flt.apply(L.VideoFrame(_frame(i), 1000 + i, L.BGR))
+        idx, ts, total = lines[i]
+        assert int(idx) == i
+        if v.empty():
+            assert ts == "empty"
+        else:
+            assert int(ts) == v.timestamp and int(total) == int(v.data.astype(np.uint64).sum())
+            expected.append(int(total))
+    assert lines[14][0] == "timings" and int(lines[14][1]) == 14 and float(lines[14][2]) > 0.0 and float(lines[14][3]) >= 0.0
+    streamed = [l for l in lines if l[0].startswith("s") and l[0] != "stream"]
+    # the capture path stamps frames 0, 1, ... (VideoFilter.cpp:96-100): outputs are frames 0..3, same pixels as apply()
+    assert [int(l[2]) for l in streamed] == expected and [int(l[1]) for l in streamed] == [0, 1, 2, 3]
+    assert lines[-1] == ["stream", "4"]
