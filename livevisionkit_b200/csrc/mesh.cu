@@ -283,6 +283,124 @@ __global__ void __launch_bounds__(T, 1)
             atomicAdd(&cell_cnt[cell], 1);
         }
         __syncthreads();
+        if (n == 8)
+        {
+            // ---- the library-default 2x2 mesh (8 unknowns, ONE cell: every feature touches all four vertices).  The
+            // sparse transpose product would walk all N features sequentially per unknown; instead the normal equations
+            // are formed once - they are block structured: the x and the y rows of a feature share their weights, so
+            // A^T A = [W 0; 0 W] interleaved with W = sum_f w w^T (10 sums) and A^T b from sum_f w m.x, sum_f w m.y
+            // (8 sums) - and the SAME preconditioned CG iteration (oracle/lscg_ref.c) runs on the 8x8 system in one
+            // thread.  Identical in exact arithmetic; the float32 summation order differs (tests: <= 5e-3 px).
+            float acc[18];
+#pragma unroll
+            for (int k = 0; k < 18; k++) acc[k] = 0.0f;
+            for (int i = tid; i < N; i += T)
+            {
+                const float4 w4 = fw[i];
+                const float wv[4] = {w4.x, w4.w, w4.y, w4.z};  // vertices 0 (i00), 1 (i10), 2 (i01), 3 (i11)
+                const float2 m = dst[i];
+                int k = 0;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = a; b < 4; b++) acc[k++] += wv[a] * wv[b];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { acc[10 + a] += wv[a] * m.x; acc[14 + a] += wv[a] * m.y; }
+            }
+#pragma unroll
+            for (int k = 0; k < 18; k++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            if ((tid & 31) == 0)
+#pragma unroll
+                for (int k = 0; k < 18; k++) q[(tid >> 5) * 18 + k] = acc[k];
+            __syncthreads();
+            if (tid == 0)
+            {
+                float sum[18];
+                for (int k = 0; k < 18; k++)
+                {
+                    float t = 0.0f;
+                    for (int w = 0; w < NW; w++) t += q[w * 18 + k];
+                    sum[k] = t;
+                }
+                const float ts = prm.temporal_weight;
+                float Nm[8][8], g[8], xs[8];
+                for (int a = 0; a < 8; a++)
+                {
+                    for (int b = 0; b < 8; b++) Nm[a][b] = 0.0f;
+                    xs[a] = x[a];
+                    g[a] = ts * (ts * xs[a]);  // temporal rows: A = ts I, b = ts x_prev
+                    Nm[a][a] = ts * ts;
+                }
+                int k = 0;
+                for (int a = 0; a < 4; a++)
+                    for (int b = a; b < 4; b++, k++)
+                        for (int comp = 0; comp < 2; comp++)
+                        {
+                            Nm[2 * a + comp][2 * b + comp] += sum[k];
+                            if (a != b) Nm[2 * b + comp][2 * a + comp] += sum[k];
+                        }
+                for (int a = 0; a < 4; a++) { g[2 * a] += sum[10 + a]; g[2 * a + 1] += sum[14 + a]; }
+                for (int r0 = 0; r0 < S; r0++)  // similarity rows (right-hand side 0)
+                    for (int a = 0; a < 4; a++)
+                        for (int b = 0; b < 4; b++)
+                            Nm[sim_col[4 * r0 + a]][sim_col[4 * r0 + b]] += sim_val[4 * r0 + a] * sim_val[4 * r0 + b];
+                float invdg[8], nres[8], pp[8], Np[8];
+                float rhs_norm2 = 0.0f, res_norm2 = 0.0f, abs_new = 0.0f;
+                for (int a = 0; a < 8; a++)
+                {
+                    invdg[a] = Nm[a][a] > 0.0f ? 1.0f / Nm[a][a] : 1.0f;
+                    float t = g[a];
+                    for (int b = 0; b < 8; b++) t -= Nm[a][b] * xs[b];
+                    nres[a] = t;
+                    rhs_norm2 += g[a] * g[a];
+                }
+                if (rhs_norm2 == 0.0f)
+                {
+                    for (int a = 0; a < 8; a++) xs[a] = 0.0f;
+                }
+                else
+                {
+                    const float threshold = FLT_EPSILON * FLT_EPSILON * rhs_norm2;
+                    for (int a = 0; a < 8; a++) res_norm2 += nres[a] * nres[a];
+                    if (!(res_norm2 < threshold))
+                    {
+                        for (int a = 0; a < 8; a++) { pp[a] = invdg[a] * nres[a]; abs_new += nres[a] * pp[a]; }
+                        while (iterations < 16)
+                        {
+                            float pNp = 0.0f;
+                            for (int a = 0; a < 8; a++)
+                            {
+                                float t = 0.0f;
+                                for (int b = 0; b < 8; b++) t += Nm[a][b] * pp[b];
+                                Np[a] = t;
+                                pNp += pp[a] * t;
+                            }
+                            const float alpha = abs_new / pNp;
+                            res_norm2 = 0.0f;
+                            for (int a = 0; a < 8; a++)
+                            {
+                                xs[a] += alpha * pp[a];
+                                nres[a] -= alpha * Np[a];
+                                res_norm2 += nres[a] * nres[a];
+                            }
+                            if (res_norm2 < threshold) break;
+                            const float abs_old = abs_new;
+                            abs_new = 0.0f;
+                            for (int a = 0; a < 8; a++) abs_new += nres[a] * (invdg[a] * nres[a]);
+                            const float beta = abs_new / abs_old;
+                            for (int a = 0; a < 8; a++) pp[a] = invdg[a] * nres[a] + beta * pp[a];
+                            iterations++;
+                        }
+                    }
+                }
+                for (int a = 0; a < 8; a++) x[a] = xs[a];
+            }
+            __syncthreads();
+        }
+        else
+        {
         // exclusive scan of the cell populations (<= a few hundred cells: one warp, 32 cells per step)
         if (tid < 32)
         {
@@ -414,6 +532,7 @@ __global__ void __launch_bounds__(T, 1)
                 }
             }
         }
+        }  // sparse path (n != 8)
         __syncthreads();
 
         // ---- results: new state, mesh copy for the host, inlier mask (FrameTracker.cpp:279-300)

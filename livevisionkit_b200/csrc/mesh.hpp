@@ -1,8 +1,9 @@
 // K6c — device solver for FrameTracker::estimate_local_motions (LiveVisionKit/Vision/FrameTracker.cpp:200-321): the
 // Eigen::LeastSquaresConjugateGradient solve of the motion-mesh system as ONE persistent CTA that follows the
-// swap-erase compaction on the tracking stream.  Used for meshes with >= MESH_DEVICE_MIN_UNKNOWNS unknowns (the OBS
-// "Vector Field" preset: 16x16 vertices -> 512 unknowns, ~135 CG iterations per frame = 2.7 ms in the host solver);
-// the library-default 2x2 mesh (8 unknowns) stays on the host (host_mesh.hpp).
+// swap-erase compaction on the tracking stream.  Used for EVERY mesh that fits one CTA's shared memory: the OBS
+// "Vector Field" preset (16x16 vertices -> 512 unknowns, ~135 CG iterations per frame = 2.7 ms in the host solver) and
+// the library-default 2x2 mesh (8 unknowns), so no preset has a CPU solver on its path.  The host restatement
+// (host_mesh.hpp) remains for meshes too large for a CTA and behind LVKB200_MESH_DEVICE_MIN=<unknowns> (debug knob).
 #pragma once
 
 #include <vector>
@@ -14,7 +15,7 @@
 namespace lvkb200
 {
 
-constexpr int MESH_DEVICE_MIN_UNKNOWNS = 64;
+constexpr int MESH_DEVICE_MIN_UNKNOWNS = 8;
 constexpr int MESH_CGLS_THREADS = 512;
 
 // Static rows of the system that are not the (diagonal) temporal rows: the similarity constraints of

@@ -20,9 +20,10 @@
 //
 // Kernels (one dependent chain on one stream; the point count lives in device memory so nothing waits for the host):
 //   k_compact_swap_erase: single CTA; replays the reference's erase order on an index permutation, then gathers
-//   k_ransac_hypotheses : 256 minimal 4-point models, one thread each, closed form (unit square -> quad, no solve)
-//   k_ransac_score      : one CTA per hypothesis, all points scored with a cooperative-groups block reduction
-//                         (truncated-quadratic / MSAC cost at the acceptance threshold)
+//   k_ransac_score      : one CTA per hypothesis: its minimal 4-point model in closed form (unit square -> quad, no
+//                         solve; one thread), then all points scored with a cooperative-groups block reduction
+//                         (truncated-quadratic / MSAC cost at the acceptance threshold) and an atomicMin of the
+//                         packed (cost, index) key = the arg-min over the hypotheses
 //   k_ransac_refine     : single CTA: arg-min hypothesis, then 3 IRLS passes of a Hartley-normalised weighted DLT
 //                         (sigma-consensus style weights), warp-parallel 8x8 Gauss-Jordan, final mask.
 
@@ -135,14 +136,10 @@ __device__ __forceinline__ bool square_to_quad(const double qx[4], const double 
     return true;
 }
 
-__global__ void __launch_bounds__(128)
-    k_ransac_hypotheses(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                        const TrackParams* __restrict__ prm, uint32_t seed, float* __restrict__ models)
+// Minimal model number k of the fixed hypothesis stream -> out[0..8] (out[8] == 0: degenerate sample, no model).
+__device__ __forceinline__ void make_hypothesis(int k, int n, const float2* __restrict__ src, const float2* __restrict__ dst,
+                                                const TrackParams* __restrict__ prm, uint32_t seed, float* out)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= HYP) return;
-    const int n = *n_ptr;
-    float* out = models + (size_t)k * 9;
     out[8] = 0.0f;  // invalid until proven otherwise
     if (prm->model == 1)
     {
@@ -223,7 +220,8 @@ __device__ __forceinline__ float reproj_err2(const float m[9], float2 p, float2 
 
 __global__ void __launch_bounds__(256)
     k_ransac_score(const float2* __restrict__ src, const float2* __restrict__ dst, const int* __restrict__ n_ptr,
-                   const float* __restrict__ models, const TrackParams* __restrict__ prm, float* __restrict__ scores)
+                   float* __restrict__ models, const TrackParams* __restrict__ prm, float* __restrict__ scores,
+                   unsigned long long* __restrict__ best_key, uint32_t seed)
 {
     const float thr2 = prm->threshold_sq;
     cg::thread_block block = cg::this_thread_block();
@@ -231,7 +229,20 @@ __global__ void __launch_bounds__(256)
     __shared__ float m[9];
     __shared__ float partial[8];
     const int n = *n_ptr;
-    if (threadIdx.x < 9) m[threadIdx.x] = models[(size_t)blockIdx.x * 9 + threadIdx.x];
+    // the CTA's own hypothesis first (one thread, ~1 us of dependent FP64): a separate 256-thread kernel for the 256
+    // closed-form models cost a launch and a drain on the frame's critical path; the other threads pull the first
+    // correspondences they will score towards L1 meanwhile
+    if (threadIdx.x == 0)
+    {
+        float h[9];
+        make_hypothesis((int)blockIdx.x, n, src, dst, prm, seed, h);
+        for (int j = 0; j < 9; j++) { m[j] = h[j]; models[(size_t)blockIdx.x * 9 + j] = h[j]; }
+    }
+    else if ((int)threadIdx.x < n)
+    {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(src + threadIdx.x));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(dst + threadIdx.x));
+    }
     block.sync();
     if (m[8] == 0.0f || n < 4)
     {
@@ -252,23 +263,75 @@ __global__ void __launch_bounds__(256)
         float s = 0.0f;
         for (int w = 0; w < 8; w++) s += partial[w];
         scores[blockIdx.x] = s;
+        // arg-min over the hypotheses, lowest index wins ties: costs are >= 0, so their bit patterns order like the values
+        if (s < 2.9e38f) atomicMin(best_key, ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)blockIdx.x);
     }
 }
 
-constexpr int RT = 256;  // refine CTA size
+constexpr int RT = 512;  // refine CTA size
+constexpr int PPT = 6;   // correspondences a thread keeps in registers (RT * PPT = 3072 >= the tracker's point capacity)
 
-// Entry (r, c) of the 8 x 9 augmented normal equations [A^T W A | A^T W b] of the weighted DLT (h33 = 1) from the 23
-// moments S[0..5] = S0, S[6..11] = Su, S[12..17] = Sv, S[18..22] = Sq, each packed xx xy x yy y 1 (see refine_body).
-__device__ __forceinline__ double gram_entry(const double* S, int r, int c)
+// Entry (r, c) of the 8 x 9 augmented normal equations [A^T W A | A^T W b] of the weighted DLT (h33 = 1) is +- one of the
+// 23 moments S[0..5] = S0, S[6..11] = Su, S[12..17] = Sv, S[18..22] = Sq, each packed xx xy x yy y 1 (see refine_body):
+// -> index into S (-1: structural zero) and sign.
+__device__ __forceinline__ void gram_index(int r, int c, int& idx, bool& neg)
 {
-    const int pack[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    auto pack = [](int i, int j) { const int a = min(i, j), b = max(i, j); return a * (5 - a) / 2 + b; };  // symmetric 3x3
     const int rb = r / 3, ri = r - 3 * rb;
-    if (c == 8) return (rb == 0) ? S[6 + pack[ri][2]] : (rb == 1) ? S[12 + pack[ri][2]] : -S[18 + pack[ri][2]];
+    neg = false;
+    if (c == 8)
+    {
+        idx = (rb == 0 ? 6 : rb == 1 ? 12 : 18) + pack(ri, 2);
+        neg = rb == 2;
+        return;
+    }
     const int cb = c / 3, ci = c - 3 * cb;
-    if (rb == cb) return (rb < 2) ? S[pack[ri][ci]] : S[18 + pack[ri][ci]];
-    if (rb + cb == 1) return 0.0;
+    if (rb == cb) { idx = (rb < 2 ? 0 : 18) + pack(ri, ci); return; }
+    if (rb + cb == 1) { idx = -1; return; }
     const int other = min(rb, cb), i = (rb < cb) ? ri : ci, j = (rb < cb) ? ci : ri;  // i: index in p, j: block-2 index
-    return -S[(other == 0 ? 6 : 12) + pack[i][j]];
+    idx = (other == 0 ? 6 : 12) + pack(i, j);
+    neg = true;
+}
+
+// 1 / d to full double precision without the IEEE division's range tests and slow path (d is a pivot / scale here):
+// hardware seed (>= 20 bits) + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
+
+// Block total of up to 32 per-thread double accumulators -> s_mom[0..31].  Within a warp a recursive-halving
+// reduce-scatter (31 shuffles for all 32 values; lane l ends up owning slot l) instead of 32 five-step butterflies, then
+// one lane per slot adds the warps' totals.  Two barriers.
+__device__ __forceinline__ void block_sum32(double (&acc)[32], double (*s_part)[32], double* s_mom)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1)
+    {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++)
+        {
+            const double keep = upper ? acc[i + half] : acc[i];
+            const double send = upper ? acc[i] : acc[i + half];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    s_part[wid][lane] = acc[0];  // this warp's total of slot `lane`
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < RT / 32; w++) s += s_part[w][threadIdx.x];
+        s_mom[threadIdx.x] = s;
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ void
@@ -278,44 +341,47 @@ __device__ __forceinline__ void
                 uint8_t* __restrict__ mask)
 {
     const float thr2 = prm->threshold_sq;
-    cg::thread_block block = cg::this_thread_block();
-    cg::thread_block_tile<32> warp = cg::tiled_partition<32>(block);
-    __shared__ float s_best[RT / 32];
-    __shared__ int s_besti[RT / 32];
-    __shared__ double s_acc[RT / 32][8];
     __shared__ double s_part[RT / 32][32];
     __shared__ double s_mom[32];
-    __shared__ double s_T[8];
     __shared__ float s_m[9];
-    __shared__ int s_ok;
-    const int tid = threadIdx.x, lane = warp.thread_rank(), wid = warp.meta_group_rank();
+    __shared__ int s_ok, s_count;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = *n_ptr;
 
-    // ---- arg-min over hypotheses (lowest index wins ties)
-    float best = 3.0e38f;
-    int besti = -1;
-    for (int k = tid; k < HYP; k += RT)
-        if (scores[k] < best) { best = scores[k]; besti = k; }
-    for (int o = 16; o > 0; o >>= 1)
+    // ---- the correspondences live in registers for the whole kernel (every pass below would re-read them from L2)
+    float2 ps[PPT], pd[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++)
     {
-        const float ob = warp.shfl_xor(best, o);
-        const int oi = warp.shfl_xor(besti, o);
-        if (oi >= 0 && (besti < 0 || ob < best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+        const int i = tid + k * RT;
+        ps[k] = i < n ? src[i] : make_float2(0.0f, 0.0f);
+        pd[k] = i < n ? dst[i] : make_float2(0.0f, 0.0f);
     }
-    if (lane == 0) { s_best[wid] = best; s_besti[wid] = besti; }
-    block.sync();
+    // BODY sees the index i and the correspondence (p, d); points beyond the register tile come from global memory
+#define LVKB_FOR_POINTS(...)                                                                                           \
+    {                                                                                                                 \
+        _Pragma("unroll") for (int k_ = 0; k_ < PPT; k_++)                                                            \
+        {                                                                                                             \
+            const int i = tid + k_ * RT;                                                                              \
+            if (i < n) { const float2 p = ps[k_], d = pd[k_]; __VA_ARGS__ }                                                  \
+        }                                                                                                             \
+        for (int i = tid + PPT * RT; i < n; i += RT) { const float2 p = src[i], d = dst[i]; __VA_ARGS__ }                    \
+    }
+
+    // ---- best hypothesis: the scoring pass left the arg-min as a packed (cost bits, index) key behind the scores
     if (tid == 0)
     {
-        float b = 3.0e38f;
-        int bi = -1;
-        for (int w = 0; w < RT / 32; w++)
-            if (s_besti[w] >= 0 && (bi < 0 || s_best[w] < b || (s_best[w] == b && s_besti[w] < bi))) { b = s_best[w]; bi = s_besti[w]; }
-        s_ok = (n >= 4 && bi >= 0 && b < 2.9e38f) ? 1 : 0;
+        unsigned long long* const key_ptr = reinterpret_cast<unsigned long long*>(const_cast<float*>(scores + HYP));
+        const unsigned long long key = *key_ptr;
+        *key_ptr = ~0ull;  // armed for the next scoring pass (the buffer is created in this state)
+        const int bi = (int)(unsigned)(key & 0xffffffffull);
+        s_ok = (n >= 4 && key != ~0ull && bi < HYP) ? 1 : 0;
         if (s_ok)
             for (int j = 0; j < 9; j++) s_m[j] = models[(size_t)bi * 9 + j];
+        s_count = 0;
         result->n = n;
     }
-    block.sync();
+    __syncthreads();
     if (!s_ok)
     {
         if (tid == 0) { result->found = 0; result->inliers = 0; }
@@ -330,46 +396,35 @@ __device__ __forceinline__ void
         // to for this linear model).  Centred closed form: a = S(x'u'+y'v')/S(x'^2+y'^2), b = S(x'v'-y'u')/S(..).
         float m[9];
         for (int j = 0; j < 9; j++) m[j] = s_m[j];
-        double c[5] = {0, 0, 0, 0, 0};
-        for (int i = tid; i < n; i += RT)
-        {
-            const float e = reproj_err2(m, src[i], dst[i]);
-            const bool in = e < thr2;
+        double acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = 0.0;
+        LVKB_FOR_POINTS({
+            const bool in = reproj_err2(m, p, d) < thr2;
             mask[i] = in ? 1 : 0;
-            if (in) { c[0] += 1.0; c[1] += src[i].x; c[2] += src[i].y; c[3] += dst[i].x; c[4] += dst[i].y; }
-        }
-        for (int j = 0; j < 5; j++) c[j] = cg::reduce(warp, c[j], cg::plus<double>());
-        if (lane == 0) for (int j = 0; j < 5; j++) s_acc[wid][j] = c[j];
-        block.sync();
-        if (tid < 5)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
-            s_T[tid] = s;
-        }
-        block.sync();
-        const double cnt = s_T[0];
-        const double cx = s_T[1] / fmax(cnt, 1.0), cy = s_T[2] / fmax(cnt, 1.0);
-        const double cu = s_T[3] / fmax(cnt, 1.0), cv = s_T[4] / fmax(cnt, 1.0);
-        double q[3] = {0, 0, 0};
-        for (int i = tid; i < n; i += RT)
-        {
-            if (!mask[i]) continue;
-            const double x = src[i].x - cx, y = src[i].y - cy, u = dst[i].x - cu, v = dst[i].y - cv;
-            q[0] += x * x + y * y; q[1] += x * u + y * v; q[2] += x * v - y * u;
-        }
-        for (int j = 0; j < 3; j++) q[j] = cg::reduce(warp, q[j], cg::plus<double>());
-        block.sync();
-        if (lane == 0) for (int j = 0; j < 3; j++) s_acc[wid][j] = q[j];
-        block.sync();
+            if (in) { acc[0] += 1.0; acc[1] += p.x; acc[2] += p.y; acc[3] += d.x; acc[4] += d.y; }
+        })
+        block_sum32(acc, s_part, s_mom);
+        const double cnt = s_mom[0];
+        const double cx = s_mom[1] / fmax(cnt, 1.0), cy = s_mom[2] / fmax(cnt, 1.0);
+        const double cu = s_mom[3] / fmax(cnt, 1.0), cv = s_mom[4] / fmax(cnt, 1.0);
+        __syncthreads();  // s_mom is reused below
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = 0.0;
+        LVKB_FOR_POINTS({
+            if (reproj_err2(m, p, d) < thr2)
+            {
+                const double x = p.x - cx, y = p.y - cy, u = d.x - cu, v = d.y - cv;
+                acc[0] += x * x + y * y; acc[1] += x * u + y * v; acc[2] += x * v - y * u;
+            }
+        })
+        block_sum32(acc, s_part, s_mom);
         if (tid == 0)
         {
-            double s[3] = {0, 0, 0};
-            for (int w = 0; w < RT / 32; w++) for (int j = 0; j < 3; j++) s[j] += s_acc[w][j];
             double a = m[0], b = m[3], tx = m[2], ty = m[5];
-            if (cnt >= 2.0 && s[0] > 1e-9)
+            if (cnt >= 2.0 && s_mom[0] > 1e-9)
             {
-                a = s[1] / s[0]; b = s[2] / s[0];
+                a = s_mom[1] / s_mom[0]; b = s_mom[2] / s_mom[0];
                 tx = cu - (a * cx - b * cy); ty = cv - (b * cx + a * cy);
             }
             result->h[0] = a; result->h[1] = -b; result->h[2] = tx;
@@ -381,40 +436,27 @@ __device__ __forceinline__ void
         return;
     }
 
-    // ---- Hartley normalisation of both point sets, once (it only conditions the normal equations)
+    // ---- isotropic normalisation of both point sets from ONE pass (it only conditions the normal equations): centroid
+    // to the origin, RMS distance to sqrt(2)
+    double cx, cy, cu, cv, s1, s2;
     {
-        double c[4] = {0, 0, 0, 0};
-        for (int i = tid; i < n; i += RT) { c[0] += src[i].x; c[1] += src[i].y; c[2] += dst[i].x; c[3] += dst[i].y; }
-        for (int j = 0; j < 4; j++) c[j] = cg::reduce(warp, c[j], cg::plus<double>());
-        if (lane == 0) for (int j = 0; j < 4; j++) s_acc[wid][j] = c[j];
-        block.sync();
-        if (tid < 4)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
-            s_T[tid] = s / n;
-        }
-        block.sync();
-        const double cx = s_T[0], cy = s_T[1], cu = s_T[2], cv = s_T[3];
-        double d[2] = {0, 0};
-        for (int i = tid; i < n; i += RT)
-        {
-            d[0] += sqrt((src[i].x - cx) * (src[i].x - cx) + (src[i].y - cy) * (src[i].y - cy));
-            d[1] += sqrt((dst[i].x - cu) * (dst[i].x - cu) + (dst[i].y - cv) * (dst[i].y - cv));
-        }
-        for (int j = 0; j < 2; j++) d[j] = cg::reduce(warp, d[j], cg::plus<double>());
-        block.sync();
-        if (lane == 0) { s_acc[wid][0] = d[0]; s_acc[wid][1] = d[1]; }
-        block.sync();
-        if (tid < 2)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_acc[w][tid];
-            s_T[4 + tid] = (s > 1e-9) ? 1.4142135623730951 * n / s : 1.0;
-        }
-        block.sync();
+        double acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = 0.0;
+        LVKB_FOR_POINTS({
+            (void)i;
+            acc[0] += p.x; acc[1] += p.y; acc[2] += d.x; acc[3] += d.y;
+            acc[4] += (double)p.x * p.x + (double)p.y * p.y;
+            acc[5] += (double)d.x * d.x + (double)d.y * d.y;
+        })
+        block_sum32(acc, s_part, s_mom);
+        const double inv_n = 1.0 / (double)n;
+        cx = s_mom[0] * inv_n; cy = s_mom[1] * inv_n; cu = s_mom[2] * inv_n; cv = s_mom[3] * inv_n;
+        const double v1 = s_mom[4] * inv_n - (cx * cx + cy * cy), v2 = s_mom[5] * inv_n - (cu * cu + cv * cv);
+        s1 = v1 > 1e-12 ? sqrt(2.0 / v1) : 1.0;
+        s2 = v2 > 1e-12 ? sqrt(2.0 / v2) : 1.0;
+        __syncthreads();  // s_mom is reused by the first IRLS pass
     }
-    const double cx = s_T[0], cy = s_T[1], cu = s_T[2], cv = s_T[3], s1 = s_T[4], s2 = s_T[5];
 
     // ---- IRLS: weighted DLT with h33 = 1 in normalised coordinates.
     // weights: sigma-consensus style, smooth and compactly supported: w = (1 - e/c)^2 for e < c, c = 2.25 * thr^2
@@ -422,10 +464,17 @@ __device__ __forceinline__ void
     //
     // The normal equations A^T W A h = A^T W b of the rows [p 0 -u p | u], [0 p -v p | v] (p = (x, y, 1)) have block
     // structure: every entry is +-one of the 23 moments  S0 = sum w p p^T, Su = sum w u p p^T, Sv = sum w v p p^T,
-    // Sq = sum w (u^2+v^2) p p^T  (gram_entry), so a thread carries 23 accumulators instead of 36 + 8, and the warp
-    // total is taken with a recursive-halving reduce-scatter (31 shuffles for all 23 values; lane l ends up owning
-    // moment l) instead of 44 five-step butterflies: the shuffle unit was what this single-CTA kernel waited on.
+    // Sq = sum w (u^2+v^2) p p^T  (gram_entry), so a thread carries 23 accumulators instead of 36 + 8.
     const float c_sup = 2.25f * thr2;
+    const float inv_c_sup = 1.0f / c_sup;
+    // Gram row of lane (lane & 7): moment index (-1: structural zero) and sign of entry (r, c), see gram_entry
+    int gidx[9];
+    bool gneg[9];
+    {
+        const int r = lane & 7;
+#pragma unroll
+        for (int c = 0; c < 9; c++) gram_index(r, c, gidx[c], gneg[c]);
+    }
     for (int it = 0; it < iterations; it++)
     {
         float m[9];
@@ -433,120 +482,112 @@ __device__ __forceinline__ void
         double acc[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) acc[j] = 0.0;
-        for (int i = tid; i < n; i += RT)
-        {
-            const float2 p = src[i], d = dst[i];
+        LVKB_FOR_POINTS({
+            (void)i;
             const float e = reproj_err2(m, p, d);
-            if (!(e == e) || e >= c_sup) continue;
-            const float t = 1.0f - e / c_sup;
-            const double w = (double)(t * t);
-            const double x = (p.x - cx) * s1, y = (p.y - cy) * s1, u = (d.x - cu) * s2, v = (d.y - cv) * s2;
-            const double wx = w * x, wy = w * y;
-            const double pp[6] = {wx * x, wx * y, wx, wy * y, wy, w};  // w * p p^T, packed xx xy x yy y 1
-            const double q = u * u + v * v;
-#pragma unroll
-            for (int j = 0; j < 6; j++)
+            if (e == e && e < c_sup)
             {
-                acc[j] += pp[j];
-                acc[6 + j] += u * pp[j];
-                acc[12 + j] += v * pp[j];
-                if (j < 5) acc[18 + j] += q * pp[j];
-            }
-        }
-        // reduce-scatter over the warp: after the step with `half`, slot i holds moment i + (lane & ~(half - 1)) % 32
+                const float t = 1.0f - e * inv_c_sup;
+                const double w = (double)(t * t);
+                const double x = (p.x - cx) * s1, y = (p.y - cy) * s1, u = (d.x - cu) * s2, v = (d.y - cv) * s2;
+                const double wx = w * x, wy = w * y;
+                const double pp[6] = {wx * x, wx * y, wx, wy * y, wy, w};  // w * p p^T, packed xx xy x yy y 1
+                const double q = u * u + v * v;
 #pragma unroll
-        for (int half = 16; half >= 1; half >>= 1)
-        {
-            const bool upper = (lane & half) != 0;
-#pragma unroll
-            for (int i = 0; i < half; i++)
-            {
-                const double keep = upper ? acc[i + half] : acc[i];
-                const double send = upper ? acc[i] : acc[i + half];
-                acc[i] = keep + warp.shfl_xor(send, half);
+                for (int j = 0; j < 6; j++)
+                {
+                    acc[j] += pp[j];
+                    acc[6 + j] += u * pp[j];
+                    acc[12 + j] += v * pp[j];
+                    if (j < 5) acc[18 + j] += q * pp[j];
+                }
             }
-        }
-        s_part[wid][lane] = acc[0];  // this warp's total of moment `lane`
-        block.sync();
-        if (tid < 32)
-        {
-            double s = 0;
-            for (int w = 0; w < RT / 32; w++) s += s_part[w][tid];
-            s_mom[tid] = s;
-        }
-        block.sync();
+        })
+        block_sum32(acc, s_part, s_mom);
         if (s_mom[5] < 4.0) break;  // sum of weights: support collapsed, keep the current model
 
-        // warp 0: Gauss-Jordan on the 8x9 augmented SPD system, lane r owns row r
+        // warp 0: Gauss-Jordan on the 8x9 augmented SPD system, lane r owns row r.  The other 15 warps wait at the
+        // barrier below for this serial stretch, so it is kept short: table-free Gram assembly (index + sign per entry
+        // computed once, before the loop), reciprocal pivots without the IEEE division, and the denormalisation spread
+        // over nine lanes (one output coefficient each).
         if (wid == 0)
         {
             double row[9];
             const int r = lane & 7;
 #pragma unroll
-            for (int c = 0; c < 9; c++) row[c] = gram_entry(s_mom, r, c);
+            for (int c = 0; c < 9; c++) row[c] = gidx[c] < 0 ? 0.0 : (gneg[c] ? -s_mom[gidx[c]] : s_mom[gidx[c]]);
             bool ok = true;
+#pragma unroll
             for (int c = 0; c < 8; c++)
             {
                 double prow[9];
-                for (int k = 0; k < 9; k++) prow[k] = warp.shfl(row[k], c);
-                if (fabs(prow[c]) < 1e-14) { ok = false; break; }
-                const double inv = 1.0 / prow[c];
-                if (r == c) { for (int k = 0; k < 9; k++) row[k] = prow[k] * inv; }
-                else { const double f = row[c] * inv; for (int k = 0; k < 9; k++) row[k] -= f * prow[k]; }
+#pragma unroll
+                for (int k = 0; k < 9; k++) prow[k] = __shfl_sync(0xffffffffu, row[k], c);
+                ok = ok && fabs(prow[c]) >= 1e-14;
+                const double inv = fast_rcp(prow[c]);
+                if (r == c)
+                {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) row[k] = prow[k] * inv;
+                }
+                else
+                {
+                    const double f = row[c] * inv;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) row[k] = fma(-f, prow[k], row[k]);
+                }
             }
-            double h[8];
-            for (int k = 0; k < 8; k++) h[k] = warp.shfl(row[8], k);
-            if (lane == 0 && ok)
+            double h[9];
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[k] = __shfl_sync(0xffffffffu, row[8], k);
+            h[8] = 1.0;
+            // denormalise: H = T2^-1 * Hn * T1,  T = [s 0 -s*c; 0 s -s*c; 0 0 1]; lane k < 9 computes coefficient k
+            const int kk = lane < 9 ? lane : 0, orow = kk / 3, ocol = kk - 3 * orow;
+            // A = Hn * T1: column ocol of rows `orow` and 2
+            auto a_entry = [&](int rr) {
+                const double h0 = h[rr * 3], h1 = h[rr * 3 + 1], h2 = h[rr * 3 + 2];
+                return ocol == 0 ? h0 * s1 : ocol == 1 ? h1 * s1 : h2 - (h0 * cx + h1 * cy) * s1;
+            };
+            const double a2 = a_entry(2);
+            double hd;  // T2^-1 = [1/s 0 c; 0 1/s c; 0 0 1]
+            if (orow == 2) hd = a2;
+            else
             {
-                // denormalise: H = T2^-1 * Hn * T1,  T = [s 0 -s*c; 0 s -s*c; 0 0 1]
-                const double Hn[9] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 1.0};
-                double A[9];  // Hn * T1
-                for (int rr = 0; rr < 3; rr++)
-                {
-                    A[rr * 3 + 0] = Hn[rr * 3 + 0] * s1;
-                    A[rr * 3 + 1] = Hn[rr * 3 + 1] * s1;
-                    A[rr * 3 + 2] = Hn[rr * 3 + 2] - Hn[rr * 3 + 0] * s1 * cx - Hn[rr * 3 + 1] * s1 * cy;
-                }
-                double Hd[9];  // T2^-1 = [1/s 0 c; 0 1/s c; 0 0 1]
-                for (int k = 0; k < 3; k++)
-                {
-                    Hd[0 + k] = A[0 + k] / s2 + cu * A[6 + k];
-                    Hd[3 + k] = A[3 + k] / s2 + cv * A[6 + k];
-                    Hd[6 + k] = A[6 + k];
-                }
-                if (fabs(Hd[8]) > 1e-12)
-                {
-                    const double invh = 1.0 / Hd[8];
-                    for (int k = 0; k < 9; k++) { result->h[k] = Hd[k] * invh; s_m[k] = (float)(Hd[k] * invh); }
-                }
+                const double ar = orow == 0 ? a_entry(0) : a_entry(1);
+                hd = ar * fast_rcp(s2) + (orow == 0 ? cu : cv) * a2;
+            }
+            const double hd8 = __shfl_sync(0xffffffffu, hd, 8);
+            ok = ok && fabs(hd8) > 1e-12 && hd8 == hd8;
+            if (ok && lane < 9)
+            {
+                const double v = hd * fast_rcp(hd8);
+                result->h[lane] = v;
+                s_m[lane] = (float)v;
             }
         }
-        block.sync();
+        __syncthreads();
     }
 
     // ---- result + final mask with the returned model
     float m[9];
     for (int j = 0; j < 9; j++) m[j] = s_m[j];
     int inl = 0;
-    for (int i = tid; i < n; i += RT)
-    {
-        const float e = reproj_err2(m, src[i], dst[i]);
-        const uint8_t in = (e < thr2) ? 1 : 0;
+    LVKB_FOR_POINTS({
+        const uint8_t in = (reproj_err2(m, p, d) < thr2) ? 1 : 0;
         mask[i] = in;
         inl += in;
-    }
-    inl = cg::reduce(warp, inl, cg::plus<int>());
-    if (lane == 0) s_besti[wid] = inl;
-    block.sync();
+    })
+    inl = __reduce_add_sync(0xffffffffu, inl);
+    if (lane == 0 && inl) atomicAdd(&s_count, inl);
+    __syncthreads();
     if (tid == 0)
     {
-        int total = 0;
-        for (int w = 0; w < RT / 32; w++) total += s_besti[w];
-        result->inliers = total;
+        result->inliers = s_count;
         result->found = 1;
         if (iterations == 0 || result->h[8] == 0.0)
             for (int k = 0; k < 9; k++) result->h[k] = (double)s_m[k];
     }
+#undef LVKB_FOR_POINTS
 }
 
 static_assert(sizeof(RansacResult) % 4 == 0, "RansacResult is moved as 32-bit words");
@@ -613,11 +654,11 @@ lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const flo
                                  const TrackParams* d_params, float* d_models, float* d_scores,
                                  RansacResult* d_result, uint8_t* d_mask, const TrackOutCopy& out)
 {
-    k_ransac_hypotheses<<<div_up(HYP, 128), 128, 0, cs>>>(d_src, d_dst, d_n, d_params, 0x9E3779B9u, d_models);
-    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, d_params, d_scores);
+    unsigned long long* best_key = reinterpret_cast<unsigned long long*>(d_scores + HYP);  // behind the scores, 8-byte aligned
+    k_ransac_score<<<HYP, 256, 0, cs>>>(d_src, d_dst, d_n, d_models, d_params, d_scores, best_key, 0x9E3779B9u);
     k_ransac_refine<<<1, RT, 0, cs>>>(d_src, d_dst, d_n, d_models, d_scores, d_params, RANSAC_REFINE_ITERS, d_result,
                                       d_mask, out);
-    count_launches(3);
+    count_launches(2);
     LVKB_CUDA(cudaGetLastError());
     return LVKB200_OK;
 }

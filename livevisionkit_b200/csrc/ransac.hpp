@@ -38,7 +38,8 @@ struct TrackOutCopy
 // no estimator kernel follows LK.
 lvkb200_status track_out_copy(cudaStream_t cs, const TrackParams* d_params, const TrackOutCopy& out);
 
-// d_* are device memory (the count too).  d_models: HYP*9 floats, d_scores: HYP floats.  With out.host set, the last
+// d_* are device memory (the count too).  d_models: HYP*9 floats, d_scores: HYP + 4 floats
+// (the last 8 bytes, 8-byte aligned, hold the packed arg-min key of the scoring pass).  With out.host set, the last
 // kernel also copies the used part of the result block (d_params->n matches + status, mask, model) to the host mirror.
 lvkb200_status ransac_homography(cudaStream_t cs, const float2* d_src, const float2* d_dst, const int* d_n,
                                  const TrackParams* d_params, float* d_models, float* d_scores,

@@ -282,7 +282,12 @@ lvkb200_status lvkb200_stream::ensure_points(int n)
     LVKB_CUDA(d_src.ensure(sizeof(float2) * cap));
     LVKB_CUDA(d_dst.ensure(sizeof(float2) * cap));
     LVKB_CUDA(d_models.ensure(sizeof(float) * 9 * RANSAC_HYPOTHESES));
-    LVKB_CUDA(d_scores.ensure(sizeof(float) * RANSAC_HYPOTHESES));
+    if (d_scores.capacity < sizeof(float) * (RANSAC_HYPOTHESES + 4))
+    {
+        // + the packed (score, index) arg-min key of the scoring pass, created "armed" (all ones); the refine kernel re-arms it
+        LVKB_CUDA(d_scores.ensure(sizeof(float) * (RANSAC_HYPOTHESES + 4)));
+        LVKB_CUDA(cudaMemsetAsync(d_scores.ptr, 0xFF, sizeof(float) * (RANSAC_HYPOTHESES + 4), cs));
+    }
     LVKB_CUDA(d_perm.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_removed.ensure(sizeof(int) * cap));
     LVKB_CUDA(d_count.ensure(sizeof(int)));

@@ -92,7 +92,8 @@ struct lvkb200_stream
     lvkb200::FeatureGrid grid;
     lvkb200::PathSmoother smoother;
     lvkb200::MeshSolver mesh_solver;
-    // K6c: meshes with >= MESH_DEVICE_MIN_UNKNOWNS unknowns are solved by one CTA on the tracking stream (mesh.cu)
+    // K6c: every mesh (>= MESH_DEVICE_MIN_UNKNOWNS = 8 unknowns, the 2x2 default included) is solved by one CTA on the
+    // tracking stream (mesh.cu)
     lvkb200::MeshCgls mesh_device;
     unsigned mesh_device_generation = ~0u;  // mesh_solver.generation() the device copy of the static rows was made from
     int mesh_device_capacity = 0;
