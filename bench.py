@@ -16,7 +16,7 @@ on fresh frames (R = --windows, default 300 // K clamped to 1..15, so a 20-step 
 each rank keeps the MEDIAN of its R windows, the line reports the MAX of those medians over ranks (the slowest
 rank), and `per_rank` carries every rank's min / median / max so that rank skew and host noise can be told apart.
 value : whole-job fps with every input frame already resident in HBM and outputs left in HBM (CUDA events on the
-        library's stream around each window).
+        library's stream around each window; the window's K frames go through lvkb200_stream_submit_batch).
 e2e   : the same metric through the public pipelined API with pinned HOST buffers (H2D of the frame and D2H of the
         result inside the window, every step), host clock between the rank's own stream synchronisations.
 roofline / roofline_issue: the dominant kernel (EASU remap): algorithmic bytes (6 B/px) resp. executed
@@ -369,12 +369,20 @@ def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_
     if sampler is not None:
         sampler.start()
     dev_ms, wall_ms, outputs = [], [], 0
+    # the K frames of a window go through lvkb200_stream_submit_batch (VideoFilter::stream for frames already in memory:
+    # frame i+1 announced, frame i submitted, for the whole window in ONE call); the pointer tables are built beforehand
+    plans = [L.BatchPlan([dev_refs[i] for i in range(warmup + w * K, warmup + (w + 1) * K)],
+                         [out_refs[i % 16] for i in range(warmup + w * K, warmup + (w + 1) * K)],
+                         list(range(warmup + w * K, warmup + (w + 1) * K))) for w in range(R)] if settings_lookahead else None
     for w in range(R):
         barrier()
         s.event_record(0)
         t0 = time.perf_counter()
-        for i in range(warmup + w * K, warmup + (w + 1) * K):
-            outputs += dev_step(i).has_output
+        if plans is not None:
+            outputs += sum(r.has_output for r in s.submit_batch(plans[w], None, L.BGR))
+        else:
+            for i in range(warmup + w * K, warmup + (w + 1) * K):
+                outputs += dev_step(i).has_output
         s.event_record(1)
         s.sync()
         wall_ms.append(1e3 * (time.perf_counter() - t0))

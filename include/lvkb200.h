@@ -196,6 +196,16 @@ lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame,
                                            void* out, size_t out_pitch, lvkb200_memspace out_space,
                                            lvkb200_result* res, uint64_t* ticket);
 lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket);
+/* VideoFilter::stream (Filters/VideoFilter.cpp:62-209) for a sequence that is already in memory (a decoded clip, a
+ * capture ring): `count` frames of one geometry and format are filtered back to back, frame i into outs[i], exactly as
+ * `count` calls of lvkb200_stream_prefetch_frame(frame i+1) + lvkb200_stream_submit(frame i) would - one call instead of
+ * 2 * count crossings of the FFI.  results[i] reports has_output / timestamp of step i (the first frame_delay steps have
+ * none and leave outs[i] untouched).  timestamps may be NULL (0, 1, ...).  Device outputs follow the rule of
+ * lvkb200_stream_submit: complete after lvkb200_stream_sync. */
+lvkb200_status lvkb200_stream_submit_batch(lvkb200_stream* s, const void* const* frames, size_t pitch, int width, int height,
+                                           lvkb200_format format, const uint64_t* timestamps, lvkb200_memspace frame_space,
+                                           void* const* outs, size_t out_pitch, lvkb200_memspace out_space, int count,
+                                           lvkb200_result* results);
 
 /* ---- lvk::DeblockingFilter --------------------------------------------------------------------- */
 

@@ -155,6 +155,30 @@ def _buffer_info(buf):
     raise TypeError(f"unsupported frame buffer type {type(buf)}")
 
 
+class BatchPlan:
+    """Pointer tables of a frame sequence for Stream.submit_batch, built once (buffers are usually reused)."""
+
+    def __init__(self, frames, outs, timestamps=None):
+        frames, outs = list(frames), list(outs)
+        if len(frames) != len(outs):
+            raise ValueError("one output buffer per frame")
+        self.count = len(frames)
+        infos, oinfos = [_buffer_info(f) for f in frames], [_buffer_info(o) for o in outs]
+        ptr0, self.pitch, self.h, self.w, ch, self.space = infos[0] if infos else (0, 0, 0, 0, 3, _capi.MEM_HOST)
+        optr0, self.opitch, oh, ow, och, self.ospace = oinfos[0] if oinfos else (0, 0, 0, 0, 3, _capi.MEM_HOST)
+        for inf in infos:
+            if inf[1:] != (self.pitch, self.h, self.w, ch, self.space):
+                raise ValueError("submit_batch takes frames of one geometry, pitch and memory space")
+        for inf in oinfos:
+            if inf[1:] != (self.opitch, self.h, self.w, ch, self.ospace):
+                raise ValueError("output buffers must match the frames")
+        self.frames = (C.c_void_p * self.count)(*[inf[0] for inf in infos])
+        self.outs = (C.c_void_p * self.count)(*[inf[0] for inf in oinfos])
+        self.timestamps = None if timestamps is None else (C.c_uint64 * self.count)(*[int(t) for t in timestamps])
+        self.results = (_capi.Result * self.count)()
+        self._keep = (frames, outs)
+
+
 def _f32(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a if shape is None else a.reshape(shape)
@@ -252,6 +276,15 @@ class Stream:
         for tk, _ in pending:
             self.wait_output(tk)
         return delivered
+
+    def submit_batch(self, frames, outs, fmt: int = BGR, timestamps=None):
+        """lvkb200_stream_submit_batch: filters `frames` back to back, frame i into outs[i] (buffers of one geometry, all
+        host or all device), announcing frame i+1 before frame i is submitted - one FFI call for the whole sequence.
+        Returns the list of per-step Results.  `frames` / `outs` may be a BatchPlan built once for reused buffers."""
+        plan = frames if isinstance(frames, BatchPlan) else BatchPlan(frames, outs, timestamps)
+        _capi.check(self._lib.lvkb200_stream_submit_batch(self._h, plan.frames, plan.pitch, plan.w, plan.h, fmt, plan.timestamps,
+                                                          plan.space, plan.outs, plan.opitch, plan.ospace, plan.count, plan.results))
+        return plan.results
 
     def prefetch(self, frame, fmt: "int | None" = None):
         """Announces the NEXT frame (call it before submitting the current one).  Without `fmt`: starts the upload of

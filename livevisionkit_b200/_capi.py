@@ -100,6 +100,8 @@ SYMBOLS = {
     "lvkb200_stream_submit_async": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, C.c_uint64, _i, _vp, _sz, _i, C.POINTER(Result),
                                               C.POINTER(C.c_uint64)]),
     "lvkb200_stream_wait_output": (C.c_int, [_vp, C.c_uint64]),
+    "lvkb200_stream_submit_batch": (C.c_int, [_vp, C.POINTER(_vp), _sz, _i, _i, _i, C.POINTER(C.c_uint64), _i, C.POINTER(_vp), _sz, _i, _i,
+                                              C.POINTER(Result)]),
     "lvkb200_device_synchronize": (C.c_int, []),
     "lvkb200_stream_event_record": (C.c_int, [_vp, _i]),
     "lvkb200_stream_event_elapsed_ms": (C.c_int, [_vp, _i, _i, _fp]),

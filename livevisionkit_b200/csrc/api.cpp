@@ -301,6 +301,27 @@ lvkb200_status lvkb200_stream_submit_async(lvkb200_stream* s, const void* frame,
     return st;
 }
 
+lvkb200_status lvkb200_stream_submit_batch(lvkb200_stream* s, const void* const* frames, size_t pitch, int width, int height,
+                                           lvkb200_format format, const uint64_t* timestamps, lvkb200_memspace frame_space,
+                                           void* const* outs, size_t out_pitch, lvkb200_memspace out_space, int count,
+                                           lvkb200_result* results)
+{
+    LVKB_REQUIRE(s != nullptr && frames != nullptr && outs != nullptr && results != nullptr && count >= 0);
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const bool announce = format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV;
+    for (int i = 0; i < count; i++)
+    {
+        LVKB_REQUIRE(frames[i] != nullptr);
+        // frame i+1 is announced before frame i is submitted: its copy into the ring, detection image and pyramid are
+        // queued behind frame i's tracking chain (the input thread of VideoFilter::stream running one frame ahead)
+        if (announce && i + 1 < count && frames[i + 1] != nullptr)
+            LVKB_TRY(s->prefetch(frames[i + 1], pitch, width, height, format, frame_space));
+        LVKB_TRY(s->submit(frames[i], pitch, width, height, format, timestamps ? timestamps[i] : static_cast<uint64_t>(i),
+                           frame_space, outs[i], out_pitch, out_space, &results[i]));
+    }
+    return LVKB200_OK;
+}
+
 lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket)
 {
     LVKB_REQUIRE(s != nullptr);

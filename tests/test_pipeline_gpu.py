@@ -286,3 +286,29 @@ def test_configure_preconditions(oracle):
     with pytest.raises(L.LvkB200Error) as e:
         L.StabilizationFilter(s, 0)
     assert e.value.status == 1
+
+
+def test_submit_batch_equals_per_frame_submit():
+    """lvkb200_stream_submit_batch (one FFI call for a whole sequence, frame i+1 announced before frame i) produces exactly
+    the outputs, cadence and timestamps of per-frame lvkb200_stream_submit."""
+    torch = pytest.importorskip("torch")
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    clip = Clip((1280, 720), "shake", frames=26)
+    frames = [torch.from_numpy(clip[i]).cuda() for i in range(26)]
+    settings = L.StabilizationFilterSettings.obs_homography_preset()
+    a, b = L.Stream(settings, 0), L.Stream(settings, 0)
+    outs_a = [torch.zeros_like(frames[0]) for _ in range(26)]
+    outs_b = [torch.zeros_like(frames[0]) for _ in range(26)]
+    res_a = [a.submit(frames[i], outs_a[i], L.BGR, 100 + i) for i in range(26)]
+    a.sync()
+    res_b = list(b.submit_batch(frames[:9], outs_b[:9], L.BGR, [100 + i for i in range(9)]))
+    res_b += list(b.submit_batch(frames[9:], outs_b[9:], L.BGR, [100 + i for i in range(9, 26)]))
+    b.sync()
+    assert sum(r.has_output for r in res_a) == 16
+    for i in range(26):
+        assert res_a[i].has_output == res_b[i].has_output and res_a[i].out_timestamp == res_b[i].out_timestamp
+        assert abs(res_a[i].trust_factor - res_b[i].trust_factor) == 0.0
+        assert torch.equal(outs_a[i], outs_b[i]), f"frame {i}: batch output differs"
+    a.close()
+    b.close()
