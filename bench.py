@@ -315,7 +315,8 @@ def _stats(xs):
     return {"min": xs[0], "median": float(np.median(xs)), "max": xs[-1]}
 
 
-def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_pass=True, stage_pass=True, sampler=None):
+def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_pass=True, stage_pass=True, sampler=None,
+                nv12_pass=False):
     """Runs `windows` timed windows of `steps` steps each for the device-resident pass and for the pipelined host pass
     on this rank's GPU.  Returns the per-window times (ms) and the side measurements; no cross-rank reduction here."""
     import torch
@@ -442,8 +443,43 @@ def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_
     parity_fail += int(not np.array_equal(pinned_out[(K - 1) % 3].numpy(), last_dev_out))
     parity_fail += int(delivered != R * K)
     flt3.stream.close()
+
+    # ======== pass 4: the same, frames crossing PCIe as NV12 (the OBS plugin's own layout, FrameIngest) ========
+    # lvkb200_stream_prefetch_obs / _submit_obs_async: 1.5 B/px in each direction instead of 3; the plane <-> packed
+    # conversions (to_ocl / to_obs) run on the copy streams.  Same clip, converted to NV12 on the host beforehand.
+    nv12_ms = None
+    if nv12_pass:
+        import cv2
+        h, w = wl.height, wl.width
+        nv = torch.empty((n_frames + 3, h * 3 // 2, w), dtype=torch.uint8).pin_memory()
+        for i in range(n_frames):
+            i420 = cv2.cvtColor(pinned_in[i].numpy(), cv2.COLOR_BGR2YUV_I420)
+            dst = nv[i].numpy()
+            dst[:h] = i420[:h]
+            uv = dst[h:].reshape(h // 2, w // 2, 2)
+            uv[:, :, 0] = i420[h:h + h // 4].reshape(h // 2, w // 2)
+            uv[:, :, 1] = i420[h + h // 4:].reshape(h // 2, w // 2)
+
+        def obs(t, ts):
+            a = t.numpy()
+            return L.ObsFrame("NV12", w, h, [a[:h], a[h:]], timestamp=ts)
+
+        srcs = [obs(nv[i], i) for i in range(n_frames)]
+        outs = [obs(nv[n_frames + i], 0) for i in range(3)]
+        flt4 = wl.make_filter(L, local)
+        flt4.stream.stream_obs(srcs[:warmup], lambda o: False, outs)
+        nv12_ms, got = [], 0
+        for wi in range(R):
+            barrier()
+            tp = time.perf_counter()
+            got += flt4.stream.stream_obs(srcs[warmup + wi * K: warmup + (wi + 1) * K], lambda o: False, outs)
+            flt4.stream.sync()
+            nv12_ms.append(1e3 * (time.perf_counter() - tp))
+        parity_fail += int(got != R * K)
+        flt4.stream.close()
+        del nv, srcs, outs
     del pinned, pinned_in, pinned_out
-    return {"dev_ms": dev_ms, "e2e_ms": e2e_ms, "wall_ms": wall_ms, "launches": launches, "outputs": outputs,
+    return {"dev_ms": dev_ms, "e2e_ms": e2e_ms, "nv12_ms": nv12_ms, "wall_ms": wall_ms, "launches": launches, "outputs": outputs,
             "parity_fail": parity_fail, "apply_fps": apply_fps, "stage_us": stage_us, "n_frames": n_frames,
             "remap_us": totals["remap"] / max(counts["remap"], 1), "clip": clip}
 
@@ -530,15 +566,17 @@ def main():
     K = args.steps
     R = args.windows if args.windows > 0 else default_windows(K)
     sampler = ClockSampler(local)
-    m = measure_gpu(wl, K, args.warmup, R, local, world, lookahead=not args.no_lookahead, sampler=sampler)
+    m = measure_gpu(wl, K, args.warmup, R, local, world, lookahead=not args.no_lookahead, sampler=sampler,
+                    nv12_pass=not args.deblock)
     clocks = sampler.stop()
 
     # ======== reduce over ranks: ONE all_gather of the per-rank counter struct (NCCL over NVLink) ========
     from tools import scaling
     d, e = _stats(m["dev_ms"]), _stats(m["e2e_ms"])
+    nv = _stats(m["nv12_ms"]) if m["nv12_ms"] else {"min": 0.0, "median": 0.0, "max": 0.0}
     mine = torch.tensor([float(K), d["median"], e["median"], float(m["launches"]) / R, float(m["parity_fail"]),
                          float(np.median(m["wall_ms"])), e["median"], float(m["outputs"]) / R,
-                         d["min"], d["max"], e["min"], e["max"]], dtype=torch.float64, device=dev)
+                         d["min"], d["max"], e["min"], e["max"], nv["median"]], dtype=torch.float64, device=dev)
     agg = scaling.aggregate(scaling.gather_counters(mine))
     if rank == 0:
         t_dev, t_e2e = agg["dev_ms"], agg["e2e_ms"]
@@ -563,6 +601,13 @@ def main():
                            "downloads overlapped with the neighbouring frames' processing",
                     "apply_fps_rank0": m["apply_fps"],
                     "apply_note": "same, through the synchronous per-frame StabilizationFilter.apply (no overlap)"},
+            "e2e_nv12": None if not agg.get("nv12_ms") else {
+                "value": agg["frames"] / (agg["nv12_ms"] * 1e-3), "unit": "frames/s", "ms_per_step": agg["nv12_ms"] / K,
+                "h2d_bytes_per_step": wl.frame_bytes() // 2, "d2h_bytes_per_step": wl.frame_bytes() // 2,
+                "per_rank_fps": agg.get("nv12_fps_per_rank"),
+                "api": "Stream.stream_obs — lvkb200_stream_prefetch_obs / _submit_obs_async: the same clip as NV12 planes in "
+                       "pinned host memory (the OBS plugin's native layout, FrameIngest.cpp:566-604); plane upload + to_ocl on "
+                       "the copy-in stream, to_obs + plane download on the copy-out stream; max over ranks of the median window"},
             "per_rank": agg.get("per_rank"),
             "gpu_launches": agg["launches"],
             "roofline": hbm,

@@ -324,6 +324,23 @@ lvkb200_status lvkb200_frame_download(lvkb200_stream* s, const void* src, size_t
 lvkb200_status lvkb200_stream_submit_obs(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_memspace in_space,
                                          lvkb200_obs_frame* out, lvkb200_memspace out_space, lvkb200_result* res);
 
+/* The pipelined form of lvkb200_stream_submit_obs for HOST frames (ideally pinned) in a planar / semi-planar / packed YUV
+ * layout - the OBS analogue of lvkb200_stream_prefetch_frame + lvkb200_stream_submit_async:
+ *   lvkb200_stream_prefetch_obs(next)        uploads the planes of the NEXT frame and converts them to the packed frame
+ *                                            (FrameIngest to_ocl) on the copy-in stream while the current frame is
+ *                                            tracked; its detection image and pyramid are built behind the current
+ *                                            frame's tracking chain.  The planes must stay unmodified until the submit
+ *                                            of that frame returns.
+ *   lvkb200_stream_submit_obs_async(in, out) filters `in` (announced or not); the stabilized frame is converted back to
+ *                                            the planes of `out` (to_obs) and downloaded on the copy-out stream after
+ *                                            the call returns; *ticket (0: no output) identifies it for
+ *                                            lvkb200_stream_wait_output.  `out` must stay valid until then.
+ * Same pixels as lvkb200_stream_submit_obs; 1.5 B/px (4:2:0) cross PCIe in each direction and no copy or conversion
+ * sits on the frame's critical path.  Keep two outputs in flight as with lvkb200_stream_submit_async. */
+lvkb200_status lvkb200_stream_prefetch_obs(lvkb200_stream* s, const lvkb200_obs_frame* in);
+lvkb200_status lvkb200_stream_submit_obs_async(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_obs_frame* out,
+                                               lvkb200_result* res, uint64_t* ticket);
+
 /* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
  * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for
  * the later one.  The per-stage analogue of Stopwatch (Timing/Stopwatch.cpp:42-64) for the bench harness. */

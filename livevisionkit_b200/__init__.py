@@ -471,6 +471,60 @@ class Stream:
             out.timestamp = cout.timestamp
         return res
 
+    def prefetch_obs(self, frame: "ObsFrame"):
+        """Announces the NEXT OBS-layout frame (host planes): upload + to_ocl conversion on the copy-in stream."""
+        cin, space = frame.c_cached()
+        if space != _capi.MEM_HOST:
+            raise ValueError("prefetch_obs takes host planes")
+        _capi.check(self._lib.lvkb200_stream_prefetch_obs(self._h, C.byref(cin)))
+
+    def submit_obs_async(self, frame: "ObsFrame", out: "ObsFrame"):
+        """-> (Result, ticket): lvkb200_stream_submit_obs_async; the planes of `out` are filled after the call
+        (wait_output(ticket))."""
+        cin, space = frame.c_cached()
+        cout, ospace = out.c_cached()
+        if space != _capi.MEM_HOST or ospace != _capi.MEM_HOST:
+            raise ValueError("submit_obs_async takes host planes")
+        res = _capi.Result()
+        ticket = C.c_uint64(0)
+        _capi.check(self._lib.lvkb200_stream_submit_obs_async(self._h, C.byref(cin), C.byref(cout), C.byref(res), C.byref(ticket)))
+        if res.has_output:
+            out.timestamp = int(res.out_timestamp)
+        return res, int(ticket.value)
+
+    def stream_obs(self, frames, callback, outputs) -> int:
+        """Pipelined VSFilter::filter over a sequence of host OBS-layout frames (the NV12 / I420 analogue of
+        `Stream.__call__`): frame t+1 is uploaded and converted while frame t is tracked, output t-1 is converted back and
+        downloaded meanwhile; two outputs stay in flight.  `outputs`: >= 3 reusable ObsFrame buffers.  Returns the number
+        of outputs delivered to `callback(ObsFrame) -> bool` (a true return stops the stream)."""
+        frames = list(frames)
+        if len(outputs) < 3:
+            raise ValueError("stream_obs() needs at least 3 output frames")
+        pending, delivered = [], 0
+        for i, f in enumerate(frames):
+            if i + 1 < len(frames):
+                self.prefetch_obs(frames[i + 1])
+            out = outputs[i % len(outputs)]
+            res, ticket = self.submit_obs_async(f, out)
+            if res.has_output:
+                pending.append((ticket, out))
+            while len(pending) > 2:
+                tk, o = pending.pop(0)
+                self.wait_output(tk)
+                delivered += 1
+                if callback(o):
+                    for tk2, _ in pending:
+                        self.wait_output(tk2)
+                    return delivered
+        for tk, o in pending:
+            self.wait_output(tk)
+            delivered += 1
+            if callback(o):
+                break
+        for tk, _ in pending:
+            self.wait_output(tk)
+        return delivered
+
     # ---- lvk::DeblockingFilter
     def deblock(self, frame, settings: "DeblockingFilterSettings | None" = None, fmt: int = BGR, out=None):
         """DeblockingFilter::filter on one frame (host or device); `out` defaults to a new buffer, may be `frame`."""
@@ -565,6 +619,15 @@ class ObsFrame:
     height: int
     planes: list
     timestamp: int = 0
+
+    def c_cached(self):
+        """to_c() once per frame object (the plane buffers of a reused frame do not move)."""
+        cached = self.__dict__.get("_c")
+        if cached is None:
+            cached = self.to_c()
+            self.__dict__["_c"] = cached
+        cached[0].timestamp = int(self.timestamp)
+        return cached
 
     def to_c(self):
         c = _capi.ObsFrame()

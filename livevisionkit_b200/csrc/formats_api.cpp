@@ -282,4 +282,132 @@ lvkb200_status lvkb200_stream_submit_obs(lvkb200_stream* s, const lvkb200_obs_fr
     return LVKB200_OK;
 }
 
+// ---- pipelined OBS-layout path -----------------------------------------------------------------------------------------
+// VideoFilter::stream for asynchronous OBS sources: the planes of frame t+1 are uploaded and converted (to_ocl) on the
+// copy-in stream while frame t is tracked, and the stabilized frame t-1 is converted back (to_obs) and downloaded on the
+// copy-out stream: 1.5 B/px (4:2:0) cross PCIe in each direction instead of 3, and none of it sits on the frame's
+// critical path.  Results are identical to lvkb200_stream_submit_obs.
+
+lvkb200_status lvkb200_stream_prefetch_obs(lvkb200_stream* s, const lvkb200_obs_frame* in)
+{
+    LVKB_REQUIRE(s != nullptr && in != nullptr);
+    Layout l;
+    LVKB_REQUIRE(describe(in->format, l));
+    LVKB_REQUIRE(l.kind != Kind::Direct && l.ocl != LVKB200_GRAY);  // planar / semi-planar / packed YUV layouts
+    const int w = (int)in->width, h = (int)in->height;
+    const PlaneGeometry g = geometry(l, w, h);
+    LVKB_TRY(check_frame(in, l, g));
+    LVKB_CUDA(cudaSetDevice(s->device));
+    const size_t row = (size_t)w * 3, fpitch = align16(row);
+    LVKB_TRY(s->ensure_pipeline());
+    LVKB_TRY(s->ensure_frame_pool(fpitch * h));
+    // a slot that still holds an announced, not yet submitted frame is never overwritten while the other one is free
+    // (submit_obs_async of an unannounced frame comes BETWEEN the announcement of frame t+1 and its submit)
+    int k = s->prefetch_next;
+    if (s->prefetched_ptr[k] != nullptr && s->prefetched_ptr[k ^ 1] == nullptr) k ^= 1;
+    s->prefetch_next = k ^ 1;
+    lvkb200_stream::QueuedFrame& ps = s->prefetch_slot[k];
+    ps.pitch = fpitch;
+    ps.w = w;
+    ps.h = h;
+    if (ps.buf.capacity < fpitch * h)
+    {
+        LVKB_TRY(s->sync_all());  // the buffer being replaced may still be read by a queued remap
+        LVKB_CUDA(ps.buf.ensure(fpitch * h));
+    }
+    LVKB_TRY(s->wait_frame_buffers_free(s->cs_in));
+    uint8_t* p[3] = {nullptr, nullptr, nullptr};
+    size_t pitch[3] = {0, 0, 0}, off[3] = {0, 0, 0}, total = 0;
+    for (int i = 0; i < g.planes; i++)
+    {
+        pitch[i] = align16(g.row_bytes[i]);
+        off[i] = total;
+        total += pitch[i] * g.rows[i];
+    }
+    // staging of this slot's PREVIOUS frame was consumed by a kernel queued earlier on the same (in-order) stream
+    if (s->planes_in_async[k].capacity < total)
+    {
+        LVKB_CUDA(cudaStreamSynchronize(s->cs_in));
+        LVKB_CUDA(s->planes_in_async[k].ensure(total));
+    }
+    for (int i = 0; i < g.planes; i++)
+    {
+        p[i] = s->planes_in_async[k].template as<uint8_t>() + off[i];
+        const size_t sp = in->linesize[i] ? in->linesize[i] : g.row_bytes[i];
+        LVKB_CUDA(cudaMemcpy2DAsync(p[i], pitch[i], in->data[i], sp, g.row_bytes[i], g.rows[i], cudaMemcpyHostToDevice, s->cs_in));
+    }
+    PlaneRef Y, U, V, A;
+    components(l, p, pitch, Y, U, V, A);
+    LVKB_CUDA(s->format_plan_in.prepare(w, h, w / l.sub_x, h / l.sub_y, s->cs_in));
+    LVKB_CUDA(launch_planes_to_packed(s->cs_in, s->format_plan_in, Y, U, V, ps.buf.template as<uint8_t>(), ps.pitch));
+    LVKB_CUDA(cudaEventRecord(s->prefetch_done[k], s->cs_in));
+    s->prefetched_ptr[k] = in->data[0];
+    s->lookahead[k] = lvkb200_stream::Lookahead{};
+    s->lookahead[k].announced = true;
+    s->lookahead[k].format = l.ocl;
+    return LVKB200_OK;
+}
+
+lvkb200_status lvkb200_stream_submit_obs_async(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_obs_frame* out,
+                                               lvkb200_result* res, uint64_t* ticket)
+{
+    LVKB_REQUIRE(s != nullptr && in != nullptr && out != nullptr && res != nullptr && ticket != nullptr);
+    Layout l;
+    LVKB_REQUIRE(describe(in->format, l));
+    LVKB_REQUIRE(l.kind != Kind::Direct && l.ocl != LVKB200_GRAY);
+    LVKB_REQUIRE(out->format == in->format && out->width == in->width && out->height == in->height);
+    LVKB_REQUIRE(s->settings.stabilize_output);  // the pass-through configuration uses lvkb200_stream_submit_obs
+    const int w = (int)in->width, h = (int)in->height;
+    LVKB_TRY(check_frame(out, l, geometry(l, w, h)));
+    LVKB_CUDA(cudaSetDevice(s->device));
+    bool announced = false;
+    for (int k = 0; k < 2; k++) announced |= (s->prefetched_ptr[k] == in->data[0]);
+    if (!announced) LVKB_TRY(lvkb200_stream_prefetch_obs(s, in));
+    s->deferred_output = true;
+    s->next_egress = true;
+    s->next_egress_frame = *out;
+    s->last_ticket = 0;
+    // the key of the announced frame is its first plane; the packed frame already sits in the prefetch slot
+    const lvkb200_status st = s->submit(in->data[0], align16((size_t)w * 3), w, h, l.ocl, in->timestamp, LVKB200_MEM_HOST,
+                                        out->data[0], align16((size_t)w * 3), LVKB200_MEM_HOST, res);
+    s->deferred_output = false;
+    s->next_egress = false;
+    *ticket = (st == LVKB200_OK && res->has_output) ? s->last_ticket : 0;
+    if (st == LVKB200_OK && res->has_output) out->timestamp = res->out_timestamp;
+    return st;
+}
+
 }  // extern "C"
+
+lvkb200_status lvkb200_stream::egress_planes(cudaStream_t stream, const uint8_t* packed, size_t pitch, int width, int height,
+                                             lvkb200_format format, const lvkb200_obs_frame& dst, int slot)
+{
+    using namespace lvkb200;
+    Layout l;
+    LVKB_REQUIRE(describe(dst.format, l) && format == l.ocl);
+    const PlaneGeometry g = geometry(l, width, height);
+    uint8_t* p[3] = {nullptr, nullptr, nullptr};
+    size_t pp[3] = {0, 0, 0}, off[3] = {0, 0, 0}, total = 0;
+    for (int i = 0; i < g.planes; i++)
+    {
+        pp[i] = align16(g.row_bytes[i]);
+        off[i] = total;
+        total += pp[i] * g.rows[i];
+    }
+    if (planes_out_async[slot].capacity < total)
+    {
+        LVKB_CUDA(cudaStreamSynchronize(stream));
+        LVKB_CUDA(planes_out_async[slot].ensure(total));
+    }
+    for (int i = 0; i < g.planes; i++) p[i] = planes_out_async[slot].as<uint8_t>() + off[i];
+    PlaneRef Y, U, V, A;
+    components(l, p, pp, Y, U, V, A);
+    LVKB_CUDA(launch_packed_to_planes(stream, packed, pitch, width, height, l.sub_x, l.sub_y, Y, U, V,
+                                      l.kind == Kind::Packed444 ? &A : nullptr, l.kind == Kind::SemiPlanar));
+    for (int i = 0; i < g.planes; i++)
+    {
+        const size_t hp = dst.linesize[i] ? dst.linesize[i] : g.row_bytes[i];
+        LVKB_CUDA(cudaMemcpy2DAsync(dst.data[i], hp, p[i], pp[i], g.row_bytes[i], g.rows[i], cudaMemcpyDeviceToHost, stream));
+    }
+    return LVKB200_OK;
+}

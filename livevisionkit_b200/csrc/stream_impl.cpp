@@ -823,6 +823,8 @@ lvkb200_status lvkb200_stream::apply_mesh(QueuedFrame& src, const Mesh& offsets,
     p.yuv = src.format == LVKB200_YUV;  // Image.cpp:100
     for (int k = 0; k < 3; k++) p.bg[k] = static_cast<uint8_t>(settings.background_colour[k]);  // Image.cpp:136-141
     pr.async_host_out = deferred_output && out_space == LVKB200_MEM_HOST;
+    pr.egress = pr.async_host_out && next_egress;
+    if (pr.egress) pr.egress_frame = next_egress_frame;
     pr.slot = 0;
     pr.out = out;
     pr.out_pitch = out_pitch;
@@ -896,8 +898,12 @@ lvkb200_status lvkb200_stream::flush_remap()
     {
         LVKB_CUDA(cudaEventRecord(async_remap_done[pr.slot], cs_remap));
         LVKB_CUDA(cudaStreamWaitEvent(cs_out, async_remap_done[pr.slot], 0));
-        LVKB_CUDA(cudaMemcpy2DAsync(pr.out, pr.out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(p.width) * 3, p.height,
-                                    cudaMemcpyDeviceToHost, cs_out));
+        if (pr.egress)
+            LVKB_TRY(egress_planes(cs_out, p.dst, p.dst_pitch, p.width, p.height, p.yuv ? LVKB200_YUV : LVKB200_BGR,
+                                   pr.egress_frame, pr.slot));
+        else
+            LVKB_CUDA(cudaMemcpy2DAsync(pr.out, pr.out_pitch, p.dst, p.dst_pitch, static_cast<size_t>(p.width) * 3, p.height,
+                                        cudaMemcpyDeviceToHost, cs_out));
         LVKB_CUDA(cudaEventRecord(async_out_done[pr.slot], cs_out));
         async_out_used[pr.slot] = true;
     }
@@ -1262,6 +1268,7 @@ void lvkb200_stream::release()
     if (cs_in) cudaStreamSynchronize(cs_in);
     if (cs_out) cudaStreamSynchronize(cs_out);
     for (auto& ps : prefetch_slot) ps.buf.release();
+    for (int k = 0; k < 2; k++) { planes_in_async[k].release(); planes_out_async[k].release(); }
     for (int k = 0; k < 2; k++)
     {
         async_out[k].release();

@@ -48,6 +48,10 @@ struct lvkb200_stream
     // ---- FrameIngest (OBS plane layouts <-> packed frames): chroma tap tables + plane / frame scratch
     lvkb200::FormatPlan format_plan;
     lvkb200::DeviceBuffer planes_in, planes_out, obs_frame_in, obs_frame_out;
+    // pipelined OBS-layout path (lvkb200_stream_prefetch_obs / _submit_obs_async): plane staging per prefetch slot and per
+    // output slot, and the ingest's geometry tables prepared on the copy-in stream
+    lvkb200::DeviceBuffer planes_in_async[2], planes_out_async[2];
+    lvkb200::FormatPlan format_plan_in;
 
     // ---- device-side stages
     lvkb200::IngestPlan ingest;
@@ -169,7 +173,17 @@ struct lvkb200_stream
         void* out = nullptr;
         size_t out_pitch = 0;
         lvkb200_memspace out_space = LVKB200_MEM_DEVICE;
+        // pipelined OBS-layout output: instead of downloading the packed frame, the copy-out stream converts it back to
+        // the planes of `egress_frame` (to_obs) and downloads those
+        bool egress = false;
+        lvkb200_obs_frame egress_frame{};
     } pending;
+    // set by lvkb200_stream_submit_obs_async around submit(): the output of that submit leaves as OBS planes
+    bool next_egress = false;
+    lvkb200_obs_frame next_egress_frame{};
+    // formats_api.cpp: packed device frame -> planes of `dst` (host memory), all on `stream`, staging slot `slot`
+    lvkb200_status egress_planes(cudaStream_t stream, const uint8_t* packed, size_t pitch, int width, int height,
+                                 lvkb200_format format, const lvkb200_obs_frame& dst, int slot);
     lvkb200_status flush_remap();
     // Allocates every still-empty frame buffer of the rotation (ring, prefetch slots, parked buffer) at once.  Lazily,
     // each of the first ~14 frames of a stream paid a cudaMalloc — and, in pipelined operation, a full sync_all in

@@ -118,3 +118,35 @@ def test_submit_obs_matches_packed_submit(I):
                 assert (p == q).all()
     assert outputs == 4
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("fmt", ["NV12", "I420", "UYVY"])
+def test_pipelined_obs_stream_equals_submit_obs(I, fmt):
+    """lvkb200_stream_prefetch_obs / _submit_obs_async (upload + to_ocl on the copy-in stream, to_obs + download on the
+    copy-out stream, two outputs in flight) deliver exactly the planes and timestamps of the synchronous
+    lvkb200_stream_submit_obs, frame for frame."""
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    w, h, n = 1280, 720, 24
+    clip = Clip((w, h), "shake", frames=n)
+    settings = L.StabilizationFilterSettings.obs_homography_preset()
+    a, b = L.Stream(settings, 0), L.Stream(settings, 0)
+    sources = []
+    for i in range(n):
+        planes = I.download_ocl_frame(clip[i], fmt)  # synthetic source in the layout (BGR bytes reinterpreted as YUV)
+        sources.append(L.ObsFrame(fmt, w, h, [np.ascontiguousarray(p).reshape(s) for p, s in zip(planes, I.plane_shapes(fmt, w, h))],
+                                  timestamp=500 + i))
+    want = []
+    for src in sources:
+        dst = L.ObsFrame(fmt, w, h, [np.zeros_like(p) for p in src.planes])
+        if a.submit_obs(src, dst).has_output:
+            want.append((dst.timestamp, [p.copy() for p in dst.planes]))
+    outs = [L.ObsFrame(fmt, w, h, [np.zeros_like(p) for p in sources[0].planes]) for _ in range(3)]
+    got = []
+    delivered = b.stream_obs(sources, lambda o: got.append((o.timestamp, [p.copy() for p in o.planes])) and False, outs)
+    assert delivered == len(want) == n - 10 and len(got) == len(want)
+    for (ts_a, pa), (ts_b, pb) in zip(want, got):
+        assert ts_a == ts_b
+        for p, q in zip(pa, pb):
+            assert (p == q).all(), f"{fmt}: pipelined planes differ at timestamp {ts_a}"
+    a.close(); b.close()

@@ -11,6 +11,7 @@ import torch.distributed as dist
 FRAMES, DEV_MS, E2E_MS, LAUNCHES, PARITY_FAIL, WALL_MS, WALL_E2E_MS, OUTPUTS = range(8)
 N_COUNTERS = 8
 DEV_MIN, DEV_MAX, E2E_MIN, E2E_MAX = range(8, 12)
+NV12_MS = 12  # optional: median window of the NV12 end-to-end pass
 
 
 def stream_seed(rank: int) -> int:
@@ -49,7 +50,12 @@ def aggregate(allc: torch.Tensor) -> dict:
             "sum_of_rank_e2e_fps": float(sum(f / (t * 1e-3) for f, t in zip(frames_r, a[:, E2E_MS]) if t > 0)),
             "sum_of_rank_value_fps": float(sum(f / (t * 1e-3) for f, t in zip(frames_r, a[:, DEV_MS]) if t > 0)),
         }
+    nv12_ms, nv12_fps = None, None
+    if a.shape[1] > NV12_MS and float(a[:, NV12_MS].max()) > 0:
+        nv12_ms = float(a[:, NV12_MS].max())
+        nv12_fps = [float(f / (t * 1e-3)) if t > 0 else 0.0 for f, t in zip(a[:, FRAMES], a[:, NV12_MS])]
     return {
+        "nv12_ms": nv12_ms, "nv12_fps_per_rank": nv12_fps,
         "per_rank": per_rank,
         "frames": frames,
         "value_fps": frames / (t_dev * 1e-3) if t_dev > 0 else 0.0,
