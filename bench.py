@@ -578,8 +578,18 @@ def main():
                          float(np.median(m["wall_ms"])), e["median"], float(m["outputs"]) / R,
                          d["min"], d["max"], e["min"], e["max"], nv["median"]], dtype=torch.float64, device=dev)
     agg = scaling.aggregate(scaling.gather_counters(mine))
+    # copy-only ceiling of THIS box with all ranks copying at once (tools/pcie_ceiling.py): what bounds `e2e` at N > 1
+    ceiling = None
+    try:
+        from tools import pcie_ceiling as PC
+        rows = PC.gather(PC.probe(local, world, wl.frame_bytes(), copies=40, dist=dist if world > 1 else None), local, world, dist)
+        ceiling = PC.summarise(rows, wl.frame_bytes())
+    except Exception as ex:
+        ceiling = {"failed": repr(ex)}
     if rank == 0:
         t_dev, t_e2e = agg["dev_ms"], agg["e2e_ms"]
+        if ceiling and "ceiling_fps_whole_job" in ceiling and agg.get("per_rank"):
+            ceiling["e2e_sum_of_ranks_over_ceiling"] = agg["per_rank"]["sum_of_rank_e2e_fps"] / ceiling["ceiling_fps_whole_job"]
         hbm, issue = rooflines(wl, m["remap_us"], clocks.get("sm_mhz"))
         line = {
             "metric": wl.metric, "value": agg["value_fps"], "unit": "frames/s", "n_gpus": world,
@@ -609,6 +619,7 @@ def main():
                        "pinned host memory (the OBS plugin's native layout, FrameIngest.cpp:566-604); plane upload + to_ocl on "
                        "the copy-in stream, to_obs + plane download on the copy-out stream; max over ranks of the median window"},
             "per_rank": agg.get("per_rank"),
+            "pcie_ceiling": ceiling,
             "gpu_launches": agg["launches"],
             "roofline": hbm,
             "roofline_issue": issue,
