@@ -508,8 +508,8 @@ lvkb200_status lvkb200_lk_track(lvkb200_stream* s, const uint8_t* prev, const ui
     size_t pitch = 0;
     lvkb200_status st = upload_gray(s, prev, width, height, dprev, &pitch);
     if (st == LVKB200_OK) st = upload_gray(s, next, width, height, dnext, &pitch);
-    if (st == LVKB200_OK) st = pp.prepare(width, height);
-    if (st == LVKB200_OK) st = pn.prepare(width, height);
+    if (st == LVKB200_OK) st = pp.prepare(width, height, s->cs);
+    if (st == LVKB200_OK) st = pn.prepare(width, height, s->cs);
     if (st == LVKB200_OK) st = pp.build(s->cs, dprev.as<uint8_t>(), pitch);
     if (st == LVKB200_OK) st = pn.build(s->cs, dnext.as<uint8_t>(), pitch);
     auto cuda_ok = [&](cudaError_t e) { if (e != cudaSuccess && st == LVKB200_OK) { set_error("lk_track: %s", cudaGetErrorString(e)); st = LVKB200_ERR_CUDA; } };

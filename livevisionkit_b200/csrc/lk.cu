@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(128)
 
 }  // namespace
 
-lvkb200_status LkPyramid::prepare(int width, int height)
+lvkb200_status LkPyramid::prepare(int width, int height, cudaStream_t cs)
 {
     if (width == w[0] && height == h[0] && levels > 0) return LVKB200_OK;
     // buildOpticalFlowPyramid stops when a level is not larger than the window
@@ -573,11 +573,12 @@ lvkb200_status LkPyramid::prepare(int width, int height)
         LVKB_CUDA(img[l].ensure(img_bytes));
         LVKB_CUDA(deriv[l].ensure(deriv_bytes));
         // the derivative planes' border is zero (BORDER_CONSTANT) and only the tile builder's interior is rewritten
-        LVKB_CUDA(cudaMemset(img[l].ptr, 0, img_bytes));
-        LVKB_CUDA(cudaMemset(deriv[l].ptr, 0, deriv_bytes));
+        LVKB_CUDA(cudaMemsetAsync(img[l].ptr, 0, img_bytes, cs));
+        LVKB_CUDA(cudaMemsetAsync(deriv[l].ptr, 0, deriv_bytes, cs));
         levels++;
     }
-    LVKB_CUDA(cudaDeviceSynchronize());  // the memsets ran on the legacy stream: order them before any stream's kernels
+    // the memsets are ordered on the stream that builds and reads this pyramid (no legacy-stream work, no device-wide
+    // synchronisation: another host thread may be capturing its own stream's graph at this moment)
     valid = false;
     return LVKB200_OK;
 }

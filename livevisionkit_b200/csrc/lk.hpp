@@ -19,7 +19,7 @@ struct LkPyramid
     size_t img_pitch[LK_MAX_LEVELS] = {}, deriv_pitch[LK_MAX_LEVELS] = {};
     DeviceBuffer img[LK_MAX_LEVELS], deriv[LK_MAX_LEVELS];
 
-    lvkb200_status prepare(int width, int height);
+    lvkb200_status prepare(int width, int height, cudaStream_t cs);
     // det: device detection image (width x height, det_pitch).  Builds all levels and derivative planes.
     lvkb200_status build(cudaStream_t cs, const uint8_t* det, size_t det_pitch);
     void release();

@@ -622,14 +622,15 @@ bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaSt
     if ((*err = d_out.ensure(out_bytes)) != cudaSuccess) return false;
     if ((*err = h_out.ensure(out_bytes)) != cudaSuccess) return false;
     std::memset(h_out.ptr, 0, out_bytes);
-    // synchronous, pageable source: configure is not on the per-frame path
+    // pageable source, completed before `blob` dies; on the stream's own queue (no legacy-stream work: another host thread
+    // may be capturing its stream's graph right now).  configure is not on the per-frame path.
+    if ((*err = cudaMemcpyAsync(d_static.ptr, blob.data(), bytes, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return false;
     if ((*err = cudaStreamSynchronize(cs)) != cudaSuccess) return false;
-    if ((*err = cudaMemcpy(d_static.ptr, blob.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return false;
     const bool resized = mesh_cols != sys.mesh_cols || mesh_rows != sys.mesh_rows;
     mesh_cols = sys.mesh_cols; mesh_rows = sys.mesh_rows;
     n_sim = S; csc_nnz = nnz; capacity = feature_capacity; smem_bytes = cv.total;
     n_unknowns = n;
-    if (resized && (*err = cudaMemset(d_state.ptr, 0, 4 * (size_t)n)) != cudaSuccess) { n_unknowns = 0; return false; }
+    if (resized && (*err = cudaMemsetAsync(d_state.ptr, 0, 4 * (size_t)n, cs)) != cudaSuccess) { n_unknowns = 0; return false; }
     return true;
 }
 
@@ -641,9 +642,9 @@ cudaError_t MeshCgls::reset_state(cudaStream_t cs)
 
 cudaError_t MeshCgls::set_state(cudaStream_t cs, const float* mesh)
 {
-    cudaError_t e = cudaStreamSynchronize(cs);
+    cudaError_t e = cudaMemcpyAsync(d_state.ptr, mesh, 4 * (size_t)n_unknowns, cudaMemcpyHostToDevice, cs);
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(d_state.ptr, mesh, 4 * (size_t)n_unknowns, cudaMemcpyHostToDevice);
+    return cudaStreamSynchronize(cs);
 }
 
 cudaError_t MeshCgls::launch(cudaStream_t cs, const MeshSolveParams& prm, const float2* d_src, const float2* d_dst,

@@ -621,7 +621,7 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     LVKB_CUDA(d_det.ensure(det_pitch * det_h));
     LVKB_TRY(ingest.prepare(frame.w, frame.h, det_w, det_h, cs));
     LVKB_TRY(fast.prepare(det_w, det_h));
-    for (auto& py : pyr) LVKB_TRY(py.prepare(det_w, det_h));
+    for (auto& py : pyr) LVKB_TRY(py.prepare(det_w, det_h, cs));
 
     // the previous submit may already have built this frame's detection image and pyramid (pre_ingest)
     const bool prebuilt = frame_prebuilt && pyr[cur].valid;

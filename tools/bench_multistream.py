@@ -35,12 +35,19 @@ def main():
         done = [0] * S
 
         def work(k):
+            try:
+                _work(k)
+            except BaseException:
+                start.abort()  # a failed worker must not leave the others (and the main thread) waiting at the barrier
+                raise
+
+        def _work(k):
             s = filters[k].stream
             for i in range(a.warmup):
                 s.prefetch(dev[(i + 1) % len(dev)], L.BGR)
                 s.submit(dev[i % len(dev)], outs[k][i % 4], L.BGR, i)
             s.sync()
-            start.wait()
+            start.wait(timeout=300)
             for i in range(a.warmup, n):
                 s.prefetch(dev[(i + 1) % len(dev)], L.BGR)
                 r = s.submit(dev[i % len(dev)], outs[k][i % 4], L.BGR, i)
@@ -50,10 +57,10 @@ def main():
         threads = [threading.Thread(target=work, args=(k,)) for k in range(S)]
         for t in threads:
             t.start()
-        start.wait()
+        start.wait(timeout=300)
         t0 = time.perf_counter()
         for t in threads:
-            t.join()
+            t.join(timeout=300)
         wall = time.perf_counter() - t0
         print(json.dumps({"streams_on_one_gpu": S, "resolution": a.resolution, "frames_per_stream": a.frames,
                           "aggregate_fps": S * a.frames / wall, "per_stream_fps": a.frames / wall, "outputs": sum(done)}))
