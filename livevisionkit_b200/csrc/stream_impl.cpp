@@ -72,6 +72,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     if (!configured)
     {
         host_trace = std::getenv("LVKB200_HOST_TRACE") != nullptr;
+        if (const char* e = std::getenv("LVKB200_REMAP_OVERLAP")) remap_overlap = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("LVKB200_MESH_DEVICE_MIN")) mesh_device_min_unknowns = std::atoi(e);
     }
     const bool det_changed = !configured || s.detection_resolution_width != settings.detection_resolution_width ||
@@ -698,6 +699,16 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     // FrameTracker.cpp:167-176: homography when the features are well distributed, partial affine otherwise
     const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
     host_tick(HP_DETECT);
+    const bool overlap = remap_overlap >= 0 ? remap_overlap != 0
+                                            : static_cast<long long>(frame.w) * frame.h >= REMAP_OVERLAP_MIN_PIXELS;
+    if (overlap && pending.active && cs_remap)
+    {
+        // everything the held-back remap depends on (its parked source frame was uploaded >= frame_delay submits ago)
+        // precedes this point of cs: the remap may start now, beside this frame's LK + RANSAC
+        if (!pre_chain) LVKB_CUDA(cudaEventCreateWithFlags(&pre_chain, cudaEventDisableTiming));
+        LVKB_CUDA(cudaEventRecord(pre_chain, cs));
+        pre_chain_valid = true;
+    }
     LVKB_TRY(enqueue_tracking(tracked, global, settings.acceptance_threshold, model_kind));
     if (!track_done) LVKB_CUDA(cudaEventCreateWithFlags(&track_done, cudaEventDisableTiming));
     LVKB_CUDA(cudaEventRecord(track_done, cs));
@@ -883,9 +894,17 @@ lvkb200_status lvkb200_stream::flush_remap()
     const RemapParams& p = pr.p;
     if (pr.async_host_out && async_out_used[pr.slot])
         LVKB_CUDA(cudaStreamWaitEvent(cs_remap, async_out_done[pr.slot], 0));  // the staging buffer's last download
-    // everything queued on cs so far (the source frame's upload, the mesh upload) precedes the remap
-    LVKB_CUDA(cudaEventRecord(chain_point, cs));
-    LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
+    if (pre_chain_valid && pr.homography)
+    {
+        LVKB_CUDA(cudaStreamWaitEvent(cs_remap, pre_chain, 0));
+    }
+    else
+    {
+        // everything queued on cs so far (the source frame's upload, the mesh upload) precedes the remap
+        LVKB_CUDA(cudaEventRecord(chain_point, cs));
+        LVKB_CUDA(cudaStreamWaitEvent(cs_remap, chain_point, 0));
+    }
+    pre_chain_valid = false;
     stage_begin(ST_REMAP, cs_remap);
     if (pr.homography)
         LVKB_CUDA(launch_remap_homography(cs_remap, p, pr.tf));
@@ -1293,6 +1312,9 @@ void lvkb200_stream::release()
     pending.active = false;
     if (chain_point) cudaEventDestroy(chain_point);
     chain_point = nullptr;
+    if (pre_chain) cudaEventDestroy(pre_chain);
+    pre_chain = nullptr;
+    pre_chain_valid = false;
     if (cs_in) cudaStreamDestroy(cs_in);
     if (cs_out) cudaStreamDestroy(cs_out);
     if (cs_remap) cudaStreamDestroy(cs_remap);

@@ -157,6 +157,15 @@ struct lvkb200_stream
     cudaEvent_t remap_done[2] = {nullptr, nullptr};  // remap number n records remap_done[n & 1] on cs_remap
     uint64_t remaps_launched = 0;
     cudaEvent_t chain_point = nullptr;  // recorded on cs before a remap is queued: uploads on cs have been issued
+    // recorded on cs BEFORE the frame's tracking chain is enqueued: a held-back remap that waits on it runs BESIDE the
+    // chain instead of behind it.  Measured (tools/gpu_overlap_ab.sh): the remap then owns every register of every SM
+    // and the chain's small kernels wait for its CTAs to retire - at 1080p (remap 39 us < chain 52 us) the step gets
+    // longer (11.2k -> 9.9k fps), at 4K (remap 133 us >> chain) it gets shorter (5.0k -> 5.5k fps).  Hence by frame size;
+    // LVKB200_REMAP_OVERLAP=0/1 forces either order.
+    cudaEvent_t pre_chain = nullptr;
+    bool pre_chain_valid = false;
+    int remap_overlap = -1;  // -1: by frame size (>= REMAP_OVERLAP_MIN_PIXELS)
+    static constexpr long long REMAP_OVERLAP_MIN_PIXELS = 3000000;
     lvkb200::DeviceBuffer spare_buf;
     // A remap whose pixels nobody waits for inside submit (device output, pipelined host output) is held back and
     // launched behind the NEXT frame's LK + RANSAC graph, where the SMs are idle (see apply_mesh / flush_remap).
