@@ -72,7 +72,7 @@ lvkb200_status lvkb200_stream::configure(const lvkb200_settings& s)
     if (!configured)
     {
         host_trace = std::getenv("LVKB200_HOST_TRACE") != nullptr;
-        if (const char* e = std::getenv("LVKB200_REMAP_OVERLAP")) remap_overlap = std::atoi(e) != 0 ? 1 : 0;
+        if (const char* e = std::getenv("LVKB200_REMAP_OVERLAP")) remap_overlap = std::min(std::max(std::atoi(e), 0), 2);
         if (const char* e = std::getenv("LVKB200_MESH_DEVICE_MIN")) mesh_device_min_unknowns = std::atoi(e);
     }
     const bool det_changed = !configured || s.detection_resolution_width != settings.detection_resolution_width ||
@@ -338,6 +338,14 @@ lvkb200_status lvkb200_stream::launch_lk(int parity, bool global, int n, bool wi
     if (with_events) stage_begin(ST_LK);
     LVKB_TRY(lk_track(cs, pyr[(parity + PYR_COUNT - 1) % PYR_COUNT], pyr[parity], (n + 3) / 4 * 4, io,
                       inline_points ? &lk_pack : nullptr));
+    if (overlap_after_lk && pending.active && cs_remap)
+    {
+        // the held-back remap may start once LK has finished: it then runs beside the compaction / scoring / refine
+        // kernels (one or a few CTAs, the machine is idle) but not beside LK (716 warps that want every SM)
+        if (!pre_chain) LVKB_CUDA(cudaEventCreateWithFlags(&pre_chain, cudaEventDisableTiming));
+        LVKB_CUDA(cudaEventRecord(pre_chain, cs));
+        pre_chain_valid = true;
+    }
     if (!global && mesh_on_device())
     {
         // swap-erase compaction -> k_mesh_cgls, which also delivers the LK results
@@ -699,9 +707,11 @@ lvkb200_status lvkb200_stream::track(const QueuedFrame& frame, Mesh& motion, boo
     // FrameTracker.cpp:167-176: homography when the features are well distributed, partial affine otherwise
     const int model_kind = (distribution > HOMOGRAPHY_DISTRIBUTION_THRESHOLD) ? 0 : 1;
     host_tick(HP_DETECT);
-    const bool overlap = remap_overlap >= 0 ? remap_overlap != 0
-                                            : static_cast<long long>(frame.w) * frame.h >= REMAP_OVERLAP_MIN_PIXELS;
-    if (overlap && pending.active && cs_remap)
+    // 0: behind the chain, 1: beside the whole chain, 2: beside everything after LK
+    const int overlap = remap_overlap >= 0 ? remap_overlap
+                                           : (static_cast<long long>(frame.w) * frame.h >= REMAP_OVERLAP_MIN_PIXELS ? 1 : 0);
+    overlap_after_lk = overlap == 2;
+    if (overlap == 1 && pending.active && cs_remap)
     {
         // everything the held-back remap depends on (its parked source frame was uploaded >= frame_delay submits ago)
         // precedes this point of cs: the remap may start now, beside this frame's LK + RANSAC

@@ -163,7 +163,7 @@ struct lvkb200_stream
     // longer (11.2k -> 9.9k fps), at 4K (remap 133 us >> chain) it gets shorter (5.0k -> 5.5k fps).  Hence by frame size;
     // LVKB200_REMAP_OVERLAP=0/1 forces either order.
     cudaEvent_t pre_chain = nullptr;
-    bool pre_chain_valid = false;
+    bool pre_chain_valid = false, overlap_after_lk = false;
     int remap_overlap = -1;  // -1: by frame size (>= REMAP_OVERLAP_MIN_PIXELS)
     static constexpr long long REMAP_OVERLAP_MIN_PIXELS = 3000000;
     lvkb200::DeviceBuffer spare_buf;
