@@ -429,18 +429,22 @@ def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_
     # synchronised start to its own stream synchronisation (no barrier, no collective inside).
     flt3 = wl.make_filter(L, local)
     pin_refs = [L.FrameRef(t) for t in pinned_in]
-    pout_refs = [L.FrameRef(t) for t in pinned_out[:3]]
-    flt3.stream([L.VideoFrame(pin_refs[i], i, L.BGR) for i in range(warmup)], lambda vf: False, pout_refs)
+    pout_refs = [L.FrameRef(t) for t in pinned_out]
+    flt3.stream([L.VideoFrame(pin_refs[i], i, L.BGR) for i in range(warmup)], lambda vf: False, pout_refs[:3])
     e2e_ms, delivered = [], 0
-    sink = []
+    # lvkb200_stream_submit_batch with HOST frames and HOST outputs = the pipelined path in one FFI call per window (frame
+    # i+1 uploading, output i-1 downloading while frame i is filtered; every output has landed when it returns); the
+    # outputs cycle through four pinned buffers
+    e2e_plans = [L.BatchPlan([pin_refs[i] for i in range(warmup + w * K, warmup + (w + 1) * K)],
+                             [pout_refs[j % 4] for j in range(K)], list(range(warmup + w * K, warmup + (w + 1) * K)))
+                 for w in range(R)]
     for w in range(R):
-        timed = [L.VideoFrame(pin_refs[i], i, L.BGR) for i in range(warmup + w * K, warmup + (w + 1) * K)]
         barrier()
         tp = time.perf_counter()
-        delivered += flt3.stream(timed, lambda vf: sink.append(vf.timestamp), pout_refs)
+        delivered += sum(r.has_output for r in flt3.stream.submit_batch(e2e_plans[w], None, L.BGR))
         flt3.stream.sync()
         e2e_ms.append(1e3 * (time.perf_counter() - tp))
-    parity_fail += int(not np.array_equal(pinned_out[(K - 1) % 3].numpy(), last_dev_out))
+    parity_fail += int(not np.array_equal(pinned_out[(K - 1) % 4].numpy(), last_dev_out))
     parity_fail += int(delivered != R * K)
     flt3.stream.close()
 
@@ -451,7 +455,7 @@ def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_
     if nv12_pass:
         import cv2
         h, w = wl.height, wl.width
-        nv = torch.empty((n_frames + 3, h * 3 // 2, w), dtype=torch.uint8).pin_memory()
+        nv = torch.empty((n_frames + 4, h * 3 // 2, w), dtype=torch.uint8).pin_memory()
         for i in range(n_frames):
             i420 = cv2.cvtColor(pinned_in[i].numpy(), cv2.COLOR_BGR2YUV_I420)
             dst = nv[i].numpy()
@@ -465,14 +469,16 @@ def measure_gpu(wl, steps, warmup, windows, local, world, lookahead=True, apply_
             return L.ObsFrame("NV12", w, h, [a[:h], a[h:]], timestamp=ts)
 
         srcs = [obs(nv[i], i) for i in range(n_frames)]
-        outs = [obs(nv[n_frames + i], 0) for i in range(3)]
+        outs = [obs(nv[n_frames + i], 0) for i in range(4)]
         flt4 = wl.make_filter(L, local)
-        flt4.stream.stream_obs(srcs[:warmup], lambda o: False, outs)
+        flt4.stream.stream_obs(srcs[:warmup], lambda o: False, outs[:3])
         nv12_ms, got = [], 0
         for wi in range(R):
+            window = srcs[warmup + wi * K: warmup + (wi + 1) * K]
+            wouts = [outs[j % 4] for j in range(K)]
             barrier()
             tp = time.perf_counter()
-            got += flt4.stream.stream_obs(srcs[warmup + wi * K: warmup + (wi + 1) * K], lambda o: False, outs)
+            got += sum(r.has_output for r in flt4.stream.submit_obs_batch(window, wouts))
             flt4.stream.sync()
             nv12_ms.append(1e3 * (time.perf_counter() - tp))
         parity_fail += int(got != R * K)
@@ -606,16 +612,17 @@ def main():
                        "remap_build": "exact" if L.remap_exact() else "contract"},
             "e2e": {"value": agg["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": wl.frame_bytes(),
                     "d2h_bytes_per_step": wl.frame_bytes(), "ms_per_step": t_e2e / K,
-                    "api": "StabilizationFilter.stream(frames, callback) — the pipelined VideoFilter::stream analogue: "
-                           "pinned host input -> H2D -> filter -> D2H -> pinned host output for every step, uploads and "
-                           "downloads overlapped with the neighbouring frames' processing",
+                    "api": "Stream.submit_batch(host frames, host outputs) = lvkb200_stream_submit_batch — the pipelined "
+                           "VideoFilter::stream analogue in one FFI call per window: pinned host input -> H2D -> filter -> "
+                           "D2H -> pinned host output for every step, uploads and downloads overlapped with the "
+                           "neighbouring frames' processing, all outputs landed when the call returns",
                     "apply_fps_rank0": m["apply_fps"],
                     "apply_note": "same, through the synchronous per-frame StabilizationFilter.apply (no overlap)"},
             "e2e_nv12": None if not agg.get("nv12_ms") else {
                 "value": agg["frames"] / (agg["nv12_ms"] * 1e-3), "unit": "frames/s", "ms_per_step": agg["nv12_ms"] / K,
                 "h2d_bytes_per_step": wl.frame_bytes() // 2, "d2h_bytes_per_step": wl.frame_bytes() // 2,
                 "per_rank_fps": agg.get("nv12_fps_per_rank"),
-                "api": "Stream.stream_obs — lvkb200_stream_prefetch_obs / _submit_obs_async: the same clip as NV12 planes in "
+                "api": "Stream.submit_obs_batch = lvkb200_stream_submit_obs_batch (prefetch_obs / submit_obs_async inside): the same clip as NV12 planes in "
                        "pinned host memory (the OBS plugin's native layout, FrameIngest.cpp:566-604); plane upload + to_ocl on "
                        "the copy-in stream, to_obs + plane download on the copy-out stream; max over ranks of the median window"},
             "per_rank": agg.get("per_rank"),

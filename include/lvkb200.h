@@ -201,7 +201,9 @@ lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket);
  * `count` calls of lvkb200_stream_prefetch_frame(frame i+1) + lvkb200_stream_submit(frame i) would - one call instead of
  * 2 * count crossings of the FFI.  results[i] reports has_output / timestamp of step i (the first frame_delay steps have
  * none and leave outs[i] untouched).  timestamps may be NULL (0, 1, ...).  Device outputs follow the rule of
- * lvkb200_stream_submit: complete after lvkb200_stream_sync. */
+ * lvkb200_stream_submit: complete after lvkb200_stream_sync.  HOST frames with HOST outputs run pipelined inside the
+ * call (upload of frame i+1 and download of output i-1 overlap frame i, two outputs in flight) and every output has
+ * landed when it returns; outs[] may then cycle through >= 4 buffers if only the most recent outputs are needed. */
 lvkb200_status lvkb200_stream_submit_batch(lvkb200_stream* s, const void* const* frames, size_t pitch, int width, int height,
                                            lvkb200_format format, const uint64_t* timestamps, lvkb200_memspace frame_space,
                                            void* const* outs, size_t out_pitch, lvkb200_memspace out_space, int count,
@@ -340,6 +342,10 @@ lvkb200_status lvkb200_stream_submit_obs(lvkb200_stream* s, const lvkb200_obs_fr
 lvkb200_status lvkb200_stream_prefetch_obs(lvkb200_stream* s, const lvkb200_obs_frame* in);
 lvkb200_status lvkb200_stream_submit_obs_async(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_obs_frame* out,
                                                lvkb200_result* res, uint64_t* ticket);
+/* The two calls above over a whole sequence of host frames (in[i] -> out[i], two outputs in flight, all outputs landed
+ * on return): lvkb200_stream_submit_batch for OBS plane layouts. */
+lvkb200_status lvkb200_stream_submit_obs_batch(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_obs_frame* out, int count,
+                                               lvkb200_result* results);
 
 /* CUDA-event timing on the stream's own CUDA stream (torch.cuda.Event cannot see it): record slot `index`
  * (0..LVKB200_EVENT_SLOTS-1) now; elapsed returns the device time between two recorded slots after waiting for

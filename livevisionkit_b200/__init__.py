@@ -492,6 +492,26 @@ class Stream:
             out.timestamp = int(res.out_timestamp)
         return res, int(ticket.value)
 
+    def submit_obs_batch(self, frames, outs):
+        """lvkb200_stream_submit_obs_batch: `frames[i]` -> `outs[i]` (host ObsFrames of one layout and size; `outs` may
+        cycle through >= 4 buffers), pipelined inside ONE FFI call.  Returns the per-step Results; every output has landed."""
+        n = len(frames)
+        if len(outs) != n:
+            raise ValueError("one output frame per input frame")
+        cin, cout = (_capi.ObsFrame * n)(), (_capi.ObsFrame * n)()
+        for i in range(n):
+            a, sa = frames[i].c_cached()
+            b, sb = outs[i].c_cached()
+            if sa != _capi.MEM_HOST or sb != _capi.MEM_HOST:
+                raise ValueError("submit_obs_batch takes host planes")
+            cin[i], cout[i] = a, b
+        results = (_capi.Result * n)()
+        _capi.check(self._lib.lvkb200_stream_submit_obs_batch(self._h, cin, cout, n, results))
+        for i in range(n):
+            if results[i].has_output:
+                outs[i].timestamp = int(results[i].out_timestamp)
+        return results
+
     def stream_obs(self, frames, callback, outputs) -> int:
         """Pipelined VSFilter::filter over a sequence of host OBS-layout frames (the NV12 / I420 analogue of
         `Stream.__call__`): frame t+1 is uploaded and converted while frame t is tracked, output t-1 is converted back and

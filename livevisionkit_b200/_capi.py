@@ -134,6 +134,7 @@ SYMBOLS = {
     "lvkb200_frame_download": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(ObsFrame), _i]),
     "lvkb200_stream_submit_obs": (C.c_int, [_vp, C.POINTER(ObsFrame), _i, C.POINTER(ObsFrame), _i, C.POINTER(Result)]),
     "lvkb200_stream_prefetch_obs": (C.c_int, [_vp, C.POINTER(ObsFrame)]),
+    "lvkb200_stream_submit_obs_batch": (C.c_int, [_vp, C.POINTER(ObsFrame), C.POINTER(ObsFrame), _i, C.POINTER(Result)]),
     "lvkb200_stream_submit_obs_async": (C.c_int, [_vp, C.POINTER(ObsFrame), C.POINTER(ObsFrame), C.POINTER(Result), C.POINTER(C.c_uint64)]),
 }
 

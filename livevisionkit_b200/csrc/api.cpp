@@ -309,17 +309,41 @@ lvkb200_status lvkb200_stream_submit_batch(lvkb200_stream* s, const void* const*
     LVKB_REQUIRE(s != nullptr && frames != nullptr && outs != nullptr && results != nullptr && count >= 0);
     LVKB_CUDA(cudaSetDevice(s->device));
     const bool announce = format == LVKB200_BGR || format == LVKB200_RGB || format == LVKB200_YUV;
-    for (int i = 0; i < count; i++)
+    // host frames and host outputs: the whole sequence runs pipelined (VideoFilter::stream's three threads): upload of
+    // frame i+1 and download of output i-1 overlap frame i, two outputs in flight; all outputs have landed on return
+    const bool pipelined = frame_space == LVKB200_MEM_HOST && out_space == LVKB200_MEM_HOST && announce;
+    uint64_t in_flight[3] = {0, 0, 0};
+    int n_flight = 0;
+    lvkb200_status st = LVKB200_OK;
+    for (int i = 0; i < count && st == LVKB200_OK; i++)
     {
         LVKB_REQUIRE(frames[i] != nullptr);
         // frame i+1 is announced before frame i is submitted: its copy into the ring, detection image and pyramid are
         // queued behind frame i's tracking chain (the input thread of VideoFilter::stream running one frame ahead)
         if (announce && i + 1 < count && frames[i + 1] != nullptr)
             LVKB_TRY(s->prefetch(frames[i + 1], pitch, width, height, format, frame_space));
-        LVKB_TRY(s->submit(frames[i], pitch, width, height, format, timestamps ? timestamps[i] : static_cast<uint64_t>(i),
-                           frame_space, outs[i], out_pitch, out_space, &results[i]));
+        s->deferred_output = pipelined;
+        s->last_ticket = 0;
+        st = s->submit(frames[i], pitch, width, height, format, timestamps ? timestamps[i] : static_cast<uint64_t>(i),
+                       frame_space, outs[i], out_pitch, out_space, &results[i]);
+        s->deferred_output = false;
+        if (st == LVKB200_OK && pipelined && results[i].has_output && s->last_ticket)
+        {
+            in_flight[n_flight++] = s->last_ticket;
+            if (n_flight > 2)
+            {
+                st = s->wait_output(in_flight[0]);
+                in_flight[0] = in_flight[1]; in_flight[1] = in_flight[2];
+                n_flight = 2;
+            }
+        }
     }
-    return LVKB200_OK;
+    for (int k = 0; k < n_flight; k++)
+    {
+        const lvkb200_status w = s->wait_output(in_flight[k]);
+        if (st == LVKB200_OK) st = w;
+    }
+    return st;
 }
 
 lvkb200_status lvkb200_stream_wait_output(lvkb200_stream* s, uint64_t ticket)

@@ -377,6 +377,37 @@ lvkb200_status lvkb200_stream_submit_obs_async(lvkb200_stream* s, const lvkb200_
     return st;
 }
 
+lvkb200_status lvkb200_stream_submit_obs_batch(lvkb200_stream* s, const lvkb200_obs_frame* in, lvkb200_obs_frame* out, int count,
+                                               lvkb200_result* results)
+{
+    LVKB_REQUIRE(s != nullptr && in != nullptr && out != nullptr && results != nullptr && count >= 0);
+    uint64_t in_flight[3] = {0, 0, 0};
+    int n_flight = 0;
+    lvkb200_status st = LVKB200_OK;
+    for (int i = 0; i < count && st == LVKB200_OK; i++)
+    {
+        if (i + 1 < count) LVKB_TRY(lvkb200_stream_prefetch_obs(s, &in[i + 1]));
+        uint64_t ticket = 0;
+        st = lvkb200_stream_submit_obs_async(s, &in[i], &out[i], &results[i], &ticket);
+        if (st == LVKB200_OK && ticket)
+        {
+            in_flight[n_flight++] = ticket;
+            if (n_flight > 2)
+            {
+                st = s->wait_output(in_flight[0]);
+                in_flight[0] = in_flight[1]; in_flight[1] = in_flight[2];
+                n_flight = 2;
+            }
+        }
+    }
+    for (int k = 0; k < n_flight; k++)
+    {
+        const lvkb200_status w = s->wait_output(in_flight[k]);
+        if (st == LVKB200_OK) st = w;
+    }
+    return st;
+}
+
 }  // extern "C"
 
 lvkb200_status lvkb200_stream::egress_planes(cudaStream_t stream, const uint8_t* packed, size_t pitch, int width, int height,

@@ -145,6 +145,15 @@ def test_pipelined_obs_stream_equals_submit_obs(I, fmt):
     got = []
     delivered = b.stream_obs(sources, lambda o: got.append((o.timestamp, [p.copy() for p in o.planes])) and False, outs)
     assert delivered == len(want) == n - 10 and len(got) == len(want)
+    # the whole sequence through ONE call (lvkb200_stream_submit_obs_batch), one output frame per input
+    c = L.Stream(settings, 0)
+    bouts = [L.ObsFrame(fmt, w, h, [np.zeros_like(p) for p in sources[0].planes]) for _ in range(n)]
+    res = c.submit_obs_batch(sources, bouts)
+    batch = [(bouts[i].timestamp, bouts[i].planes) for i in range(n) if res[i].has_output]
+    assert len(batch) == len(want)
+    for (ts_a, pa), (ts_b, pb) in zip(want, batch):
+        assert ts_a == ts_b and all((p == q).all() for p, q in zip(pa, pb)), f"{fmt}: batch planes differ at {ts_a}"
+    c.close()
     for (ts_a, pa), (ts_b, pb) in zip(want, got):
         assert ts_a == ts_b
         for p, q in zip(pa, pb):

@@ -312,3 +312,29 @@ def test_submit_batch_equals_per_frame_submit():
         assert torch.equal(outs_a[i], outs_b[i]), f"frame {i}: batch output differs"
     a.close()
     b.close()
+
+
+def test_submit_batch_host_pipelined_equals_apply():
+    """lvkb200_stream_submit_batch with HOST frames and HOST outputs runs the pipelined path inside one call (outputs
+    cycling through four buffers): every output equals the synchronous per-frame apply()."""
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    n = 24
+    clip = Clip((960, 540), "shake", frames=n)
+    frames = [clip[i] for i in range(n)]
+    settings = L.StabilizationFilterSettings.obs_homography_preset()
+    a, b = L.StabilizationFilter(settings, 0), L.Stream(settings, 0)
+    want = [a.apply(L.VideoFrame(frames[i], 7 + i, L.BGR)) for i in range(n)]
+    outs = [np.zeros_like(frames[0]) for _ in range(n)]
+    res = b.submit_batch(frames, outs, L.BGR, [7 + i for i in range(n)])
+    for i in range(n):
+        assert bool(res[i].has_output) == (not want[i].empty())
+        if res[i].has_output:
+            assert res[i].out_timestamp == want[i].timestamp and (outs[i] == want[i].data).all(), f"frame {i}"
+    # cycling outputs: the last four outputs are intact when the call returns
+    ring = [np.zeros_like(frames[0]) for _ in range(4)]
+    c = L.Stream(settings, 0)
+    c.submit_batch(frames, [ring[i % 4] for i in range(n)], L.BGR, [7 + i for i in range(n)])
+    for i in range(n - 4, n):
+        assert (ring[i % 4] == want[i].data).all()
+    b.close(); c.close()
