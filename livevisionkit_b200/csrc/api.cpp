@@ -30,7 +30,17 @@ void set_error(const char* fmt, ...)
 
 static lvkb200_assert_handler g_assert_handler = nullptr;
 static std::atomic<uint64_t> g_launches{0};
-void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+// Launches recorded while THIS thread captures a CUDA graph are not executed: they are tallied per thread and credited on
+// every replay of the graph instead (other threads' streams keep counting into the process-wide total meanwhile).
+static thread_local bool t_capturing = false;
+static thread_local int t_captured = 0;
+void count_launches(int n)
+{
+    if (t_capturing) { t_captured += n; return; }
+    g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed);
+}
+void begin_launch_capture() { t_capturing = true; t_captured = 0; }
+int end_launch_capture() { t_capturing = false; return t_captured; }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 void report_assert(const char* file, const char* function, const char* assertion)

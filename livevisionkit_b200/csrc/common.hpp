@@ -66,6 +66,9 @@ struct TrackParams
 // Process-wide count of kernels launched by this library (bench.py reports it as gpu_launches).
 void count_launches(int n);
 uint64_t launch_count();
+// Around a stream capture on the calling thread: launches are tallied (returned by end_) instead of counted.
+void begin_launch_capture();
+int end_launch_capture();
 
 // ---- kernel launchers (one per reference stage) --------------------------------------------------------------------
 

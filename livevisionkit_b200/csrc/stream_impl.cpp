@@ -461,16 +461,16 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
     if (!global) return LVKB200_OK;
     if (!use_graphs || profile_stages) return record_estimator_chain(profile_stages);
 
-    // compaction + RANSAC (4 kernels) replay as ONE CUDA graph: one launch instead of four, no inter-kernel API gaps
+    // compaction + RANSAC (3 kernels) replay as ONE CUDA graph: one launch instead of three, no inter-kernel API gaps
     cudaGraphExec_t& exec = track_graph[0][1];
     if (!exec)
     {
-        const uint64_t launches_before = launch_count();
         cudaGraph_t graph = nullptr;
         LVKB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        begin_launch_capture();
         const lvkb200_status st = record_estimator_chain(false);
+        graph_kernels = end_launch_capture();  // credited per replay below
         const cudaError_t e = cudaStreamEndCapture(cs, &graph);
-        count_launches(-static_cast<int>(launch_count() - launches_before));  // counted per replay instead
         if (st != LVKB200_OK || e != cudaSuccess || !graph)
         {
             if (graph) cudaGraphDestroy(graph);
@@ -489,7 +489,7 @@ lvkb200_status lvkb200_stream::enqueue_tracking(const std::vector<float>& pts, b
         }
     }
     LVKB_CUDA(cudaGraphLaunch(exec, cs));
-    count_launches(4);  // compact, hypotheses, score, refine
+    count_launches(graph_kernels);  // compact, score (+ hypotheses), refine
     return LVKB200_OK;
 }
 

@@ -164,6 +164,7 @@ struct lvkb200_stream
     // LVKB200_REMAP_OVERLAP=0/1 forces either order.
     cudaEvent_t pre_chain = nullptr;
     bool pre_chain_valid = false, overlap_after_lk = false;
+    int graph_kernels = 0;  // kernels inside the captured estimator graph (counted once per replay)
     int remap_overlap = -1;  // -1: by frame size (>= REMAP_OVERLAP_MIN_PIXELS)
     static constexpr long long REMAP_OVERLAP_MIN_PIXELS = 3000000;
     lvkb200::DeviceBuffer spare_buf;
