@@ -810,9 +810,21 @@ class CompositeFilter:
         return frame
 
     def stream_frames(self, frames, callback, outputs=None) -> int:
-        if not self._fused:
-            raise NotImplementedError("pipelined streaming is provided for the fused deblocking -> stabilization chain")
-        return self.filters[1].stream_frames(frames, callback, outputs)
+        """lvk::VideoFilter::stream (Filters/VideoFilter.cpp:62-209) for a chain: the fused Deblocking -> Stabilization
+        chain runs pipelined on the stabilizer's device pipeline; any other chain is applied frame by frame (what the
+        reference's filter thread does, VideoFilter.cpp:130-139): empty outputs (a filter that is still buffering) are
+        skipped, a true return of `callback` terminates the stream.  Returns the number of outputs delivered."""
+        if self._fused:
+            return self.filters[1].stream_frames(frames, callback, outputs)
+        delivered = 0
+        for frame in frames:
+            out = self.apply(frame)
+            if out.empty():
+                continue
+            delivered += 1
+            if callback(out):
+                break
+        return delivered
 
 
 class StabilizationFilter:

@@ -122,3 +122,31 @@ def test_chained_in_front_of_stabilizer(D, oracle):
         a = chain.filters[1].apply(L.VideoFrame(f, i, L.BGR))
         b = plain.apply(L.VideoFrame(f, i, L.BGR))
         assert a.empty() == b.empty() and (a.empty() or (a.data == b.data).all())
+
+
+def test_composite_stream_frames_generic_chain():
+    """CompositeFilter.stream_frames for a chain that is not the fused one (Stabilization -> Scaling): outputs equal the
+    filters applied one after the other, empty frames of the buffering stabilizer are skipped, a true callback return
+    stops the stream (VideoFilter.cpp:130-139, 180-206)."""
+    import livevisionkit_b200 as L
+    from tools.synth import Clip
+    clip = Clip((640, 360), "shake", frames=16)
+    settings = L.StabilizationFilterSettings.obs_homography_preset()
+    scale = L.ScalingFilterSettings((960, 540), 0.8, False)
+    chain = L.CompositeFilter([L.StabilizationFilter(settings), L.ScalingFilter(scale)])
+    stab, scaler = L.StabilizationFilter(settings), L.ScalingFilter(scale)
+    frames = [L.VideoFrame(clip[i], i, L.BGR) for i in range(16)]
+    got = []
+    n = chain.stream_frames(frames, lambda vf: got.append((vf.timestamp, vf.data.copy())) and False)
+    want = []
+    for f in frames:
+        v = stab.apply(f)
+        if not v.empty():
+            w = scaler.apply(v)
+            want.append((w.timestamp, w.data.copy()))
+    assert n == len(want) == 6 and len(got) == 6
+    for (ta, a), (tb, b) in zip(want, got):
+        assert ta == tb and a.shape == (540, 960, 3) and (a == b).all()
+    chain2 = L.CompositeFilter([L.StabilizationFilter(settings), L.ScalingFilter(scale)])
+    seen = []
+    assert chain2.stream_frames(frames, lambda vf: seen.append(vf.timestamp) or len(seen) >= 2) == 2
