@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(FT_THREADS, CTAS)
     // nearest / direct paths recompute the position).
     int lin[4];
     float ppx[4], ppy[4];
-    unsigned easu_mask = 0, nearest_mask = 0, inside_mask = 0;
+    unsigned easu_mask = 0, inside_mask = 0;
     int minx = INT_MAX, miny = INT_MAX, maxx = INT_MIN, maxy = INT_MIN;
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -279,12 +279,11 @@ __global__ void __launch_bounds__(FT_THREADS, CTAS)
         ppy[k] = fy - floorf(fy);
         lin[k] = sy * FW + sx;
         const bool inside = (x < dW) && (y < dH);
-        // FSR.cl:387-399: EASU iff 1 <= sx < W-4 and 1 <= sy < H-4; nearest neighbour iff inside the source otherwise
+        // FSR.cl:387-399: EASU iff 1 <= sx < W-4 and 1 <= sy < H-4 (nearest neighbour / background otherwise: decided
+        // in the rare path below, which recomputes the position)
         const bool easu = inside && (unsigned)(sx - 1) < (unsigned)(W - 5) && (unsigned)(sy - 1) < (unsigned)(H - 5);
-        const bool in_src = (unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H;
         if (inside) inside_mask |= 1u << k;
         if (easu) easu_mask |= 1u << k;
-        if (inside && !easu && in_src) nearest_mask |= 1u << k;
         minx = min(minx, easu ? sx : INT_MAX); maxx = max(maxx, easu ? sx : INT_MIN);
         miny = min(miny, easu ? sy : INT_MAX); maxy = max(maxy, easu ? sy : INT_MIN);
     }
@@ -401,16 +400,19 @@ __global__ void __launch_bounds__(FT_THREADS, CTAS)
     // rare pixels, behind one warp-wide test: EASU pixels of a tile whose footprint does not fit the staging window
     // (extreme warps) -> direct global reads; border band (FSR.cl:387-399) -> nearest neighbour.  The position is
     // recomputed (same arithmetic, same result).
-    if (__any_sync(0xffffffffu, nearest_mask != 0 || (!staged && easu_mask != 0)))
+    if (__any_sync(0xffffffffu, easu_mask != inside_mask || (!staged && easu_mask != 0)))
     {
 #pragma unroll 1
         for (int k = 0; k < 4; k++)
         {
-            const bool direct = !staged && ((easu_mask >> k) & 1u), nearest = (nearest_mask >> k) & 1u;
-            if (!direct && !nearest) continue;
+            const bool direct = !staged && ((easu_mask >> k) & 1u);
+            const bool other = ((inside_mask & ~easu_mask) >> k) & 1u;  // inside the destination, not an EASU pixel
+            if (!direct && !other) continue;
             float fx, fy;
             source_position<MODE>(x, ybase + 4 * k, W, H, T, M, fx, fy);
             const int sx = __float2int_rz(fx), sy = __float2int_rz(fy);
+            // nearest neighbour iff the position lies inside the source; everything else keeps the background
+            if (other && !((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H)) continue;
             const uint8_t* p = src + (size_t)sy * src_pitch + 3 * sx;
             unsigned v;
             if (direct)
