@@ -20,6 +20,7 @@
 // Compiled with --fmad=false: the weights / the acceptance test are the reference's unfused expressions.
 
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 
 #include "mesh.hpp"
@@ -573,6 +574,559 @@ __global__ void __launch_bounds__(T, 1)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Round 2: the sparse solve re-tiled for issue rate (k_mesh_cgls2).  The ncu source view of the kernel above on the
+// "Vector Field" preset (profiles/r02_mesh_cgls_v1_lines.txt: 688 us, 136 iterations, 17 400 warp-instructions per
+// iteration at 44 % issue-active) showed where an iteration went: 43 % in the transposed product (a lane per unknown
+// walking the features of its four cells: the warp runs as long as its most crowded vertex, ~26 visits of 15
+// instructions), 22 % in the row products (two integer divisions and a three-way branch per row unit), 9 % in block
+// reductions.  Here:
+//   * 1024 threads.  The features are renumbered in cell order once per frame (weights and vertex index stored at the
+//     sorted position), so every per-iteration access is contiguous and division-free.
+//   * A^T r is split: warps 16-31 sum CHAINS - one (cell, corner weight) pair = sum over the cell's features of
+//     w_corner * (r_x, r_y) - with the cells dealt to warps in order of population (eight equally crowded cells per
+//     warp, no lane waits for a crowded neighbour); warps 0-15 meanwhile walk the similarity columns; after one
+//     barrier a column adds its four chain sums.  ~3 200 balanced visits instead of 16 warps x 26.
+//   * q = A p stays in registers between the product and the residual update (a thread owns the same rows in both).
+// Same iteration as before (Eigen's LSCG, oracle/lscg_ref.c); the float32 summation order of the dot products and of
+// the per-vertex gather differs again (tests: same tolerances as the kernel above).  Meshes beyond the slot limits
+// below, and the 2x2 mesh, stay on k_mesh_cgls.
+namespace v2
+{
+
+constexpr int T2 = 1024, NW2 = T2 / 32, COLT = 512;
+constexpr int MAX_SLOT_N = 2, MAX_SLOT_S = 2, MAX_SLOT_F = 4;  // unknowns / similarity rows / features a thread may own
+static_assert(NW2 == 32, "the block sums read one warp total per lane");
+
+struct Carve2
+{
+    size_t x, p, s, invd, r, sw, sim_val, csc_val, P, csc_ptr, cell_start, cell_cnt, colP, sim_col, csc_row, si00,
+        fcell, forder, chain_cell, red, total;
+    __host__ __device__ Carve2(int n, int S, int nnz, int cells, int cap)
+    {
+        size_t o = 0;
+        auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
+        x = take(4 * (size_t)n); p = take(4 * (size_t)n); s = take(4 * (size_t)n); invd = take(4 * (size_t)n);
+        r = take(4 * ((size_t)n + S + 2 * (size_t)cap));
+        sw = take(16 * (size_t)cap);
+        sim_val = take(16 * (size_t)S); csc_val = take(4 * (size_t)nnz);
+        P = take(8 * (4 * (size_t)cells + 1));
+        csc_ptr = take(4 * ((size_t)n + 1)); cell_start = take(4 * ((size_t)cells + 1)); cell_cnt = take(4 * (size_t)cells);
+        colP = take(8 * (size_t)n); sim_col = take(8 * (size_t)S); csc_row = take(2 * (size_t)nnz);
+        si00 = take(2 * (size_t)cap); fcell = take(2 * (size_t)cap + 8); forder = take(2 * (size_t)cap);
+        chain_cell = take(2 * (size_t)cells);
+        red = take(NW2 * sizeof(float) + NW2 * sizeof(float2));
+        total = o;
+    }
+};
+
+__device__ __forceinline__ float block_sum1(float a, float* slot)
+{
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = a;
+    __syncthreads();
+    return warp_sum(slot[threadIdx.x & 31]);
+}
+
+// Sum of (a, b) over the COLUMN warps (threads < COLT; the others hold nothing), returned to every thread.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* slot)
+{
+    if (threadIdx.x < COLT)
+    {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = make_float2(a, b);
+    }
+    __syncthreads();
+    static_assert(COLT / 32 == 16, "the second round is a 16-lane butterfly");
+    float2 t = slot[threadIdx.x & 15];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+    {
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    }
+    return t;
+}
+
+struct Sh
+{
+    float *x, *p, *s, *invd, *r;
+    float4* sw;
+    float *sim_val, *csc_val;
+    float2* P;
+    int *csc_ptr, *cell_start, *cell_cnt;
+    ushort4* colP;
+    uint16_t *sim_col, *csc_row, *si00, *fcell, *forder, *chain_cell;
+    int n, S, N, cells, cols;
+    float ts;
+};
+
+// emit(col, (A^T r)[col]) for every unknown, r = the row vector in h.r.  SQUARE: the squared column norms instead.
+// Contains one barrier; the caller separates two calls by another one (h.P and h.s are rewritten).
+template <bool SQUARE, typename Emit>
+__device__ __forceinline__ void transpose_product(const Sh& h, Emit emit)
+{
+    const int tid = threadIdx.x;
+    if (tid >= COLT)
+    {
+        const float2* uf = reinterpret_cast<const float2*>(h.r + h.n + h.S);  // (x row, y row) of a feature: n + S is even
+        for (int j = tid - COLT; j < h.cells; j += T2 - COLT)
+        {
+            const int cell = h.chain_cell[j];
+            const int k1 = h.cell_start[cell + 1];
+            float2 c0 = make_float2(0.0f, 0.0f), c1 = c0, c2 = c0, c3 = c0;
+#pragma unroll 2
+            for (int k = h.cell_start[cell]; k < k1; k++)
+            {
+                const float4 w = h.sw[k];
+                if (SQUARE)
+                {
+                    c0.x += w.x * w.x; c1.x += w.y * w.y; c2.x += w.z * w.z; c3.x += w.w * w.w;
+                }
+                else
+                {
+                    const float2 uv = uf[k];
+                    c0.x += w.x * uv.x; c0.y += w.x * uv.y;
+                    c1.x += w.y * uv.x; c1.y += w.y * uv.y;
+                    c2.x += w.z * uv.x; c2.y += w.z * uv.y;
+                    c3.x += w.w * uv.x; c3.y += w.w * uv.y;
+                }
+            }
+            if (SQUARE) { c0.y = c0.x; c1.y = c1.x; c2.y = c2.x; c3.y = c3.x; }
+            float4* const out = reinterpret_cast<float4*>(h.P + 4 * cell);
+            out[0] = make_float4(c0.x, c0.y, c1.x, c1.y);
+            out[1] = make_float4(c2.x, c2.y, c3.x, c3.y);
+        }
+    }
+    else
+    {
+        for (int col = tid; col < h.n; col += COLT)
+        {
+            float acc = SQUARE ? h.ts * h.ts : h.ts * h.r[col];
+            const int k1 = h.csc_ptr[col + 1];
+#pragma unroll 1
+            for (int k = h.csc_ptr[col]; k < k1; k += 4)  // padded to whole groups of four (zero weights) on the host
+            {
+                const float4 a = *reinterpret_cast<const float4*>(h.csc_val + k);
+                const ushort4 ri = *reinterpret_cast<const ushort4*>(h.csc_row + k);
+                if (SQUARE) { acc += a.x * a.x; acc += a.y * a.y; acc += a.z * a.z; acc += a.w * a.w; }
+                else
+                {
+                    const float u0 = h.r[ri.x], u1 = h.r[ri.y], u2 = h.r[ri.z], u3 = h.r[ri.w];
+                    acc += a.x * u0; acc += a.y * u1; acc += a.z * u2; acc += a.w * u3;
+                }
+            }
+            h.s[col] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid < COLT)
+    {
+        const float* Pf = reinterpret_cast<const float*>(h.P);
+        for (int col = tid; col < h.n; col += COLT)
+        {
+            const ushort4 pi = h.colP[col];
+            const int comp = col & 1;
+            // corner i00 of cell (vx, vy) and i10 of (vx-1, vy); i01 of (vx, vy-1) and i11 of (vx-1, vy-1)
+            const float f = (Pf[2 * pi.x + comp] + Pf[2 * pi.y + comp]) + (Pf[2 * pi.z + comp] + Pf[2 * pi.w + comp]);
+            emit(col, h.s[col] + f);
+        }
+    }
+}
+
+__device__ __forceinline__ void copy16(const uint8_t* src, uint8_t* dst, int bytes)
+{
+    for (int i = threadIdx.x; i < (bytes + 15) / 16; i += T2)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+template <int SN, int SS, int SF>
+__global__ void __launch_bounds__(T2, 1)
+    k_mesh_cgls2(MeshSys sys, MeshSolveParams prm, const float2* __restrict__ src, const float2* __restrict__ dst,
+                 const int* __restrict__ n_ptr, const TrackParams* __restrict__ tp, float* __restrict__ state,
+                 uint8_t* __restrict__ mask, uint8_t* __restrict__ res_dev, uint8_t* __restrict__ res_host,
+                 TrackOutCopy out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int n = sys.n, S = sys.S, cols = sys.cols, rows = sys.rows, gw = cols - 1, gh = rows - 1;
+    const int cells = gw * gh;
+    const Carve2 cv(n, S, sys.csc_nnz, cells, sys.cap);
+    Sh h;
+    h.x = reinterpret_cast<float*>(smem + cv.x); h.p = reinterpret_cast<float*>(smem + cv.p);
+    h.s = reinterpret_cast<float*>(smem + cv.s); h.invd = reinterpret_cast<float*>(smem + cv.invd);
+    h.r = reinterpret_cast<float*>(smem + cv.r); h.sw = reinterpret_cast<float4*>(smem + cv.sw);
+    h.sim_val = reinterpret_cast<float*>(smem + cv.sim_val); h.csc_val = reinterpret_cast<float*>(smem + cv.csc_val);
+    h.P = reinterpret_cast<float2*>(smem + cv.P);
+    h.csc_ptr = reinterpret_cast<int*>(smem + cv.csc_ptr); h.cell_start = reinterpret_cast<int*>(smem + cv.cell_start);
+    h.cell_cnt = reinterpret_cast<int*>(smem + cv.cell_cnt); h.colP = reinterpret_cast<ushort4*>(smem + cv.colP);
+    h.sim_col = reinterpret_cast<uint16_t*>(smem + cv.sim_col); h.csc_row = reinterpret_cast<uint16_t*>(smem + cv.csc_row);
+    h.si00 = reinterpret_cast<uint16_t*>(smem + cv.si00); h.fcell = reinterpret_cast<uint16_t*>(smem + cv.fcell);
+    h.forder = reinterpret_cast<uint16_t*>(smem + cv.forder); h.chain_cell = reinterpret_cast<uint16_t*>(smem + cv.chain_cell);
+    float* const red1 = reinterpret_cast<float*>(smem + cv.red);
+    float2* const red2 = reinterpret_cast<float2*>(smem + cv.red + NW2 * sizeof(float));
+    float* const x = h.x; float* const p = h.p; float* const r = h.r;
+
+    const int N = min(*n_ptr, sys.cap);
+    h.n = n; h.S = S; h.N = N; h.cells = cells; h.cols = cols; h.ts = prm.temporal_weight;
+    const float ts = prm.temporal_weight;
+    const int NS = n + S;
+    MeshSolveResult* const hdr = reinterpret_cast<MeshSolveResult*>(res_dev);
+    float* const mesh_out = reinterpret_cast<float*>(res_dev + sizeof(MeshSolveResult));
+    int iterations = 0;
+    const bool solve = N >= prm.min_samples;  // FrameTracker.cpp:152-156: too few samples -> no estimate at all
+
+    if (solve)
+    {
+        // ---- stage the static system and the warm start
+        for (int i = tid; i < n; i += T2) x[i] = state[i];
+        for (int i = tid; i <= n; i += T2) h.csc_ptr[i] = sys.csc_ptr[i];
+        for (int i = tid; i < 4 * S; i += T2) { h.sim_col[i] = sys.sim_col[i]; h.sim_val[i] = sys.sim_val[i]; }
+        for (int i = tid; i < sys.csc_nnz; i += T2) { h.csc_row[i] = sys.csc_row[i]; h.csc_val[i] = sys.csc_val[i]; }
+        for (int i = tid; i < cells; i += T2) h.cell_cnt[i] = 0;
+        if (tid == 0) h.P[4 * cells] = make_float2(0.0f, 0.0f);  // what a vertex on the border adds for a missing cell
+        __syncthreads();
+        // ---- mesh cell of every tracked point (FrameTracker.cpp:236-246), cell populations
+        for (int i = tid; i < N; i += T2)
+        {
+            const float2 t = src[i];
+            int kx = (int)max(min(__float2ll_rz(t.x / prm.key_w), (long long)INT_MAX), (long long)INT_MIN);
+            int ky = (int)max(min(__float2ll_rz(t.y / prm.key_h), (long long)INT_MAX), (long long)INT_MIN);
+            kx = min(max(kx, 0), gw - 1);
+            ky = min(max(ky, 0), gh - 1);
+            const int cell = ky * gw + kx;
+            h.fcell[i] = (uint16_t)cell;
+            atomicAdd(&h.cell_cnt[cell], 1);
+        }
+        __syncthreads();
+        if (tid < 32)
+        {
+            // exclusive scan of the cell populations (one warp, 32 cells per step)
+            int carry = 0;
+            for (int c0 = 0; c0 < cells; c0 += 32)
+            {
+                const int c = c0 + tid;
+                const int v = c < cells ? h.cell_cnt[c] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t2;
+                }
+                if (c < cells) h.cell_start[c] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) h.cell_start[cells] = carry;
+        }
+        else
+        {
+            // the four chain sums an unknown adds up: indices into P (4 per cell; slot 4*cells holds zero)
+            for (int col = tid - 32; col < n; col += T2 - 32)
+            {
+                const int vtx = col >> 1;
+                const int vy = vtx / cols, vx = vtx - vy * cols;
+                const int none = 4 * cells;
+                const bool l = vx > 0, t = vy > 0, rr = vx < gw, b = vy < gh;
+                ushort4 pi;
+                pi.x = (uint16_t)((rr && b) ? 4 * (vy * gw + vx) + 0 : none);            // i00 of (vx, vy): w0
+                pi.y = (uint16_t)((l && b) ? 4 * (vy * gw + vx - 1) + 3 : none);         // i10 of (vx-1, vy): w3
+                pi.z = (uint16_t)((rr && t) ? 4 * ((vy - 1) * gw + vx) + 1 : none);      // i01 of (vx, vy-1): w1
+                pi.w = (uint16_t)((l && t) ? 4 * ((vy - 1) * gw + vx - 1) + 2 : none);   // i11 of (vx-1, vy-1): w2
+                h.colP[col] = pi;
+            }
+        }
+        __syncthreads();
+        // ---- features into cell order (stable: ascending index inside a cell), weights at the sorted position
+        for (int i = tid; i < N; i += T2)
+        {
+            const uint16_t me = h.fcell[i];
+            int rank = 0;
+            for (int j = 0; j < i; j++) rank += (h.fcell[j] == me);
+            const int k = h.cell_start[me] + rank;
+            h.forder[k] = (uint16_t)i;
+            // barycentric weights of the point in its cell (Math.tpp:247-265)
+            const int ky = me / gw, kx = me - ky * gw;
+            const float2 t = src[i];
+            const float p0x = (float)kx * prm.key_w, p0y = (float)ky * prm.key_h;
+            const float p1x = (float)(kx + 1) * prm.key_w, p1y = (float)(ky + 1) * prm.key_h;
+            const float rx = fminf(p0x, p1x), ry = fminf(p0y, p1y);
+            const float rw = fmaxf(p0x, p1x) - rx, rh = fmaxf(p0y, p1y) - ry;
+            const float inv_area = 1.0f / (rw * rh);
+            const float x2 = rx + rw, y2 = ry + rh;
+            const float rx1 = x2 - t.x, ry1 = y2 - t.y, rx2 = t.x - rx, ry2 = t.y - ry;
+            h.sw[k] = make_float4(rx1 * ry1 * inv_area, rx1 * ry2 * inv_area, rx2 * ry2 * inv_area, rx2 * ry1 * inv_area);
+            h.si00[k] = (uint16_t)(2 * (ky * cols + kx));
+        }
+        // cells by falling population: the order the chains are dealt to the warps in
+        for (int c = tid; c < cells; c += T2)
+        {
+            const int mine = h.cell_cnt[c];
+            int rank = 0;
+            for (int o = 0; o < cells; o++)
+            {
+                const int other = h.cell_cnt[o];
+                rank += (other > mine) || (other == mine && o < c);
+            }
+            h.chain_cell[rank] = (uint16_t)c;
+        }
+        __syncthreads();
+
+        // ---- r <- b  (temporal rows: ts * x_prev, similarity rows: 0, feature rows: the matched point)
+#pragma unroll
+        for (int sl = 0; sl < SN; sl++)
+        {
+            const int u = tid + sl * T2;
+            if (u < n) r[u] = ts * x[u];
+        }
+#pragma unroll
+        for (int sl = 0; sl < SS; sl++)
+        {
+            const int k = tid + sl * T2;
+            if (k < S) r[n + k] = 0.0f;
+        }
+        float2* const rf = reinterpret_cast<float2*>(r + NS);
+        const float2* const p2 = reinterpret_cast<const float2*>(p);
+        const float2* const x2v = reinterpret_cast<const float2*>(x);
+#pragma unroll
+        for (int sl = 0; sl < SF; sl++)
+        {
+            const int k = tid + sl * T2;
+            if (k < N) rf[k] = dst[h.forder[k]];
+        }
+        __syncthreads();
+        // ---- LeastSquareDiagonalPreconditioner, |A^T b|^2
+        transpose_product<true>(h, [&](int col, float d) { h.invd[col] = d > 0.0f ? 1.0f / d : 1.0f; });
+        __syncthreads();
+        float zz = 0.0f;
+        transpose_product<false>(h, [&](int, float z) { zz += z * z; });
+        const float rhs_norm2 = block_sum1(zz, red1);
+        // ---- residual = b - A x  (every thread its own rows)
+#pragma unroll
+        for (int sl = 0; sl < SN; sl++)
+        {
+            const int u = tid + sl * T2;
+            if (u < n) r[u] = r[u] - ts * x[u];
+        }
+#pragma unroll
+        for (int sl = 0; sl < SS; sl++)
+        {
+            const int k = tid + sl * T2;
+            if (k < S)
+            {
+                const ushort4 ci = reinterpret_cast<const ushort4*>(h.sim_col)[k];
+                const float4 cw = reinterpret_cast<const float4*>(h.sim_val)[k];
+                r[n + k] = r[n + k] - (cw.x * x[ci.x] + cw.y * x[ci.y] + cw.z * x[ci.z] + cw.w * x[ci.w]);
+            }
+        }
+#pragma unroll
+        for (int sl = 0; sl < SF; sl++)
+        {
+            const int k = tid + sl * T2;
+            if (k < N)
+            {
+                const float4 w = h.sw[k];
+                const int a00 = h.si00[k] >> 1, a01 = a00 + cols;
+                const float2 v00 = x2v[a00], v10 = x2v[a00 + 1], v01 = x2v[a01], v11 = x2v[a01 + 1];
+                float2 b = rf[k];
+                b.x = b.x - (w.x * v00.x + w.y * v01.x + w.z * v11.x + w.w * v10.x);
+                b.y = b.y - (w.x * v00.y + w.y * v01.y + w.z * v11.y + w.w * v10.y);
+                rf[k] = b;
+            }
+        }
+        __syncthreads();
+
+        if (rhs_norm2 == 0.0f)
+        {
+            for (int i = tid; i < n; i += T2) x[i] = 0.0f;
+        }
+        else
+        {
+            const float threshold = FLT_EPSILON * FLT_EPSILON * rhs_norm2;
+            float ss = 0.0f, sz = 0.0f;
+            transpose_product<false>(h, [&](int col, float v) {
+                h.s[col] = v;
+                const float z = h.invd[col] * v;
+                p[col] = z;
+                ss += v * v;
+                sz += v * z;
+            });
+            const float2 t0 = block_sum2(ss, sz, red2);  // (its barrier also completes p)
+            float abs_new = t0.y;
+            if (!(t0.x < threshold))
+            {
+                const int max_iters = 2 * n;
+                while (iterations < max_iters)
+                {
+                    // q = A p (kept in registers: the thread owns the same rows in the residual update)
+                    float qn[SN], qs[SS], qfx[SF], qfy[SF];
+                    float qq = 0.0f;
+#pragma unroll
+                    for (int sl = 0; sl < SN; sl++)
+                    {
+                        const int u = tid + sl * T2;
+                        qn[sl] = 0.0f;
+                        if (u < n)
+                        {
+                            const float v = ts * p[u];
+                            qn[sl] = v;
+                            qq += v * v;
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < SS; sl++)
+                    {
+                        const int k = tid + sl * T2;
+                        qs[sl] = 0.0f;
+                        if (k < S)
+                        {
+                            const ushort4 ci = reinterpret_cast<const ushort4*>(h.sim_col)[k];
+                            const float4 cw = reinterpret_cast<const float4*>(h.sim_val)[k];
+                            const float v = cw.x * p[ci.x] + cw.y * p[ci.y] + cw.z * p[ci.z] + cw.w * p[ci.w];
+                            qs[sl] = v;
+                            qq += v * v;
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < SF; sl++)
+                    {
+                        const int k = tid + sl * T2;
+                        qfx[sl] = 0.0f; qfy[sl] = 0.0f;
+                        if (k < N)
+                        {
+                            const float4 w = h.sw[k];
+                            const int a00 = h.si00[k] >> 1, a01 = a00 + cols;
+                            const float2 v00 = p2[a00], v10 = p2[a00 + 1], v01 = p2[a01], v11 = p2[a01 + 1];
+                            const float vx = w.x * v00.x + w.y * v01.x + w.z * v11.x + w.w * v10.x;
+                            const float vy = w.x * v00.y + w.y * v01.y + w.z * v11.y + w.w * v10.y;
+                            qfx[sl] = vx; qfy[sl] = vy;
+                            qq += vx * vx;
+                            qq += vy * vy;
+                        }
+                    }
+                    const float alpha = abs_new / block_sum1(qq, red1);
+                    // x += alpha p ; residual -= alpha q
+#pragma unroll
+                    for (int sl = 0; sl < SN; sl++)
+                    {
+                        const int u = tid + sl * T2;
+                        if (u < n)
+                        {
+                            x[u] += alpha * p[u];
+                            r[u] -= alpha * qn[sl];
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < SS; sl++)
+                    {
+                        const int k = tid + sl * T2;
+                        if (k < S) r[n + k] -= alpha * qs[sl];
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < SF; sl++)
+                    {
+                        const int k = tid + sl * T2;
+                        if (k < N)
+                        {
+                            float2 b = rf[k];
+                            b.x -= alpha * qfx[sl];
+                            b.y -= alpha * qfy[sl];
+                            rf[k] = b;
+                        }
+                    }
+                    __syncthreads();
+                    // s = A^T residual ; z = M^-1 s
+                    ss = 0.0f; sz = 0.0f;
+                    transpose_product<false>(h, [&](int col, float v) {
+                        h.s[col] = v;
+                        ss += v * v;
+                        sz += v * (h.invd[col] * v);
+                    });
+                    const float2 t1 = block_sum2(ss, sz, red2);
+                    if (t1.x < threshold) break;
+                    const float beta = t1.y / abs_new;
+                    abs_new = t1.y;
+                    if (tid < COLT)
+                        for (int col = tid; col < n; col += COLT) p[col] = h.invd[col] * h.s[col] + beta * p[col];
+                    iterations++;
+                    __syncthreads();
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- results: new state, mesh copy for the host, inlier mask (FrameTracker.cpp:279-300)
+        for (int i = tid; i < n; i += T2)
+        {
+            const float v = x[i];
+            state[i] = v;
+            mesh_out[i] = v;
+        }
+        for (int k = tid; k < N; k += T2)
+        {
+            const float4 w = h.sw[k];
+            const int i = h.forder[k];
+            const int i00 = h.si00[k], i10 = i00 + 2, i01 = i00 + 2 * cols, i11 = i01 + 2;
+            // row product in the reference's triplet order i00, i01, i11, i10
+            const float ex = ((w.x * x[i00] + w.y * x[i01]) + w.z * x[i11]) + w.w * x[i10];
+            const float ey = ((w.x * x[i00 + 1] + w.y * x[i01 + 1]) + w.z * x[i11 + 1]) + w.w * x[i10 + 1];
+            const float2 m = dst[i];
+            mask[i] = (fabsf(ex - m.x) + fabsf(ey - m.y)) < prm.acceptance ? 1 : 0;
+        }
+    }
+    if (tid == 0)
+    {
+        hdr->solved = solve ? 1 : 0;
+        hdr->iterations = iterations;
+        hdr->n = N;
+        hdr->pad = 0;
+    }
+    __syncthreads();  // the block's global writes (mask, header, mesh) are visible to all of its threads
+    if (res_host) copy16(res_dev, res_host, (int)sizeof(MeshSolveResult) + (solve ? 4 * n : 0));
+    if (out.host)
+    {
+        const int tracked = tp->n;
+        copy16(out.dev, out.host, tracked * (int)sizeof(float2));
+        copy16(out.dev + out.off_status, out.host + out.off_status, tracked);
+        if (solve) copy16(out.dev + out.off_mask, out.host + out.off_mask, N);
+    }
+}
+
+
+// The slot triple (unknowns, similarity rows, features per thread) the kernel is instantiated for.
+inline int slot_variant(int n, int S, int cap)
+{
+    if (n <= T2 && S <= T2 && cap <= T2) return 0;
+    if (n <= T2 && S <= T2 && cap <= 3 * T2) return 1;
+    return 2;
+}
+
+inline cudaError_t set_smem(int variant, size_t bytes)
+{
+    const int b = static_cast<int>(bytes);
+    switch (variant)
+    {
+    case 0: return cudaFuncSetAttribute(k_mesh_cgls2<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    case 1: return cudaFuncSetAttribute(k_mesh_cgls2<1, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    default: return cudaFuncSetAttribute(k_mesh_cgls2<MAX_SLOT_N, MAX_SLOT_S, MAX_SLOT_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    }
+}
+
+template <typename... Args>
+inline void launch(int variant, size_t smem, cudaStream_t cs, Args... args)
+{
+    switch (variant)
+    {
+    case 0: k_mesh_cgls2<1, 1, 1><<<1, T2, smem, cs>>>(args...); break;
+    case 1: k_mesh_cgls2<1, 1, 3><<<1, T2, smem, cs>>>(args...); break;
+    default: k_mesh_cgls2<MAX_SLOT_N, MAX_SLOT_S, MAX_SLOT_F><<<1, T2, smem, cs>>>(args...); break;
+    }
+}
+
+}  // namespace v2
+
 }  // namespace
 
 bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaStream_t cs, cudaError_t* err)
@@ -582,20 +1136,37 @@ bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaSt
     const int cells = (sys.mesh_cols - 1) * (sys.mesh_rows - 1);
     n_unknowns = 0;
     if (sys.mesh_cols < 2 || sys.mesh_rows < 2 || n + S > 65535 || feature_capacity > 65535 || cells > 65535) return false;
-    const Carve cv(n, S, nnz, cells, feature_capacity);
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cv.total > static_cast<size_t>(max_smem)) return false;
-    if ((*err = cudaFuncSetAttribute(k_mesh_cgls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total)) != cudaSuccess)
-        return false;
 
-    // column-major copy of the similarity rows (stable: ascending row inside every column)
+    // column-major copy of the similarity rows (stable: ascending row inside every column).  For the re-tiled kernel
+    // every column's list is padded to whole groups of four with zero weights on the column's own (temporal) row.
+    std::vector<int> count(n, 0);
+    for (int k = 0; k < nnz; k++) count[sys.col[k]]++;
+    const char* force_v1 = std::getenv("LVKB200_MESH_V1");
+    int padded = 0;
+    for (int c = 0; c < n; c++) padded += (count[c] + 3) / 4 * 4;
+    // the re-tiled kernel for every sparse system within its per-thread slot limits (LVKB200_MESH_V1=1: the round-1 kernel)
+    const v2::Carve2 cv2(n, S, padded, cells, feature_capacity);
+    const bool use_v2 = n != 8 && n <= v2::MAX_SLOT_N * v2::T2 && S <= v2::MAX_SLOT_S * v2::T2 &&
+                        feature_capacity <= v2::MAX_SLOT_F * v2::T2 && 4 * cells + 1 <= 65535 && (n + S) % 2 == 0 &&
+                        cv2.total <= static_cast<size_t>(max_smem) && !(force_v1 && force_v1[0] == '1');
+    const int cn = use_v2 ? padded : nnz;  // entries of the column-major copy
+    const Carve cv1(n, S, nnz, cells, feature_capacity);
+    const size_t smem_needed = use_v2 ? cv2.total : cv1.total;
+    if (smem_needed > static_cast<size_t>(max_smem)) return false;
+    const int slots_wanted = use_v2 ? v2::slot_variant(n, S, feature_capacity) : -1;
+    *err = use_v2 ? v2::set_smem(slots_wanted, smem_needed)
+                  : cudaFuncSetAttribute(k_mesh_cgls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed);
+    if (*err != cudaSuccess) return false;
+
     std::vector<int> ptr(n + 1, 0);
-    for (int k = 0; k < nnz; k++) ptr[sys.col[k] + 1]++;
-    for (int c = 0; c < n; c++) ptr[c + 1] += ptr[c];
-    std::vector<uint16_t> crow(nnz), scol(nnz);
-    std::vector<float> cval(nnz);
+    for (int c = 0; c < n; c++) ptr[c + 1] = ptr[c] + (use_v2 ? (count[c] + 3) / 4 * 4 : count[c]);
+    std::vector<uint16_t> crow(cn), scol(nnz);
+    std::vector<float> cval(cn, 0.0f);
+    for (int c = 0; c < n; c++)
+        for (int k = ptr[c]; k < ptr[c + 1]; k++) crow[k] = static_cast<uint16_t>(c);  // padding: 0 * r[c]
     std::vector<int> fill(ptr.begin(), ptr.end() - 1);
     for (int r = 0; r < S; r++)
         for (int k = 4 * r; k < 4 * r + 4; k++)
@@ -606,16 +1177,16 @@ bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaSt
             scol[k] = static_cast<uint16_t>(sys.col[k]);
         }
 
-    // one blob: [sim_val f32 x nnz | csc_val f32 x nnz | csc_ptr i32 x (n+1) | sim_col u16 x nnz | csc_row u16 x nnz]
-    const size_t o_simval = 0, o_cscval = o_simval + 4 * (size_t)nnz, o_ptr = o_cscval + 4 * (size_t)nnz,
+    // one blob: [sim_val f32 x nnz | csc_val f32 x cn | csc_ptr i32 x (n+1) | sim_col u16 x nnz | csc_row u16 x cn]
+    const size_t o_simval = 0, o_cscval = o_simval + 4 * (size_t)nnz, o_ptr = o_cscval + 4 * (size_t)cn,
                  o_simcol = o_ptr + 4 * ((size_t)n + 1), o_cscrow = o_simcol + 2 * (size_t)nnz,
-                 bytes = o_cscrow + 2 * (size_t)nnz;
+                 bytes = o_cscrow + 2 * (size_t)cn;
     std::vector<uint8_t> blob(bytes);
     std::memcpy(blob.data() + o_simval, sys.val.data(), 4 * (size_t)nnz);
-    std::memcpy(blob.data() + o_cscval, cval.data(), 4 * (size_t)nnz);
+    std::memcpy(blob.data() + o_cscval, cval.data(), 4 * (size_t)cn);
     std::memcpy(blob.data() + o_ptr, ptr.data(), 4 * ((size_t)n + 1));
     std::memcpy(blob.data() + o_simcol, scol.data(), 2 * (size_t)nnz);
-    std::memcpy(blob.data() + o_cscrow, crow.data(), 2 * (size_t)nnz);
+    std::memcpy(blob.data() + o_cscrow, crow.data(), 2 * (size_t)cn);
     if ((*err = d_static.ensure(bytes + 16)) != cudaSuccess) return false;
     if ((*err = d_state.ensure(4 * (size_t)n)) != cudaSuccess) return false;
     const size_t out_bytes = sizeof(MeshSolveResult) + 4 * (size_t)n + 16;
@@ -628,7 +1199,7 @@ bool MeshCgls::configure(const MeshStaticRows& sys, int feature_capacity, cudaSt
     if ((*err = cudaStreamSynchronize(cs)) != cudaSuccess) return false;
     const bool resized = mesh_cols != sys.mesh_cols || mesh_rows != sys.mesh_rows;
     mesh_cols = sys.mesh_cols; mesh_rows = sys.mesh_rows;
-    n_sim = S; csc_nnz = nnz; capacity = feature_capacity; smem_bytes = cv.total;
+    n_sim = S; csc_nnz = cn; capacity = feature_capacity; smem_bytes = smem_needed; slots = slots_wanted;
     n_unknowns = n;
     if (resized && (*err = cudaMemsetAsync(d_state.ptr, 0, 4 * (size_t)n, cs)) != cudaSuccess) { n_unknowns = 0; return false; }
     return true;
@@ -651,16 +1222,20 @@ cudaError_t MeshCgls::launch(cudaStream_t cs, const MeshSolveParams& prm, const 
                              const int* d_n, const TrackParams* d_params, uint8_t* d_mask, const TrackOutCopy& out)
 {
     const uint8_t* b = d_static.as<uint8_t>();
-    const size_t nnz = static_cast<size_t>(csc_nnz), n = static_cast<size_t>(n_unknowns);
+    const size_t nnz = 4 * static_cast<size_t>(n_sim), cn = static_cast<size_t>(csc_nnz), n = static_cast<size_t>(n_unknowns);
     MeshSys sys{};
     sys.cols = mesh_cols; sys.rows = mesh_rows; sys.n = n_unknowns; sys.S = n_sim; sys.csc_nnz = csc_nnz; sys.cap = capacity;
     sys.sim_val = reinterpret_cast<const float*>(b);
     sys.csc_val = reinterpret_cast<const float*>(b + 4 * nnz);
-    sys.csc_ptr = reinterpret_cast<const int*>(b + 8 * nnz);
-    sys.sim_col = reinterpret_cast<const uint16_t*>(b + 8 * nnz + 4 * (n + 1));
-    sys.csc_row = reinterpret_cast<const uint16_t*>(b + 8 * nnz + 4 * (n + 1) + 2 * nnz);
-    k_mesh_cgls<<<1, T, smem_bytes, cs>>>(sys, prm, d_src, d_dst, d_n, d_params, d_state.as<float>(), d_mask,
-                                          d_out.as<uint8_t>(), h_out.device_view<uint8_t>(), out);
+    sys.csc_ptr = reinterpret_cast<const int*>(b + 4 * nnz + 4 * cn);
+    sys.sim_col = reinterpret_cast<const uint16_t*>(b + 4 * nnz + 4 * cn + 4 * (n + 1));
+    sys.csc_row = reinterpret_cast<const uint16_t*>(b + 4 * nnz + 4 * cn + 4 * (n + 1) + 2 * nnz);
+    if (slots >= 0)
+        v2::launch(slots, smem_bytes, cs, sys, prm, d_src, d_dst, d_n, d_params, d_state.as<float>(), d_mask,
+                   d_out.as<uint8_t>(), h_out.device_view<uint8_t>(), out);
+    else
+        k_mesh_cgls<<<1, T, smem_bytes, cs>>>(sys, prm, d_src, d_dst, d_n, d_params, d_state.as<float>(), d_mask,
+                                              d_out.as<uint8_t>(), h_out.device_view<uint8_t>(), out);
     count_launches(1);
     return cudaGetLastError();
 }

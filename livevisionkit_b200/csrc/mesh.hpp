@@ -68,6 +68,7 @@ public:
 private:
     int n_unknowns = 0, n_sim = 0, mesh_cols = 0, mesh_rows = 0, capacity = 0, csc_nnz = 0;
     size_t smem_bytes = 0;
+    int slots = -1;  // >= 0: k_mesh_cgls2 (1024 threads, chains) in that slot variant; -1: k_mesh_cgls
     DeviceBuffer d_static, d_state, d_out;
     PinnedBuffer h_out;
 };

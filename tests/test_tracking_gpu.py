@@ -356,12 +356,16 @@ def test_local_motions_vs_oracle(gpu_stream, oracle, monkeypatch):
     s.close()
 
 
-@pytest.mark.parametrize("mesh", ["field16x16", "default2x2_on_device"])
+@pytest.mark.parametrize("mesh", ["field16x16", "field16x16_round1_kernel", "default2x2_on_device"])
 def test_local_motions_device_solver_vs_oracle(gpu_stream, oracle, mesh, monkeypatch):
-    """K6c k_mesh_cgls (one CTA, whole LSCG solve in shared memory) against the sequential CPU restatement of Eigen's
-    LeastSquaresConjugateGradient (oracle/lscg_ref.c): same iteration, different float32 summation order."""
+    """K6c k_mesh_cgls2 / k_mesh_cgls (one CTA, whole LSCG solve in shared memory) against the sequential CPU restatement
+    of Eigen's LeastSquaresConjugateGradient (oracle/lscg_ref.c): same iteration, different float32 summation order.
+    The 16x16 mesh runs on the re-tiled 1024-thread kernel by default and on the round-1 kernel (which remains the
+    solver of the 2x2 mesh and of meshes beyond the re-tiled kernel's slot limits) behind LVKB200_MESH_V1=1."""
     import livevisionkit_b200 as L
-    if mesh == "field16x16":
+    if mesh == "field16x16_round1_kernel":
+        monkeypatch.setenv("LVKB200_MESH_V1", "1")
+    if mesh.startswith("field16x16"):
         sg, so = L.StabilizationFilterSettings.obs_field_preset(), oracle.StabilizationSettings.obs_field_preset()
     else:  # the library-default 2x2 mesh: on the device by default
         sg, so = L.StabilizationFilterSettings(), oracle.StabilizationSettings()
