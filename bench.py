@@ -505,7 +505,10 @@ def rooflines(wl, remap_us, sm_mhz):
     alg_bytes = 6.0 * wl.width * wl.height
     achieved = alg_bytes / (remap_us * 1e-6) / 1e9 if remap_us > 0 else 0.0
     traffic, instr_px, src = _kernel_facts(wl.res)
-    hbm = {"bound": "hbm", "kernel": "k_easu_remap_fast<homography>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # the 16x16 "Vector Field" mesh is warped by the kernel's mesh variant (per-pixel bilinear lookup of the offset field
+    # in front of the same EASU body); the committed instruction count is the homography variant's, a lower bound for it
+    kernel = "k_easu_remap_fast<mesh>" if wl.preset == "F" else "k_easu_remap_fast<homography>"
+    hbm = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind, "avg_kernel_us": remap_us,
            "algorithmic_bytes_per_launch": alg_bytes,
            "note": "EASU is bound by instruction issue / FP32 pipe / shared-memory bandwidth, not by HBM (DRAM ~2 % busy): "
@@ -516,7 +519,7 @@ def rooflines(wl, remap_us, sm_mhz):
         warp_instr = instr_px * wl.width * wl.height / 32.0
         peak_ips = 148 * 4 * clk  # warp-instructions per second: SMs x schedulers x clock
         ach = warp_instr / (remap_us * 1e-6)
-        issue = {"bound": "issue", "kernel": "k_easu_remap_fast<homography>", "achieved": ach / 1e9, "peak": peak_ips / 1e9,
+        issue = {"bound": "issue", "kernel": kernel, "achieved": ach / 1e9, "peak": peak_ips / 1e9,
                  "unit": "Gwarp-instr/s", "frac": ach / peak_ips, "thread_instructions_per_pixel": instr_px,
                  "warp_instructions_per_launch": warp_instr, "sm_mhz": clk / 1e6, "source": src}
     return hbm, issue

@@ -582,16 +582,19 @@ __global__ void __launch_bounds__(T, 1)
 // walking the features of its four cells: the warp runs as long as its most crowded vertex, ~26 visits of 15
 // instructions), 22 % in the row products (two integer divisions and a three-way branch per row unit), 9 % in block
 // reductions.  Here:
-//   * 1024 threads.  The features are renumbered in cell order once per frame (weights and vertex index stored at the
-//     sorted position), so every per-iteration access is contiguous and division-free.
-//   * A^T r is split: warps 16-31 sum CHAINS - one (cell, corner weight) pair = sum over the cell's features of
-//     w_corner * (r_x, r_y) - with the cells dealt to warps in order of population (eight equally crowded cells per
-//     warp, no lane waits for a crowded neighbour); warps 0-15 meanwhile walk the similarity columns; after one
-//     barrier a column adds its four chain sums.  ~3 200 balanced visits instead of 16 warps x 26.
-//   * q = A p stays in registers between the product and the residual update (a thread owns the same rows in both).
-// Same iteration as before (Eigen's LSCG, oracle/lscg_ref.c); the float32 summation order of the dot products and of
-// the per-vertex gather differs again (tests: same tolerances as the kernel above).  Meshes beyond the slot limits
-// below, and the 2x2 mesh, stay on k_mesh_cgls.
+//   * 1024 threads.  The features are renumbered in cell order once per frame (one warp, match.any on the cell index;
+//     weights and vertex index stored at the sorted position), so every per-iteration access is contiguous and
+//     division-free.
+//   * A^T r is split: warps 16-31 sum CHAINS - per cell, the four corner-weighted sums of its features' (r_x, r_y),
+//     two lanes per cell (even / odd features), the cells dealt to the warps in order of population so that no lane
+//     waits for a crowded neighbour; warps 0-15 meanwhile walk the similarity columns (lists padded to groups of
+//     four with zero weights: LDS.128); after one barrier a column adds its four chain sums.
+//   * q = A p stays in registers between the product and the residual update (a thread owns the same rows in both);
+//     the kernel is instantiated per (unknowns, similarity rows, features) a thread may own.
+// 396 us, 12 400 warp-instructions per iteration (profiles/r02_mesh_cgls2_lines.txt).  Same iteration as before
+// (Eigen's LSCG, oracle/lscg_ref.c); the float32 summation order of the dot products and of the per-vertex gather
+// differs again (tests: same tolerances as the kernel above).  Meshes beyond the slot limits below, and the 2x2 mesh,
+// stay on k_mesh_cgls.
 namespace v2
 {
 
@@ -672,13 +675,18 @@ __device__ __forceinline__ void transpose_product(const Sh& h, Emit emit)
     if (tid >= COLT)
     {
         const float2* uf = reinterpret_cast<const float2*>(h.r + h.n + h.S);  // (x row, y row) of a feature: n + S is even
-        for (int j = tid - COLT; j < h.cells; j += T2 - COLT)
+        // two lanes per cell: the even and the odd features of its (sorted) list; whole warps stay in the loop for the
+        // exchange (2 * cells is even: a pair is live or idle together)
+        const int lane = tid & 31;
+        for (int j0 = tid - COLT - lane; j0 < 2 * h.cells; j0 += T2 - COLT)
         {
-            const int cell = h.chain_cell[j];
-            const int k1 = h.cell_start[cell + 1];
+            const int j = j0 + lane;
+            const bool live = j < 2 * h.cells;
+            const int cell = live ? h.chain_cell[j >> 1] : 0;
+            const int k1 = live ? h.cell_start[cell + 1] : 0;
             float2 c0 = make_float2(0.0f, 0.0f), c1 = c0, c2 = c0, c3 = c0;
 #pragma unroll 2
-            for (int k = h.cell_start[cell]; k < k1; k++)
+            for (int k = live ? h.cell_start[cell] + (j & 1) : 0; k < k1; k += 2)
             {
                 const float4 w = h.sw[k];
                 if (SQUARE)
@@ -694,10 +702,16 @@ __device__ __forceinline__ void transpose_product(const Sh& h, Emit emit)
                     c3.x += w.w * uv.x; c3.y += w.w * uv.y;
                 }
             }
+            // the even lane writes corners 0 and 1, the odd lane corners 2 and 3: each sends the partner's half
+            const bool odd = (j & 1) != 0;
             if (SQUARE) { c0.y = c0.x; c1.y = c1.x; c2.y = c2.x; c3.y = c3.x; }
-            float4* const out = reinterpret_cast<float4*>(h.P + 4 * cell);
-            out[0] = make_float4(c0.x, c0.y, c1.x, c1.y);
-            out[1] = make_float4(c2.x, c2.y, c3.x, c3.y);
+            float4 give = odd ? make_float4(c0.x, c0.y, c1.x, c1.y) : make_float4(c2.x, c2.y, c3.x, c3.y);
+            const float4 keep = odd ? make_float4(c2.x, c2.y, c3.x, c3.y) : make_float4(c0.x, c0.y, c1.x, c1.y);
+            give.x = __shfl_xor_sync(0xffffffffu, give.x, 1); give.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+            give.z = __shfl_xor_sync(0xffffffffu, give.z, 1); give.w = __shfl_xor_sync(0xffffffffu, give.w, 1);
+            if (live)
+                reinterpret_cast<float4*>(h.P + 4 * cell)[odd ? 1 : 0] =
+                    make_float4(keep.x + give.x, keep.y + give.y, keep.z + give.z, keep.w + give.w);
         }
     }
     else
@@ -839,15 +853,47 @@ __global__ void __launch_bounds__(T2, 1)
             }
         }
         __syncthreads();
-        // ---- features into cell order (stable: ascending index inside a cell), weights at the sorted position
-        for (int i = tid; i < N; i += T2)
+        // ---- features into cell order (stable: ascending index inside a cell).  One warp walks the features 32 at a
+        // time: lanes of the same cell find each other with match.any and take consecutive places behind the cell's
+        // running fill mark - O(N / 32) steps instead of an O(N) comparison loop per feature.
+        if (tid < 32)
         {
-            const uint16_t me = h.fcell[i];
-            int rank = 0;
-            for (int j = 0; j < i; j++) rank += (h.fcell[j] == me);
-            const int k = h.cell_start[me] + rank;
-            h.forder[k] = (uint16_t)i;
-            // barycentric weights of the point in its cell (Math.tpp:247-265)
+            int* const fill = reinterpret_cast<int*>(h.P);  // (the chain sums are not in use yet)
+            for (int c = tid; c < cells; c += 32) fill[c] = h.cell_start[c];
+            __syncwarp();
+            for (int base = 0; base < N; base += 32)
+            {
+                const int i = base + tid;
+                const unsigned cell = i < N ? h.fcell[i] : 0xFFFFu;  // the lanes behind the last feature: a group of their own
+                const unsigned peers = __match_any_sync(0xffffffffu, cell);
+                const int rank = __popc(peers & ((1u << tid) - 1u));
+                if (i < N) h.forder[fill[cell] + rank] = (uint16_t)i;
+                __syncwarp();
+                if (i < N && rank == 0) fill[cell] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        else
+        {
+            // cells by falling population: the order the chains are dealt to the warps in
+            for (int c = tid - 32; c < cells; c += T2 - 32)
+            {
+                const int mine = h.cell_cnt[c];
+                int rank = 0;
+                for (int o = 0; o < cells; o++)
+                {
+                    const int other = h.cell_cnt[o];
+                    rank += (other > mine) || (other == mine && o < c);
+                }
+                h.chain_cell[rank] = (uint16_t)c;
+            }
+        }
+        __syncthreads();
+        // barycentric weights of every point in its cell (Math.tpp:247-265), at the sorted position
+        for (int k = tid; k < N; k += T2)
+        {
+            const int i = h.forder[k];
+            const int me = h.fcell[i];
             const int ky = me / gw, kx = me - ky * gw;
             const float2 t = src[i];
             const float p0x = (float)kx * prm.key_w, p0y = (float)ky * prm.key_h;
@@ -859,18 +905,6 @@ __global__ void __launch_bounds__(T2, 1)
             const float rx1 = x2 - t.x, ry1 = y2 - t.y, rx2 = t.x - rx, ry2 = t.y - ry;
             h.sw[k] = make_float4(rx1 * ry1 * inv_area, rx1 * ry2 * inv_area, rx2 * ry2 * inv_area, rx2 * ry1 * inv_area);
             h.si00[k] = (uint16_t)(2 * (ky * cols + kx));
-        }
-        // cells by falling population: the order the chains are dealt to the warps in
-        for (int c = tid; c < cells; c += T2)
-        {
-            const int mine = h.cell_cnt[c];
-            int rank = 0;
-            for (int o = 0; o < cells; o++)
-            {
-                const int other = h.cell_cnt[o];
-                rank += (other > mine) || (other == mine && o < c);
-            }
-            h.chain_cell[rank] = (uint16_t)c;
         }
         __syncthreads();
 
