@@ -9,3 +9,14 @@ timeout 400 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_k20.json 2>/dev/null
 timeout 200 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference_k20.json 2>/dev/null
 timeout 100 python tools/bench_rows.py --res 4k 2>&1 | head -1 | cut -c1-160
+timeout 200 python bench.py --preset F --steps 100 --warmup 20 --no-extra-configs --no-cpu-baseline > gpurun_out/bench_F.json 2>/dev/null
+timeout 200 python bench.py --preset D --steps 100 --warmup 20 --no-extra-configs --no-cpu-baseline > gpurun_out/bench_D.json 2>/dev/null
+python - <<'PY'
+import json
+for n in ("bench_default", "bench_k20", "bench_reference_k20", "bench_F", "bench_D"):
+    try:
+        j = json.loads(open(f"gpurun_out/{n}.json").read().strip().splitlines()[-1])
+        print(n, "value", round(j["value"], 1), "e2e", round(j["e2e"]["value"], 1), "launches", j.get("gpu_launches"))
+    except Exception as e:
+        print(n, "unreadable", e)
+PY
