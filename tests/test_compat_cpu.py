@@ -9,7 +9,12 @@ and VideoEditor modules link unchanged".  OpenCV, libobs and Qt are absent here,
       VideoProcessor::print_filter_timings / log_timing_data (Modules/VideoEditor/VideoProcessor.cpp) — extracted from
       /root/reference at test time (never copied into the repo), behind stubs for libobs / the plugin's helpers
       (tests/cpp/reference_callsite_stubs.hpp), compiled UNCHANGED with -Werror;
-  (3) tests/cpp/test_compat_types.cpp — run: lvk::Time / Stopwatch statistics, Unique ids, shallow VideoFrame copies."""
+  (3) tests/cpp/test_compat_types.cpp — run: lvk::Time / Stopwatch statistics, Unique ids, shallow VideoFrame copies;
+  (4) the OBS call site of lvk::DeblockingFilter (ADBFilter.cpp / .hpp, BASELINE config 5's first stage), same method;
+  (5) the VideoEditor's filter factory: the reference's own FilterParser.hpp / OptionParser.hpp included IN PLACE from
+      /root/reference with `#include <LiveVisionKit.hpp>` resolved to lvk-compat (tests/cpp/lvk_include), plus the
+      add_filter<lvk::StabilizationFilter, ...> / add_filter<lvk::DeblockingFilter, ...> registrations of
+      VideoIOConfiguration.cpp — C++20, -Werror."""
 import os
 import re
 import shutil
@@ -25,8 +30,8 @@ LINK = [f"-L{LIBDIR}", "-l:liblvkb200.so", f"-Wl,-rpath,{LIBDIR}"]
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
 
 
-def _compile(src, exe, extra=()):
-    cmd = ["g++", "-std=c++17", "-O0", "-Werror", *extra, src, "-o", exe, *LINK]
+def _compile(src, exe, extra=(), std="c++17"):
+    cmd = ["g++", f"-std={std}", "-O0", "-Werror", *extra, src, "-o", exe, *LINK]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-4000:]
 
@@ -72,4 +77,63 @@ def test_reference_lines_compile_unchanged(tmp_path):
     unit = tmp_path / "reference_lines.cpp"
     unit.write_text('#include "%s"\nnamespace lvk\n{\n%s\n%s\n%s\n%s\n}\nint main() { return 0; }\n'
                     % (os.path.join(ROOT, "tests", "cpp", "reference_callsite_stubs.hpp"), constants, decl, bodies, timings))
-    _compile(str(unit), str(tmp_path / "reference_lines"), ["-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv")])
+    for std in ("c++17", "c++20"):  # the reference builds as C++20; lvk-compat itself only needs C++17
+        _compile(str(unit), str(tmp_path / "reference_lines"), ["-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv")], std=std)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_deblocking_callsite_compiles_unchanged(tmp_path):
+    """The OBS call site of lvk::DeblockingFilter (BASELINE config 5's first stage): ADBFilter::configure / ADBFilter /
+    filter / draw_debug_hud (Modules/OBS-Plugin/Sources/Enhancement/ADBFilter.cpp) and the class declaration from
+    ADBFilter.hpp, extracted at test time and compiled unchanged against lvk-compat with -Werror."""
+    adb_cpp = open(os.path.join(REF, "Modules/OBS-Plugin/Sources/Enhancement/ADBFilter.cpp")).read()
+    adb_hpp = open(os.path.join(REF, "Modules/OBS-Plugin/Sources/Enhancement/ADBFilter.hpp")).read()
+    constants = _function(adb_cpp, "constexpr auto PROP_STRENGTH =", "obs_properties_t* ADBFilter::Properties()")
+    a = adb_hpp.index("class ADBFilter : public VisionFilter")
+    decl = adb_hpp[a:adb_hpp.index("};", a) + 2]
+    bodies = _function(adb_cpp, "void ADBFilter::configure(obs_data_t* settings)", "bool ADBFilter::validate() const")
+    for needle in ("m_Filter.reconfigure([&](DeblockingFilterSettings& settings)", "settings.detection_levels =",
+                   "m_Filter.set_timing_samples(TIMING_SAMPLES)", "m_Filter.apply(frame, frame, true)",
+                   "m_Filter.draw_influence(frame)", "m_Filter.apply(frame, frame)",
+                   "m_Filter.timings().average().milliseconds()", "m_Filter.timings().deviation().milliseconds()"):
+        assert needle in bodies, needle
+    unit = tmp_path / "reference_adb_lines.cpp"
+    unit.write_text('#include "%s"\nnamespace lvk\n{\n%s\n%s\n%s\n}\nint main() { return 0; }\n'
+                    % (os.path.join(ROOT, "tests", "cpp", "reference_callsite_stubs.hpp"), constants, decl, bodies))
+    for std in ("c++17", "c++20"):
+        _compile(str(unit), str(tmp_path / "reference_adb_lines"), ["-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv")], std=std)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_editor_filter_parser_compiles_unchanged(tmp_path):
+    """The VideoEditor's filter factory: the reference's OWN FilterParser.hpp / OptionParser.hpp (included in place from
+    /root/reference, `#include <LiveVisionKit.hpp>` resolved to lvk-compat) and the two registrations of
+    VideoIOConfiguration.cpp - `add_filter<lvk::StabilizationFilter, lvk::StabilizationFilterSettings>` (".crop_prop",
+    ".crop_out", ".smoothing" bound to the settings members) and `add_filter<lvk::DeblockingFilter,
+    lvk::DeblockingFilterSettings>` (".levels") - extracted at test time, compiled unchanged with -Werror.  This is the
+    path `lvk-editor in.mp4 out.mp4 -f adb -f vs .cp 0.1` takes to build BASELINE config 5's filter chain: it
+    instantiates std::make_shared<F>() and Configurable<C>::configure through the boundary's class templates."""
+    cfg = open(os.path.join(REF, "Modules/VideoEditor/VideoIOConfiguration.cpp")).read()
+    regs = _function(cfg, "m_FilterParser.add_filter<lvk::StabilizationFilter, lvk::StabilizationFilterSettings>(",
+                     "//---------------------------------------------------------------------------------------------------------------------")
+    regs = regs[:regs.rindex("}")]  # drop the closing brace of the enclosing member function
+    for needle in ("config.corrective_limits.width = crop", "&config.crop_to_stable_region", "&config.predictive_samples",
+                   "add_filter<lvk::DeblockingFilter, lvk::DeblockingFilterSettings>(", "&config.detection_levels"):
+        assert needle in regs, needle
+    unit = tmp_path / "editor_filter_parser.cpp"
+    unit.write_text('#include <FilterParser.hpp>\n'
+                    'struct Registrar\n{\n    clt::FilterParser m_FilterParser;\n    void register_filters()\n    {\n%s\n    }\n};\n'
+                    'int main(int argc, char**)\n{\n'
+                    '    Registrar r;\n'
+                    '    if (argc > 100)  // compiled and linked, not run: constructing a filter opens a CUDA stream\n'
+                    '    {\n'
+                    '        r.register_filters();\n'
+                    '        std::deque<std::string> args{"vs", ".cp", "0.1", ".s", "12"};\n'
+                    '        std::shared_ptr<lvk::VideoFilter> f = r.m_FilterParser.try_parse(args);\n'
+                    '        return f ? 0 : 1;\n'
+                    '    }\n'
+                    '    return 0;\n}\n' % regs)
+    _compile(str(unit), str(tmp_path / "editor_filter_parser"),
+             ["-I" + os.path.join(REF, "Modules/VideoEditor"), "-I" + os.path.join(ROOT, "tests", "cpp", "lvk_include"),
+              "-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv")],
+             std="c++20")  # the reference is a C++20 code base (CMakeLists.txt: CMAKE_CXX_STANDARD 20)
