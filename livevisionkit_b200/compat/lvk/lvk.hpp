@@ -79,12 +79,20 @@ namespace context
         };
 }
 
+// The assertion family of Directives.hpp:46-95: a failed check reports (file, function, text) to the handler and carries
+// on; the range forms report the violated relation ("0 <= x <= 1", "lo < x < hi") like the reference does.
 #ifndef LVK_DISABLE_CHECKS
-#define LVK_ASSERT(assertion) \
-    if (!(assertion)) { lvk::context::assert_handler(__FILE__, __func__, #assertion); }
+#define LVK_COMPAT_CHECK(passes, text) \
+    if (!(passes)) { lvk::context::assert_handler(__FILE__, __func__, text); }
 #else
-#define LVK_ASSERT(assertion)
+#define LVK_COMPAT_CHECK(passes, text)
 #endif
+#define LVK_ASSERT(assertion) LVK_COMPAT_CHECK(assertion, #assertion)
+#define LVK_ASSERT_IF(condition, assertion) LVK_COMPAT_CHECK(!(condition) || (assertion), #assertion)
+#define LVK_ASSERT_01(value) LVK_COMPAT_CHECK(!(value < 0 || value > 1), "0 <= " #value " <= 1")
+#define LVK_ASSERT_01_STRICT(value) LVK_COMPAT_CHECK(!(value <= 0 || value >= 1), "0 < " #value " < 1")
+#define LVK_ASSERT_RANGE(value, min, max) LVK_COMPAT_CHECK(!(value < min || value > max), #min " <= " #value " <= " #max)
+#define LVK_ASSERT_RANGE_STRICT(value, min, max) LVK_COMPAT_CHECK(!(value <= min || value >= max), #min " < " #value " < " #max)
 
 // ---- Utility/Unique.hpp:25-45, Unique.tpp:27-60 -----------------------------------------------------------------------
 struct GlobalScope;
@@ -266,6 +274,29 @@ private:
     bool m_Running = false;
     StreamBuffer<Time> m_History;
     Time m_ElapsedTime{0}, m_StartTime{0}, m_Memory{0};
+};
+
+// ---- Timing/TickTimer.hpp:24-44: a Stopwatch that counts its laps (the editor's frame timer, VideoProcessor.hpp:68) ---
+class TickTimer : public Stopwatch
+{
+public:
+    explicit TickTimer(const uint32_t history = 1) : Stopwatch(history) { LVK_ASSERT(history > 0); }
+    Time tick()  // closes the running lap (into the history) and opens the next one
+    {
+        ++m_Ticks;
+        return m_LastLap = restart();
+    }
+    Time tick(const Time& timestep)  // fixed-rate ticking: the lap is stretched to at least `timestep`
+    {
+        wait_until(timestep);
+        return tick();
+    }
+    uint64_t tick_count() const { return m_Ticks; }
+    void reset_counter() { m_Ticks = 0; }
+    Time delta() const { return m_LastLap; }
+private:
+    uint64_t m_Ticks = 0;
+    Time m_LastLap{0};
 };
 
 // ---- Data/VideoFrame.hpp:25-79 -------------------------------------------------------------------------------------

@@ -71,12 +71,6 @@ struct CSVLogger
     void next() {}
     bool started = false;
 };
-struct TickTimer
-{
-    uint64_t tick_count() const { return 0; }
-    Time average() const { return Time(1000000); }
-    Time deviation() const { return Time(0); }
-};
 class VideoProcessor
 {
 public:

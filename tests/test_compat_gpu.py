@@ -92,3 +92,49 @@ def test_cpp_compat_layer_with_umat_videoframe(tmp_path):
     # the capture path stamps frames 0, 1, ... (VideoFilter.cpp:96-100): outputs are frames 0..3, same pixels as apply()
     assert [int(l[2]) for l in streamed] == expected and [int(l[1]) for l in streamed] == [0, 1, 2, 3]
     assert lines[-1] == ["stream", "4"]
+
+
+EDITOR = os.path.join(ROOT, "oracle", "_ref", "lvk-editor")
+
+
+def _read_raw_clip(path):
+    with open(path, "rb") as f:
+        magic, w, h, _fps, n = f.readline().split()
+        assert magic == b"LVKRAW1"
+        w, h, n = int(w), int(h), int(n)
+        return [np.frombuffer(f.read(w * h * 3), np.uint8).reshape(h, w, 3) for _ in range(n)]
+
+
+@pytest.mark.skipif(not os.path.isfile(EDITOR), reason="oracle/_ref/lvk-editor is built where /root/reference exists "
+                                                       "(oracle/ref_build/build_lvk_editor.sh); it travels prebuilt")
+def test_reference_video_editor_unchanged_runs_config5_chain(tmp_path):
+    """The reference's OWN VideoEditor CLI - its sources compiled unchanged against lvk-compat and linked with
+    liblvkb200.so (tests/test_compat_cpu.py builds it; oracle/ref_build/build_lvk_editor.sh) - run the way BASELINE
+    config 5 is spelled on its command line: `lvk-editor in out -f adb .l 2 -f vs .s 6 .cp 0.08`.  Frames go
+    cv::VideoCapture -> CompositeFilter::stream -> {DeblockingFilter, StabilizationFilter} -> cv::VideoWriter (the
+    mock OpenCV's raw-clip container); the written clip must equal, byte for byte, what the Python mirror produces for
+    the same chain and settings through the same C-ABI."""
+    import livevisionkit_b200 as L
+    n = 30
+    src, dst = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    with open(src, "wb") as f:
+        f.write(b"LVKRAW1 %d %d %.6f %010d\n" % (640, 360, 30.0, n))
+        for i in range(n):
+            f.write(_frame(i).tobytes())
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "livevisionkit_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    run = subprocess.run([EDITOR, src, dst, "-f", "adb", ".l", "2", "-f", "vs", ".s", "6", ".cp", "0.08"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert run.returncode == 0, run.stderr[-2000:]
+    written = _read_raw_clip(dst)
+
+    deblocker = L.DeblockingFilter(L.DeblockingFilterSettings(detection_levels=2), device=0)
+    settings = L.StabilizationFilterSettings(predictive_samples=6, corrective_limits=(0.08, 0.08))
+    stabilizer = L.StabilizationFilter(settings, 0)
+    expected = []
+    for i in range(n):
+        v = stabilizer.apply(deblocker.apply(L.VideoFrame(_frame(i).copy(), i, L.BGR)))
+        if not v.empty():
+            expected.append(np.array(v.data, copy=True))
+    assert len(expected) == n - stabilizer.frame_delay() and len(written) == len(expected), (len(written), len(expected))
+    for k, (a, b) in enumerate(zip(written, expected)):
+        assert np.array_equal(a, b), f"output frame {k} differs from the Python mirror's"
