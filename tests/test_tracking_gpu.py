@@ -356,7 +356,8 @@ def test_local_motions_vs_oracle(gpu_stream, oracle, monkeypatch):
     s.close()
 
 
-@pytest.mark.parametrize("mesh", ["field16x16", "field16x16_round1_kernel", "default2x2_on_device"])
+@pytest.mark.parametrize("mesh", ["field16x16", "field16x16_round1_kernel", "field16x16_one_slot", "field24x24_two_slots",
+                                  "default2x2_on_device"])
 def test_local_motions_device_solver_vs_oracle(gpu_stream, oracle, mesh, monkeypatch):
     """K6c k_mesh_cgls2 / k_mesh_cgls (one CTA, whole LSCG solve in shared memory) against the sequential CPU restatement
     of Eigen's LeastSquaresConjugateGradient (oracle/lscg_ref.c): same iteration, different float32 summation order.
@@ -365,15 +366,24 @@ def test_local_motions_device_solver_vs_oracle(gpu_stream, oracle, mesh, monkeyp
     import livevisionkit_b200 as L
     if mesh == "field16x16_round1_kernel":
         monkeypatch.setenv("LVKB200_MESH_V1", "1")
-    if mesh.startswith("field16x16"):
+    n = 1100
+    if mesh.startswith("field"):
         sg, so = L.StabilizationFilterSettings.obs_field_preset(), oracle.StabilizationSettings.obs_field_preset()
+        # k_mesh_cgls2 is instantiated per (unknowns, similarity rows, features) a thread may own: the preset's capacity
+        # (1 856 features) takes <1,1,3>; a sparser detection grid (capacity 704) <1,1,1>; 1 152 unknowns <2,2,4>
+        if mesh == "field16x16_one_slot":
+            n = 700
+            for cfg in (sg, so):
+                cfg.max_feature_density, cfg.min_feature_density = 0.06, 0.03
+        elif mesh == "field24x24_two_slots":
+            for cfg in (sg, so):
+                cfg.motion_resolution = (24, 24)
     else:  # the library-default 2x2 mesh: on the device by default
         sg, so = L.StabilizationFilterSettings(), oracle.StabilizationSettings()
     w, h = so.detection_resolution
     mc, mr = so.motion_resolution
     s = L.Stream(sg, 0)
     rng = np.random.default_rng(11)
-    n = 1100
     p = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], axis=1).astype(np.float32)
     # a smooth non-rigid field (what the mesh is for) + noise + gross outliers
     flow = np.stack([1.5 + 2.0 * np.sin(p[:, 1] / h * 3.0), -0.8 + 1.5 * np.cos(p[:, 0] / w * 2.0)], axis=1)
