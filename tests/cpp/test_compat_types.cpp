@@ -2,6 +2,7 @@
 // lvk::Time / lvk::Stopwatch (Timing/Stopwatch.cpp:27-166), lvk::Unique (Utility/Unique.tpp), lvk::VideoFrame copy
 // semantics (reference-counted shallow copies like cv::UMat, Data/VideoFrame.cpp:37-44; clone() is deep).
 #include <cstdio>
+#include <string>
 
 #include "../../livevisionkit_b200/compat/lvk/lvk.hpp"
 
@@ -61,6 +62,40 @@ int main()
     CHECK(view.data == frame.data + frame.step + 3 && view.cols == 2 && view.step == frame.step);
     lvk::VideoFrame moved = std::move(frame);
     CHECK(frame.empty() && !moved.empty() && moved.data[7] == 11);
+    // lvk::TickTimer (Timing/TickTimer.cpp:30-66): a Stopwatch that counts its laps; tick(timestep) stretches the lap
+    lvk::TickTimer ticker(4);
+    CHECK(ticker.tick_count() == 0 && ticker.delta().is_zero());
+    ticker.start();
+    const Time lap = ticker.tick(Time::Microseconds(300.0));
+    CHECK(lap >= Time::Microseconds(300.0) && ticker.delta() == lap && ticker.tick_count() == 1 && ticker.is_running());
+    ticker.tick();
+    CHECK(ticker.tick_count() == 2 && ticker.history().size() == 2 && ticker.average() >= ticker.delta() / 2.0);
+    ticker.reset_counter();
+    CHECK(ticker.tick_count() == 0 && ticker.history().size() == 2);
+
+    // the assertion family (Directives.hpp:46-95): a failed check reports the violated relation and carries on
+    std::string reported;
+    const auto previous_handler = lvk::context::assert_handler;
+    lvk::context::assert_handler = [&](std::string, std::string, std::string assertion) { reported = assertion; };
+    const float ratio = 1.5f;
+    const int level = 7;
+    LVK_ASSERT_01(ratio);
+    CHECK(reported == "0 <= ratio <= 1");
+    LVK_ASSERT_01_STRICT(ratio);
+    CHECK(reported == "0 < ratio < 1");
+    LVK_ASSERT_RANGE(level, 1, 5);
+    CHECK(reported == "1 <= level <= 5");
+    LVK_ASSERT_RANGE_STRICT(level, 1, 7);
+    CHECK(reported == "1 < level < 7");
+    reported.clear();
+    LVK_ASSERT_IF(level > 10, ratio < 1.0f);  // the condition does not hold: nothing is checked
+    LVK_ASSERT_RANGE(level, 1, 7);
+    LVK_ASSERT_01(0.25f);
+    CHECK(reported.empty());
+    LVK_ASSERT_IF(level > 5, ratio < 1.0f);
+    CHECK(reported == "ratio < 1.0f");
+    lvk::context::assert_handler = previous_handler;
+
     std::printf("compat types ok\n");
     return 0;
 }
