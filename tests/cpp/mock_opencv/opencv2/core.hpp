@@ -21,20 +21,44 @@
 namespace cv
 {
 
-struct Point { int x = 0, y = 0; Point() = default; Point(int px, int py) : x(px), y(py) {}
-               Point operator+(const Point& o) const { return {x + o.x, y + o.y}; } };
-struct Size { int width = 0, height = 0; Size() = default; Size(int w, int h) : width(w), height(h) {}
-              bool operator==(const Size& o) const { return width == o.width && height == o.height; }
-              bool operator!=(const Size& o) const { return !(*this == o); } };
-struct Size2f { float width = 0, height = 0; Size2f() = default; Size2f(float w, float h) : width(w), height(h) {} };
+// geometry as in OpenCV: class templates with the usual aliases (the library's Functions/Drawing.hpp takes cv::Rect_<T>)
+template <typename T> struct Point_
+{
+    T x = 0, y = 0;
+    Point_() = default;
+    Point_(T px, T py) : x(px), y(py) {}
+    Point_ operator+(const Point_& o) const { return {static_cast<T>(x + o.x), static_cast<T>(y + o.y)}; }
+};
+template <typename T> struct Size_
+{
+    T width = 0, height = 0;
+    Size_() = default;
+    Size_(T w, T h) : width(w), height(h) {}
+    bool operator==(const Size_& o) const { return width == o.width && height == o.height; }
+    bool operator!=(const Size_& o) const { return !(*this == o); }
+};
+using Point = Point_<int>;
+using Point2f = Point_<float>;
+using Size = Size_<int>;
+using Size2f = Size_<float>;
 struct Scalar { double val[4] = {0, 0, 0, 0}; Scalar() = default;
                 Scalar(double a, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
                 double operator[](int i) const { return val[i]; } double& operator[](int i) { return val[i]; } };
-struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() = default;
-              Rect(int px, int py, int w, int h) : x(px), y(py), width(w), height(h) {}
-              Point tl() const { return {x, y}; } Point br() const { return {x + width, y + height}; } };
+template <typename T> struct Rect_
+{
+    T x = 0, y = 0, width = 0, height = 0;
+    Rect_() = default;
+    Rect_(T px, T py, T w, T h) : x(px), y(py), width(w), height(h) {}
+    Point_<T> tl() const { return {x, y}; }
+    Point_<T> br() const { return {static_cast<T>(x + width), static_cast<T>(y + height)}; }
+    Size_<T> size() const { return {width, height}; }
+};
+using Rect = Rect_<int>;
+using Rect2f = Rect_<float>;
 
 enum AccessFlag { ACCESS_READ = 1 << 24, ACCESS_WRITE = 1 << 25, ACCESS_RW = 3 << 24 };
+enum UMatUsageFlags { USAGE_DEFAULT = 0, USAGE_ALLOCATE_HOST_MEMORY = 1 << 0, USAGE_ALLOCATE_DEVICE_MEMORY = 1 << 1,
+                      USAGE_ALLOCATE_SHARED_MEMORY = 1 << 2 };
 
 struct Mat
 {
@@ -52,6 +76,7 @@ public:
     size_t step = 0;
 
     UMat() = default;
+    explicit UMat(UMatUsageFlags) {}  // (the mock has one kind of memory)
     UMat(int r, int c, int type) { create(r, c, type); }
     UMat(const UMat&) = default;             // reference-counted: copies share the pixels
     UMat(UMat&& o) noexcept { *this = std::move(o); }

@@ -185,3 +185,42 @@ def test_reference_video_editor_builds_unchanged_and_runs_its_loop(tmp_path):
         fail = subprocess.run([exe, str(tmp_path / "in.raw"), str(tmp_path / "out2.raw"), "-f", "vs"], capture_output=True,
                               text=True, env=env, timeout=60)
         assert fail.returncode != 0 and "no CPU fallback" in fail.stderr, fail.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_obs_plugin_filter_sources_compile_unchanged(tmp_path):
+    """The OBS plugin's stabilization and deblocking filters as WHOLE translation units: Sources/Stabilisation/VSFilter.cpp +
+    VSSource.cpp and Sources/Enhancement/ADBFilter.cpp + ADBSource.cpp, compiled in place and unchanged (-std=c++20
+    -Werror) together with the plugin's own headers they include (Interop/VisionFilter.hpp, OBSFrame.hpp, FrameIngest.hpp,
+    Utility/OBSDispatch.tpp, Logging.tpp, Effects/OBSEffect.tpp ...).  `#include <LiveVisionKit.hpp>` resolves to
+    lvk-compat; libobs and OpenCV are mocks (tests/cpp/mock_obs, tests/cpp/mock_opencv); the library's debug-HUD drawing
+    helpers are inert stubs.  OBSDispatch instantiates filter_create_auto / filter_process / filter_configure with the
+    filter classes, so construction, configure() and filter() are all compiled against the boundary; the resulting
+    objects' undefined symbols show where the plugin's frame path lands: on the C-ABI."""
+    plugin = os.path.join(REF, "Modules", "OBS-Plugin")
+    inc = tmp_path / "inc"
+    inc.mkdir()
+    (inc / "LiveVisionKit.hpp").write_text(
+        '#pragma once\n#define LVK_COMPAT_USE_OPENCV\n#include <opencv2/opencv.hpp>\n#include <opencv2/core/ocl.hpp>\n'
+        '#include "%s"\n#include "%s"\n' % (os.path.join(ROOT, "livevisionkit_b200", "compat", "lvk", "lvk.hpp"),
+                                            os.path.join(ROOT, "tests", "cpp", "mock_obs", "lvk_debug_hud_stubs.hpp")))
+    (inc / "Directives.hpp").write_text('#pragma once\n#include "%s"\n'
+                                        % os.path.join(ROOT, "livevisionkit_b200", "compat", "lvk", "lvk.hpp"))
+    flags = ["-std=c++20", "-Werror", "-O0", "-c", f"-I{inc}", "-I" + os.path.join(ROOT, "tests", "cpp", "mock_obs"),
+             "-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv"), f"-I{plugin}"]
+    objects = {}
+    for src in ("Sources/Stabilisation/VSFilter.cpp", "Sources/Stabilisation/VSSource.cpp",
+                "Sources/Enhancement/ADBFilter.cpp", "Sources/Enhancement/ADBSource.cpp"):
+        obj = str(tmp_path / (os.path.basename(src)[:-4] + ".o"))
+        out = subprocess.run(["g++", *flags, os.path.join(plugin, src), "-o", obj], capture_output=True, text=True)
+        assert out.returncode == 0, src + "\n" + out.stderr[-4000:]
+        objects[os.path.basename(src)] = subprocess.run(["nm", "-u", "-C", obj], capture_output=True, text=True).stdout
+    for symbol in ("lvkb200_stream_create", "lvkb200_stream_configure", "lvkb200_stream_submit", "lvkb200_stream_frame_delay",
+                   "lvkb200_stream_stable_region"):
+        assert symbol in objects["VSFilter.cpp"], symbol
+    assert "lvkb200_deblock" in objects["ADBFilter.cpp"]
+    # the registration units instantiated the dispatch templates with the filter classes
+    for symbol in ("lvk::VSFilter::VSFilter(obs_source*)", "lvk::VSFilter::configure(obs_data*)",
+                   "lvk::VisionFilter::process(obs_source_frame*)"):
+        assert symbol in objects["VSSource.cpp"], symbol
+    assert "lvk::ADBFilter::ADBFilter(obs_source*)" in objects["ADBSource.cpp"]
